@@ -1,0 +1,193 @@
+/*
+ * slicednb.h -- C-ABI of the B200-native SlicedNonbondedForce kernel core.
+ *
+ * This is the drop-in boundary.  A platform plugin that implements
+ * OpenMMLab::CalcSlicedNonbondedForceKernel
+ * (reference: openmmapi/include/OpenMMLabKernels.h:29-87) forwards each of its
+ * virtual methods to one entry point below:
+ *
+ *   initialize(system, force)            -> snb_create          (OpenMMLabKernels.h:50)
+ *   execute(context, f, e, direct, recip)-> snb_execute         (OpenMMLabKernels.h:61)
+ *   copyParametersToContext(ctx, force)  -> snb_update_parameters (OpenMMLabKernels.h:68)
+ *   getPMEParameters(alpha,nx,ny,nz)     -> snb_get_pme_parameters   (OpenMMLabKernels.h:77)
+ *   getLJPMEParameters(alpha,nx,ny,nz)   -> snb_get_ljpme_parameters (OpenMMLabKernels.h:86)
+ *   ~KernelImpl                          -> snb_destroy
+ *
+ * The descriptor `snb_desc` is a flat snapshot of everything
+ * ReferenceCalcSlicedNonbondedForceKernel::initialize reads from the
+ * SlicedNonbondedForce and the System
+ * (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:65-191).
+ *
+ * Plain pointers and sizes only; no C++ or torch types; no exception crosses
+ * this boundary (status codes + snb_last_error()).
+ *
+ * The SAME descriptor and execute signature are implemented by the CPU oracle
+ * (oracle/, test infrastructure only) under the prefix snb_oracle_*, so parity
+ * tests feed both sides byte-identical inputs.
+ */
+#ifndef SLICEDNB_H_
+#define SLICEDNB_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* NonbondedMethod, same values as CalcSlicedNonbondedForceKernel::NonbondedMethod
+ * (openmmapi/include/OpenMMLabKernels.h:31-38). */
+enum {
+    SNB_NO_CUTOFF = 0,
+    SNB_CUTOFF_NON_PERIODIC = 1,
+    SNB_CUTOFF_PERIODIC = 2,
+    SNB_EWALD = 3,
+    SNB_PME = 4,
+    SNB_LJPME = 5
+};
+
+/* execute() flags = the four bools of CalcSlicedNonbondedForceKernel::execute
+ * (openmmapi/include/OpenMMLabKernels.h:61). */
+enum {
+    SNB_INCLUDE_FORCES = 1,
+    SNB_INCLUDE_ENERGY = 2,
+    SNB_INCLUDE_DIRECT = 4,
+    SNB_INCLUDE_RECIPROCAL = 8,
+    SNB_EXECUTE_ALL = 15
+};
+
+/* status codes */
+enum {
+    SNB_OK = 0,
+    SNB_ERR_INVALID = 1,        /* bad descriptor / argument                         */
+    SNB_ERR_BOX_TOO_SMALL = 2,  /* ReferenceOpenMMLabKernels.cpp:208-210             */
+    SNB_ERR_PARTICLE_COUNT = 3, /* ReferenceOpenMMLabKernels.cpp:264-265             */
+    SNB_ERR_EXCEPTION_SET = 4,  /* ReferenceOpenMMLabKernels.cpp:290-291             */
+    SNB_ERR_WRONG_METHOD = 5,   /* ReferenceOpenMMLabKernels.cpp:315-316,324-325     */
+    SNB_ERR_CUDA = 6,           /* CUDA / cuFFT / NCCL failure                        */
+    SNB_ERR_UNSUPPORTED = 7
+};
+
+/* creation flags (product only; ignored by the oracle) */
+enum {
+    SNB_FLAG_DETERMINISTIC = 1  /* reserved: forces are always accumulated in 64-bit fixed point */
+};
+
+typedef struct snb_desc {
+    int32_t struct_size;               /* = sizeof(snb_desc); guards against ABI drift */
+    int32_t num_particles;
+    int32_t num_subsets;               /* SlicedNonbondedForce::getNumSubsets          */
+    int32_t method;                    /* SNB_NO_CUTOFF .. SNB_LJPME                    */
+    double  cutoff;                    /* getCutoffDistance (nm)                        */
+    int32_t use_switching_function;
+    int32_t use_dispersion_correction;
+    double  switching_distance;
+    double  reaction_field_dielectric;
+    int32_t exceptions_use_pbc;        /* getExceptionsUsePeriodicBoundaryConditions    */
+    int32_t flags;                     /* SNB_FLAG_*                                    */
+    double  ewald_error_tolerance;     /* used only when an alpha below is 0            */
+    double  default_box[9];            /* System default periodic box, rows a,b,c       */
+    double  ewald_alpha;               /* getPMEParameters; 0 => derive from tolerance  */
+    int32_t pme_grid[3];
+    int32_t device_index;              /* CUDA device of this handle                    */
+    double  dispersion_alpha;          /* getLJPMEParameters; 0 => derive               */
+    int32_t dispersion_grid[3];
+    int32_t reserved0;
+
+    const double*  charge;             /* [N] base particle parameters                  */
+    const double*  sigma;              /* [N]                                           */
+    const double*  epsilon;            /* [N]                                           */
+    const int32_t* subset;             /* [N] getParticleSubset                         */
+
+    int32_t num_exceptions;
+    int32_t num_global_parameters;
+    const int32_t* exception_particles;/* [X][2]                                        */
+    const double*  exception_params;   /* [X][3] chargeProd, sigma, epsilon             */
+
+    const double*  global_parameter_defaults; /* [G]                                    */
+
+    int32_t num_particle_offsets;
+    int32_t num_exception_offsets;
+    const int32_t* particle_offset_index;  /* [P][2] global parameter, particle         */
+    const double*  particle_offset_scale;  /* [P][3] chargeScale, sigmaScale, epsScale  */
+    const int32_t* exception_offset_index; /* [E][2] global parameter, exception        */
+    const double*  exception_offset_scale; /* [E][3]                                    */
+
+    int32_t num_scaling_parameters;
+    int32_t num_derivatives;
+    const int32_t* scaling_parameters; /* [K][5] globalParam, subset1, subset2, includeCoulomb, includeLJ */
+    const int32_t* derivative_parameters; /* [D] global-parameter index of each requested derivative      */
+} snb_desc;
+
+typedef struct snb_handle snb_handle;
+
+/* slice index of a subset pair: SlicedNonbondedForce.h:22 */
+static inline int snb_slice_index(int i, int j) { return i > j ? i*(i+1)/2 + j : j*(j+1)/2 + i; }
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+/* initialize(): ReferenceOpenMMLabKernels.cpp:65-191 / CudaOpenMMLabKernels.cpp:254-886.
+ * Copies everything it needs; `desc` and its arrays may be freed on return. */
+int snb_create(const snb_desc* desc, snb_handle** out);
+void snb_destroy(snb_handle* h);
+
+/* copyParametersToContext(): ReferenceOpenMMLabKernels.cpp:263-312.
+ * Particle count and the set of non-excluded exceptions must be unchanged. */
+int snb_update_parameters(snb_handle* h, const snb_desc* desc);
+
+/* ---- evaluation ---------------------------------------------------------- */
+
+/* execute(): ReferenceOpenMMLabKernels.cpp:193-261.
+ *   positions          [N][3] nm, host memory
+ *   box                [9] rows a,b,c of the reduced triclinic box (ignored for non-periodic methods)
+ *   global_parameters  [G] current Context parameter values (context.getParameter)
+ *   flags              SNB_INCLUDE_*
+ *   forces             [N][3] kJ/mol/nm, host; ADDED to (may be NULL when !FORCES)
+ *   energy             out: sum_{slice,term} lambda*E  (0 if !ENERGY)
+ *   slice_energies     [L][2] (Coulomb, vdW) raw slice energies, overwritten; may be NULL
+ *   derivatives        [D] ADDED to, regardless of ENERGY (reference :252-258); may be NULL iff D==0
+ */
+int snb_execute(snb_handle* h, const double* positions, const double* box,
+                const double* global_parameters, int flags,
+                double* forces, double* energy, double* slice_energies, double* derivatives);
+
+/* Same evaluation with inputs/outputs resident in device memory (no host copies):
+ *   posq_dev    [N] float4 (x,y,z,unused) in ORIGINAL particle order
+ *   forces_dev  [3][N] long long, 2^32 fixed point, component-major; ADDED to; may be 0
+ * Energies/derivatives are read back with snb_read_energies (one small D2H). */
+int snb_execute_device(snb_handle* h, const void* posq_dev, const double* box,
+                       const double* global_parameters, int flags, void* forces_dev);
+int snb_read_energies(snb_handle* h, int flags, double* energy, double* slice_energies,
+                      double* derivatives);
+
+int snb_get_pme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz);
+int snb_get_ljpme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz);
+
+/* ---- multi-GPU (tile list partitioned across ranks; reciprocal on rank 0) -- */
+int snb_nccl_unique_id(void* id128);             /* fills a 128-byte ncclUniqueId       */
+int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size);
+
+/* ---- introspection for tests and benches --------------------------------- */
+
+/* Sorted list of interacting pairs (i<j, lexicographic) found by the device
+ * neighbour search of the LAST execute; *pairs is malloc'ed, caller frees
+ * with snb_free. */
+int snb_dump_pairs(snb_handle* h, int32_t** pairs, int64_t* num_pairs);
+void snb_free(void* p);
+
+/* per-phase device times (ms) of the last execute, when timing is enabled */
+enum { SNB_PHASE_SORT = 0, SNB_PHASE_LIST, SNB_PHASE_DIRECT, SNB_PHASE_BONDED,
+       SNB_PHASE_SPREAD, SNB_PHASE_FFT, SNB_PHASE_CONV, SNB_PHASE_INTERP,
+       SNB_PHASE_REDUCE, SNB_PHASE_TOTAL, SNB_NUM_PHASES };
+int snb_set_timing(snb_handle* h, int enabled);
+int snb_get_phase_times(snb_handle* h, float* ms /*[SNB_NUM_PHASES]*/);
+/* counters of the last execute: [0]=interacting pairs, [1]=tile entries, [2]=kernel launches */
+int snb_get_counters(snb_handle* h, int64_t* out /*[8]*/);
+
+const char* snb_last_error(void);
+const char* snb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLICEDNB_H_ */

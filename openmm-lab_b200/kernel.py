@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference's kernel interface for this path.
+
+``CalcSlicedNonbondedForceKernel`` has the five methods of the reference's abstract
+class (openmmapi/include/OpenMMLabKernels.h:29-87) -- ``initialize``, ``execute``,
+``copyParametersToContext``, ``getPMEParameters``, ``getLJPMEParameters`` -- each a
+thin forward to one C-ABI entry point of include/slicednb.h.  The B200 kernel class
+below binds them to the CUDA library built from csrc/; it has NO CPU fallback and
+raises at import of the library if the extension is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import PackedDesc, SnbDesc, SnbError
+
+_dp = C.POINTER(C.c_double)
+
+
+class CalcSlicedNonbondedForceKernel:
+    """Binds the kernel interface to a C library exporting ``<prefix>create`` etc."""
+
+    NoCutoff, CutoffNonPeriodic, CutoffPeriodic, Ewald, PME, LJPME = range(6)
+
+    @staticmethod
+    def Name():
+        return "CalcSlicedNonbondedForce"
+
+    def __init__(self, lib, prefix, device_index=0):
+        self._lib = lib
+        self._prefix = prefix
+        self._handle = C.c_void_p()
+        self._device_index = device_index
+        self._packed = None
+
+    def _fn(self, name):
+        return getattr(self._lib, self._prefix+name)
+
+    def _check(self, status):
+        if status != _abi.OK:
+            err = self._fn("last_error")
+            err.restype = C.c_char_p
+            raise SnbError(status, err().decode())
+
+    # initialize(system, force) -- OpenMMLabKernels.h:50
+    def initialize(self, system, force):
+        self.destroy()
+        box = system.getDefaultPeriodicBoxVectors()
+        self._packed = PackedDesc(force, np.asarray(box, dtype=np.float64), self._device_index)
+        create = self._fn("create")
+        create.argtypes = [C.POINTER(SnbDesc), C.POINTER(C.c_void_p)]
+        self._check(create(C.byref(self._packed.desc), C.byref(self._handle)))
+        self.numParticles = force.getNumParticles()
+        self.numSlices = force.getNumSlices()
+        self.globalNames = self._packed.global_names
+        self.derivativeNames = self._packed.derivative_names
+        self.sliceEnergies = np.zeros((self.numSlices, 2))
+
+    # execute(context, includeForces, includeEnergy, includeDirect, includeReciprocal) -- OpenMMLabKernels.h:61
+    def execute(self, context, includeForces, includeEnergy, includeDirect, includeReciprocal):
+        flags = (_abi.INCLUDE_FORCES if includeForces else 0) | (_abi.INCLUDE_ENERGY if includeEnergy else 0) | \
+                (_abi.INCLUDE_DIRECT if includeDirect else 0) | (_abi.INCLUDE_RECIPROCAL if includeReciprocal else 0)
+        pos = np.ascontiguousarray(context._positions, dtype=np.float64)
+        box = np.ascontiguousarray(context._box, dtype=np.float64).reshape(9)
+        params = np.array([context.getParameter(n) for n in self.globalNames], dtype=np.float64)
+        derivs = np.zeros(max(1, len(self.derivativeNames)))
+        energy = C.c_double(0.0)
+        fn = self._fn("execute")
+        fn.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, _dp, C.POINTER(C.c_double), _dp, _dp]
+        forces = context._forces
+        self._check(fn(self._handle, pos.ctypes.data_as(_dp), box.ctypes.data_as(_dp), params.ctypes.data_as(_dp), flags,
+                       forces.ctypes.data_as(_dp) if includeForces else None, C.byref(energy),
+                       self.sliceEnergies.ctypes.data_as(_dp), derivs.ctypes.data_as(_dp)))
+        for k, name in enumerate(self.derivativeNames):
+            context._energyParameterDerivatives[name] = context._energyParameterDerivatives.get(name, 0.0)+derivs[k]
+        return energy.value
+
+    # copyParametersToContext(context, force) -- OpenMMLabKernels.h:68
+    def copyParametersToContext(self, context, force):
+        packed = PackedDesc(force, np.asarray(context._system.getDefaultPeriodicBoxVectors(), dtype=np.float64), self._device_index)
+        fn = self._fn("update_parameters")
+        fn.argtypes = [C.c_void_p, C.POINTER(SnbDesc)]
+        self._check(fn(self._handle, C.byref(packed.desc)))
+        self._packed = packed
+
+    def _pme(self, name):
+        alpha, nx, ny, nz = C.c_double(), C.c_int(), C.c_int(), C.c_int()
+        fn = self._fn(name)
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self._check(fn(self._handle, C.byref(alpha), C.byref(nx), C.byref(ny), C.byref(nz)))
+        return alpha.value, nx.value, ny.value, nz.value
+
+    # getPMEParameters / getLJPMEParameters -- OpenMMLabKernels.h:77,86
+    def getPMEParameters(self):
+        return self._pme("get_pme_parameters")
+
+    def getLJPMEParameters(self):
+        return self._pme("get_ljpme_parameters")
+
+    def dumpPairs(self):
+        """Sorted (i<j) interacting pairs of the last execute (test introspection)."""
+        ptr, count = C.POINTER(C.c_int32)(), C.c_int64()
+        fn = self._fn("dump_pairs")
+        fn.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int64)]
+        self._check(fn(self._handle, C.byref(ptr), C.byref(count)))
+        out = np.ctypeslib.as_array(ptr, shape=(max(count.value, 1), 2))[:count.value].copy()
+        free = self._fn("free")
+        free.argtypes = [C.c_void_p]
+        free(ptr)
+        return out
+
+    def destroy(self):
+        if self._handle:
+            fn = self._fn("destroy")
+            fn.argtypes = [C.c_void_p]
+            fn.restype = None
+            fn(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libslicednb_b200.so")
+
+
+def load_library():
+    """Load the CUDA core.  Fails loudly: there is no CPU or PyTorch fallback for this path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `python __graft_entry__.py build` "
+                              "(nvcc, sm_100a); this path has no CPU fallback" % LIB_PATH)
+        _LIB = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    return _LIB
+
+
+class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
+    """The sm_100a implementation, registered on platform "B200" (platform.py)."""
+
+    def __init__(self, device_index=0):
+        super().__init__(load_library(), "snb_", device_index)
+
+    def executeDevice(self, posq_ptr, box, params, flags, forces_ptr):
+        fn = self._lib.snb_execute_device
+        fn.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, C.c_int, C.c_void_p]
+        box = np.ascontiguousarray(box, dtype=np.float64).reshape(9)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(fn(self._handle, posq_ptr, box.ctypes.data_as(_dp), params.ctypes.data_as(_dp), flags, forces_ptr))
+
+    def readEnergies(self, flags):
+        fn = self._lib.snb_read_energies
+        fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), _dp, _dp]
+        derivs = np.zeros(max(1, len(self.derivativeNames)))
+        energy = C.c_double()
+        self._check(fn(self._handle, flags, C.byref(energy), self.sliceEnergies.ctypes.data_as(_dp), derivs.ctypes.data_as(_dp)))
+        return energy.value, self.sliceEnergies.copy(), derivs[:len(self.derivativeNames)].copy()
+
+    def setTiming(self, enabled):
+        self._check(self._lib.snb_set_timing(self._handle, int(enabled)))
+
+    def getPhaseTimes(self):
+        ms = (C.c_float*len(_abi.PHASES))()
+        self._check(self._lib.snb_get_phase_times(self._handle, ms))
+        return dict(zip(_abi.PHASES, list(ms)))
+
+    def getCounters(self):
+        out = (C.c_int64*8)()
+        self._check(self._lib.snb_get_counters(self._handle, out))
+        return list(out)
+
+    def commInit(self, unique_id, rank, world_size):
+        fn = self._lib.snb_comm_init
+        fn.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        self._check(fn(self._handle, unique_id, rank, world_size))
