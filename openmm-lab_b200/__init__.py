@@ -10,6 +10,7 @@ from .context import Context, Platform, State, System
 from .force import OpenMMException, SlicedNonbondedForce
 from .kernel import B200CalcSlicedNonbondedForceKernel, CalcSlicedNonbondedForceKernel, load_library
 from .platform import registerKernelFactories, registerPlatforms
+from . import systems
 
 registerKernelFactories()
 

@@ -1,0 +1,976 @@
+// C-ABI of the B200 SlicedNonbondedForce core (include/slicednb.h) and the host-side
+// orchestration of one evaluation.  Host logic restated from the reference kernel glue:
+//   initialize               platforms/reference/src/ReferenceOpenMMLabKernels.cpp:65-191
+//   execute                  :193-261        computeParameters :332-385
+//   copyParametersToContext  :263-312        get(LJ)PMEParameters :314-330
+//   calcDispersionCorrections openmmapi/src/SlicedNonbondedForceImpl.cpp:263-354 (in 64-bit/double;
+//                            the reference overflows `int` for N > 16383, :346,351)
+// Scheduling differs from the reference's CUDA platform (CudaOpenMMLabKernels.cpp:888-1112) by
+// design: one stream-ordered sequence with no host synchronisation until the final read-back.
+#include "kernels.cuh"
+
+#include <cufft.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_lastError;
+
+struct SnbException : public std::exception {
+    int code;
+    std::string msg;
+    SnbException(int code, const std::string& msg) : code(code), msg(msg) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+
+#define CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    throw SnbException(SNB_ERR_CUDA, std::string(#call)+": "+cudaGetErrorString(e_)); } while (0)
+#define CUFFT_CHECK(call) do { cufftResult r_ = (call); if (r_ != CUFFT_SUCCESS) \
+    throw SnbException(SNB_ERR_CUDA, std::string(#call)+": cuFFT error "+std::to_string((int) r_)); } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        if (count <= n && p) return;
+        release();
+        CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1)*sizeof(T)));
+        n = std::max<size_t>(count, 1);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void upload(const T* src, size_t count, cudaStream_t s) {
+        alloc(count);
+        if (count) CUDA_CHECK(cudaMemcpyAsync(p, src, count*sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    ~DevBuf() { release(); }
+};
+template <typename T> struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        if (count <= n && p) return;
+        if (p) cudaFreeHost(p);
+        CUDA_CHECK(cudaMallocHost(&p, std::max<size_t>(count, 1)*sizeof(T)));
+        n = std::max<size_t>(count, 1);
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+double evalIntegral(double r, double rs, double rc, double sigma) {
+    // SlicedNonbondedForceImpl.cpp:150-185
+    double A = 1/(rc-rs), A2 = A*A, A3 = A2*A;
+    double sig2 = sigma*sigma, sig6 = sig2*sig2*sig2;
+    double rs2 = rs*rs, rs3 = rs*rs2;
+    double r2 = r*r, r3 = r*r2, r4 = r*r3, r5 = r*r4, r6 = r*r5, r9 = r3*r6;
+    return sig6*A3*((
+        sig6*(rs3*28*(6*rs2*A2+15*rs*A+10)-r*rs2*945*(rs2*A2+2*rs*A+1)+r2*rs*1080*(2*rs2*A2+3*rs*A+1)
+              -r3*420*(6*rs2*A2+6*rs*A+1)+r4*756*(2*rs*A2+A)-r5*378*A2)
+        -r6*(rs3*84*(6*rs2*A2+15*rs*A+10)-r*rs2*3780*(rs2*A2+2*rs*A+1)+r2*rs*7560*(2*rs2*A2+3*rs*A+1))
+        )/(252*r9)-log(r)*10*(6*rs2*A2+6*rs*A+1)+r*15*(2*rs*A2+A)-r2*3*A2);
+}
+
+uint64_t hilbertIndex(uint32_t x, uint32_t y, uint32_t z, int bits) {
+    // Skilling's transpose form of the 3-D Hilbert curve
+    uint32_t X[3] = {x, y, z};
+    uint32_t M = 1u<<(bits-1), t;
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        uint32_t P = Q-1;
+        for (int i = 0; i < 3; i++) {
+            if (X[i]&Q) X[0] ^= P;
+            else { t = (X[0]^X[i])&P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    for (int i = 1; i < 3; i++) X[i] ^= X[i-1];
+    t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2]&Q) t ^= Q-1;
+    for (int i = 0; i < 3; i++) X[i] ^= t;
+    uint64_t h = 0;
+    for (int b = bits-1; b >= 0; b--)
+        for (int i = 0; i < 3; i++)
+            h = (h<<1)|((X[i]>>b)&1u);
+    return h;
+}
+
+std::vector<double> bsplineModuli(int n) {
+    // ReferencePME.cpp:88-183: |DFT of the integer-sampled order-5 spline|^2 with the <1e-7 fix-up
+    const int order = SNB_PME_ORDER;
+    double data[SNB_PME_ORDER];
+    data[order-1] = 0; data[1] = 0; data[0] = 1;
+    for (int k = 3; k < order; k++) {
+        double div = 1.0/(k-1.0);
+        data[k-1] = 0;
+        for (int l = 1; l < k-1; l++)
+            data[k-l-1] = div*(l*data[k-l-2]+(k-l)*data[k-l-1]);
+        data[0] = div*data[0];
+    }
+    double div = 1.0/(order-1);
+    data[order-1] = 0;
+    for (int l = 1; l < order-1; l++)
+        data[order-l-1] = div*(l*data[order-l-2]+(order-l)*data[order-l-1]);
+    data[0] = div*data[0];
+    std::vector<double> bs(std::max(n, order+1), 0.0), mod(n);
+    for (int i = 1; i <= order; i++) bs[i] = data[i-1];
+    for (int i = 0; i < n; i++) {
+        double sc = 0, ss = 0;
+        for (int j = 0; j < n; j++) {
+            double arg = (2.0*M_PI*i*j)/n;
+            sc += bs[j]*cos(arg);
+            ss += bs[j]*sin(arg);
+        }
+        mod[i] = sc*sc+ss*ss;
+    }
+    for (int i = 0; i < n; i++)
+        if (mod[i] < 1.0e-7)
+            mod[i] = (mod[(i-1+n)%n]+mod[(i+1)%n])/2;
+    return mod;
+}
+
+struct PmeGrid {
+    int n[3] = {0, 0, 0};
+    double alpha = 0;
+    cufftHandle fwd = 0, inv = 0;
+    bool planned = false;
+    DevBuf<float> real;
+    DevBuf<float2> cplx;
+    DevBuf<float> eterm;
+    DevBuf<double> moduli[3];
+    double etermBox[6] = {0, 0, 0, 0, 0, 0};
+    bool etermValid = false;
+    ~PmeGrid() { if (planned) { cufftDestroy(fwd); cufftDestroy(inv); } }
+};
+
+}  // namespace
+
+struct snb_handle {
+    // ---- snapshot of the force (ReferenceOpenMMLabKernels.cpp:65-191) ----
+    int N = 0, NP = 0, NB = 0, S = 1, L = 1, G = 0, method = 0, device = 0;
+    double cutoff = 1, switchDist = 0, rfDielectric = 78.3, alpha = 0, dalpha = 0;
+    bool useSwitch = false, exceptionsPeriodic = false, useDispersion = false;
+    int grid[3] = {0, 0, 0}, dgrid[3] = {0, 0, 0};
+    std::vector<int> subsets;
+    std::vector<std::array<double, 3>> baseParticle;          // q, sigma, eps
+    int X = 0, num14 = 0;
+    std::vector<int2> exceptionAtoms;
+    std::vector<std::array<double, 3>> baseException;         // chargeProd, sigma, eps
+    std::vector<int> is14;
+    std::vector<std::array<int, 2>> particleOffsetIdx, exceptionOffsetIdx;   // (param, index)
+    std::vector<std::array<double, 3>> particleOffsetScale, exceptionOffsetScale;
+    std::vector<std::array<int, 2>> sliceParam;                // [L] (Coul, vdW) global index or -1
+    std::vector<std::array<bool, 2>> sliceHasDeriv;
+    std::vector<int> derivativeParams;
+    std::vector<double> dispersionCoef;
+    std::set<int> offsetParams;
+    // ---- derived host state ----
+    bool paramsDirty = true;
+    std::vector<double> lastOffsetValues;
+    std::vector<double> selfC, selfV;                          // per subset
+    double lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
+    int cellDim[3] = {0, 0, 0}, numCells = 0;
+    int pbcModeOverride = -1;
+    // ---- device state ----
+    cudaStream_t stream = nullptr;
+    int numSMs = 148;
+    DevBuf<double> posd, paramsD, exception14, blockCenter, extent, energyBuf, forcesOutD;
+    DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn;
+    DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
+                exclStart, exclList, is14D, counters;
+    DevBuf<int2> exceptionAtomsD, jList;
+    DevBuf<int4> workItems;
+    DevBuf<long long> forceSorted, forceOrig;
+    PinnedBuf<double> hPos, hForces, hEnergy;
+    PinnedBuf<int> hCounters;
+    size_t maxChunks = 0, maxItems = 0;
+    PmeGrid pme, dpme;
+    // ---- results of the last execute ----
+    std::vector<double> sliceEnergies;
+    double lastEnergy = 0;
+    std::vector<double> lastGlobals;
+    int lastFlags = 0;
+    bool listValid = false;
+    DirectArgs lastDirect;
+    bool timing = false;
+    cudaEvent_t ev[SNB_NUM_PHASES+2];
+    bool evCreated = false;
+    float phaseMs[SNB_NUM_PHASES];
+    long long countersOut[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+void validateDesc(const snb_desc& d) {
+    if (d.struct_size != (int32_t) sizeof(snb_desc))
+        throw SnbException(SNB_ERR_INVALID, "snb_desc.struct_size does not match this library");
+    if (d.num_particles < 0 || d.num_subsets < 1)
+        throw SnbException(SNB_ERR_INVALID, "bad particle or subset count");
+    if (d.num_subsets > SNB_MAX_SUBSETS)
+        throw SnbException(SNB_ERR_UNSUPPORTED, "more than 8 subsets are not supported by this build");
+    if (d.method < SNB_NO_CUTOFF || d.method > SNB_LJPME)
+        throw SnbException(SNB_ERR_INVALID, "unknown nonbonded method");
+    if (d.method == SNB_EWALD)
+        throw SnbException(SNB_ERR_UNSUPPORTED, "classic Ewald summation is not implemented on the B200 platform; use PME");
+    for (int i = 0; i < d.num_particles; i++)
+        if (d.subset[i] < 0 || d.subset[i] >= d.num_subsets)
+            throw SnbException(SNB_ERR_INVALID, "particle subset out of range");
+}
+
+std::vector<int> find14s(const snb_desc& d) {
+    std::set<int> withOffsets;
+    for (int k = 0; k < d.num_exception_offsets; k++)
+        withOffsets.insert(d.exception_offset_index[2*k+1]);
+    std::vector<int> is14(d.num_exceptions, 0);
+    for (int i = 0; i < d.num_exceptions; i++) {
+        double qq = d.exception_params[3*i], eps = d.exception_params[3*i+2];
+        if (qq != 0.0 || eps != 0.0 || withOffsets.count(i))
+            is14[i] = 1;
+    }
+    return is14;
+}
+
+std::vector<double> calcDispersionCorrections(const snb_desc& d) {
+    int L = d.num_subsets*(d.num_subsets+1)/2;
+    std::vector<double> out(L, 0.0);
+    if (d.method == SNB_NO_CUTOFF || d.method == SNB_CUTOFF_NON_PERIODIC)
+        return out;
+    int n = d.num_particles;
+    std::vector<double> sigma(d.sigma, d.sigma+n), epsilon(d.epsilon, d.epsilon+n);
+    for (int k = 0; k < d.num_particle_offsets; k++) {
+        int p = d.particle_offset_index[2*k], idx = d.particle_offset_index[2*k+1];
+        double v = d.global_parameter_defaults[p];
+        sigma[idx] += v*d.particle_offset_scale[3*k+1];
+        epsilon[idx] += v*d.particle_offset_scale[3*k+2];
+    }
+    typedef std::tuple<double, double, int> ParticleClass;
+    std::map<ParticleClass, long long> classCounts;
+    for (int i = 0; i < n; i++)
+        classCounts[std::make_tuple(sigma[i], epsilon[i], d.subset[i])]++;
+    std::vector<double> sum1(L, 0), sum2(L, 0), sum3(L, 0);
+    bool useSwitch = d.use_switching_function;
+    double rc = d.cutoff, rs = d.switching_distance;
+    auto add = [&](int slice, double count, double sig, double eps) {
+        double s2 = sig*sig, s6 = s2*s2*s2;
+        sum1[slice] += count*eps*s6*s6;
+        sum2[slice] += count*eps*s6;
+        if (useSwitch)
+            sum3[slice] += count*eps*(evalIntegral(rc, rs, rc, sig)-evalIntegral(rs, rs, rc, sig));
+    };
+    for (auto& c : classCounts) {
+        int sub = std::get<2>(c.first);
+        add(sub*(sub+3)/2, (double) (c.second*(c.second+1)/2), std::get<0>(c.first), std::get<1>(c.first));
+    }
+    for (auto c1 = classCounts.begin(); c1 != classCounts.end(); ++c1)
+        for (auto c2 = classCounts.begin(); c2 != c1; ++c2)
+            add(snb_slice_index(std::get<2>(c1->first), std::get<2>(c2->first)), (double) c1->second*(double) c2->second,
+                0.5*(std::get<0>(c1->first)+std::get<0>(c2->first)), sqrt(std::get<1>(c1->first)*std::get<1>(c2->first)));
+    double np = n, numInteractions = (double) (((long long) n*((long long) n+1))/2);
+    for (int s = 0; s < L; s++)
+        out[s] = 8*np*np*M_PI*(sum1[s]/numInteractions/(9*pow(rc, 9))-sum2[s]/numInteractions/(3*pow(rc, 3))+sum3[s]/numInteractions);
+    return out;
+}
+
+void calcPMEParameters(const snb_desc& d, bool lj, double& alpha, int grid[3]) {
+    // OpenMM NonbondedForceImpl::calcPMEParameters (third party; call sites ReferenceOpenMMLabKernels.cpp:171,176,178)
+    alpha = lj ? d.dispersion_alpha : d.ewald_alpha;
+    const int32_t* g = lj ? d.dispersion_grid : d.pme_grid;
+    grid[0] = g[0]; grid[1] = g[1]; grid[2] = g[2];
+    if (alpha == 0.0) {
+        double tol = d.ewald_error_tolerance;
+        alpha = (1.0/d.cutoff)*std::sqrt(-log(2.0*tol));
+        for (int k = 0; k < 3; k++) {
+            double len = d.default_box[4*k];
+            int n = lj ? (int) ceil(alpha*len/(3*pow(tol, 0.2))) : (int) ceil(2*alpha*len/(3*pow(tol, 0.2)));
+            grid[k] = std::max(n, 6);
+        }
+    }
+}
+
+void loadParameters(snb_handle& h, const snb_desc& d) {
+    h.subsets.assign(d.subset, d.subset+d.num_particles);
+    h.baseParticle.resize(h.N);
+    for (int i = 0; i < h.N; i++)
+        h.baseParticle[i] = {d.charge[i], d.sigma[i], d.epsilon[i]};
+    h.baseException.resize(h.X);
+    h.exceptionAtoms.resize(h.X);
+    for (int e = 0; e < h.X; e++) {
+        h.baseException[e] = {d.exception_params[3*e], d.exception_params[3*e+1], d.exception_params[3*e+2]};
+        h.exceptionAtoms[e] = make_int2(d.exception_particles[2*e], d.exception_particles[2*e+1]);
+    }
+    h.paramsDirty = true;
+}
+
+void setupPme(snb_handle& h, PmeGrid& g, const int n[3], double alpha) {
+    g.alpha = alpha;
+    for (int k = 0; k < 3; k++) g.n[k] = n[k];
+    size_t G = (size_t) n[0]*n[1]*n[2], GC = (size_t) n[0]*n[1]*(n[2]/2+1);
+    g.real.alloc(G*h.S);
+    g.cplx.alloc(GC*h.S);
+    g.eterm.alloc(GC);
+    int dims[3] = {n[0], n[1], n[2]};
+    CUFFT_CHECK(cufftPlanMany(&g.fwd, 3, dims, nullptr, 1, (int) G, nullptr, 1, (int) GC, CUFFT_R2C, h.S));
+    CUFFT_CHECK(cufftPlanMany(&g.inv, 3, dims, nullptr, 1, (int) GC, nullptr, 1, (int) G, CUFFT_C2R, h.S));
+    g.planned = true;
+    CUFFT_CHECK(cufftSetStream(g.fwd, h.stream));
+    CUFFT_CHECK(cufftSetStream(g.inv, h.stream));
+    for (int k = 0; k < 3; k++) {
+        std::vector<double> m = bsplineModuli(n[k]);
+        g.moduli[k].upload(m.data(), m.size(), h.stream);
+        CUDA_CHECK(cudaStreamSynchronize(h.stream));
+    }
+}
+
+snb_handle* createHandle(const snb_desc& d) {
+    validateDesc(d);
+    snb_handle* hp = new snb_handle();
+    snb_handle& h = *hp;
+    try {
+        h.device = d.device_index;
+        CUDA_CHECK(cudaSetDevice(h.device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, h.device));
+        h.numSMs = prop.multiProcessorCount;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+        h.N = d.num_particles;
+        h.NB = (h.N+31)/32;
+        h.NP = h.NB*32;
+        h.S = d.num_subsets;
+        h.L = h.S*(h.S+1)/2;
+        h.G = d.num_global_parameters;
+        h.X = d.num_exceptions;
+        h.method = d.method;
+        h.cutoff = d.cutoff;
+        h.useSwitch = d.method != SNB_NO_CUTOFF && d.use_switching_function;
+        h.switchDist = d.switching_distance;
+        h.rfDielectric = d.reaction_field_dielectric;
+        h.sliceParam.assign(h.L, {-1, -1});
+        h.sliceHasDeriv.assign(h.L, {false, false});
+        h.derivativeParams.assign(d.derivative_parameters, d.derivative_parameters+d.num_derivatives);
+        std::set<int> requested(h.derivativeParams.begin(), h.derivativeParams.end());
+        for (int k = 0; k < d.num_scaling_parameters; k++) {
+            const int32_t* sp = d.scaling_parameters+5*k;
+            if (sp[0] < 0 || sp[0] >= h.G || sp[1] < 0 || sp[1] >= h.S || sp[2] < 0 || sp[2] >= h.S)
+                throw SnbException(SNB_ERR_INVALID, "scaling parameter out of range");
+            int slice = snb_slice_index(sp[1], sp[2]);
+            bool hasDeriv = requested.count(sp[0]) != 0;
+            if (sp[3]) { h.sliceParam[slice][0] = sp[0]; h.sliceHasDeriv[slice][0] = hasDeriv; }
+            if (sp[4]) { h.sliceParam[slice][1] = sp[0]; h.sliceHasDeriv[slice][1] = hasDeriv; }
+        }
+        loadParameters(h, d);
+        h.is14 = find14s(d);
+        h.num14 = (int) std::count(h.is14.begin(), h.is14.end(), 1);
+        for (int k = 0; k < d.num_particle_offsets; k++) {
+            h.particleOffsetIdx.push_back({d.particle_offset_index[2*k], d.particle_offset_index[2*k+1]});
+            h.particleOffsetScale.push_back({d.particle_offset_scale[3*k], d.particle_offset_scale[3*k+1], d.particle_offset_scale[3*k+2]});
+            h.offsetParams.insert(d.particle_offset_index[2*k]);
+        }
+        for (int k = 0; k < d.num_exception_offsets; k++) {
+            h.exceptionOffsetIdx.push_back({d.exception_offset_index[2*k], d.exception_offset_index[2*k+1]});
+            h.exceptionOffsetScale.push_back({d.exception_offset_scale[3*k], d.exception_offset_scale[3*k+1], d.exception_offset_scale[3*k+2]});
+            h.offsetParams.insert(d.exception_offset_index[2*k]);
+        }
+        if (h.method == SNB_PME || h.method == SNB_LJPME)
+            calcPMEParameters(d, false, h.alpha, h.grid);
+        if (h.method == SNB_LJPME) {
+            calcPMEParameters(d, true, h.dalpha, h.dgrid);
+            h.useSwitch = false;
+        }
+        h.exceptionsPeriodic = (h.method == SNB_NO_CUTOFF || h.method == SNB_CUTOFF_NON_PERIODIC) ? false : d.exceptions_use_pbc != 0;
+        h.useDispersion = d.use_dispersion_correction != 0;
+        h.dispersionCoef = h.useDispersion ? calcDispersionCorrections(d) : std::vector<double>(h.L, 0.0);
+
+        // exclusion CSR over original indices (every exception excludes its pair, :104-112)
+        std::vector<int> start(h.N+1, 0), list(2*(size_t) h.X);
+        for (int e = 0; e < h.X; e++) {
+            int a = h.exceptionAtoms[e].x, b = h.exceptionAtoms[e].y;
+            if (a < 0 || a >= h.N || b < 0 || b >= h.N || a == b)
+                throw SnbException(SNB_ERR_INVALID, "illegal particle index for an exception");
+            start[a+1]++; start[b+1]++;
+        }
+        for (int i = 0; i < h.N; i++) start[i+1] += start[i];
+        std::vector<int> fill(start.begin(), start.end()-1);
+        for (int e = 0; e < h.X; e++) {
+            int a = h.exceptionAtoms[e].x, b = h.exceptionAtoms[e].y;
+            list[fill[a]++] = b;
+            list[fill[b]++] = a;
+        }
+        h.exclStart.upload(start.data(), start.size(), h.stream);
+        h.exclList.upload(list.data(), list.size(), h.stream);
+        h.exceptionAtomsD.upload(h.exceptionAtoms.data(), h.X, h.stream);
+        h.is14D.upload(h.is14.data(), h.X, h.stream);
+        CUDA_CHECK(cudaStreamSynchronize(h.stream));
+
+        h.posd.alloc(3*(size_t) h.N);
+        h.paramsD.alloc(3*(size_t) h.N);
+        h.params4.alloc(h.N);
+        h.subsetD.alloc(h.N);
+        h.exception14.alloc(3*(size_t) h.X);
+        h.atomCell.alloc(h.N); h.atomSlot.alloc(h.N);
+        h.sortedAtom.alloc(h.NP); h.sortedPos.alloc(h.N);
+        h.posqLocal.alloc(h.NP); h.sparams.alloc(h.NP);
+        h.blockCenter.alloc(3*(size_t) h.NB); h.blockExt.alloc(h.NB);
+        h.extent.alloc(6);
+        h.energyBuf.alloc(2*SNB_MAX_SLICES);
+        h.counters.alloc(8);
+        h.forceSorted.alloc(3*(size_t) h.NP); h.forceOrig.alloc(3*(size_t) h.NP);
+        h.forcesOutD.alloc(3*(size_t) h.N);
+        h.hPos.alloc(3*(size_t) h.N); h.hForces.alloc(3*(size_t) h.N);
+        h.hEnergy.alloc(2*SNB_MAX_SLICES);
+        h.hCounters.alloc(8);
+        h.sliceEnergies.assign(2*h.L, 0.0);
+        if (h.method == SNB_PME || h.method == SNB_LJPME)
+            setupPme(h, h.pme, h.grid, h.alpha);
+        if (h.method == SNB_LJPME)
+            setupPme(h, h.dpme, h.dgrid, h.dalpha);
+    }
+    catch (...) {
+        delete hp;
+        throw;
+    }
+    return hp;
+}
+
+void updateHandle(snb_handle& h, const snb_desc& d) {
+    // ReferenceOpenMMLabKernels.cpp:263-312
+    if (d.num_particles != h.N)
+        throw SnbException(SNB_ERR_PARTICLE_COUNT, "updateParametersInContext: The number of particles has changed");
+    validateDesc(d);
+    std::vector<int> is14 = find14s(d);
+    if ((int) std::count(is14.begin(), is14.end(), 1) != h.num14 || d.num_exceptions != h.X)
+        throw SnbException(SNB_ERR_EXCEPTION_SET, "updateParametersInContext: The number of non-excluded exceptions has changed");
+    CUDA_CHECK(cudaSetDevice(h.device));
+    h.is14 = is14;
+    h.is14D.upload(h.is14.data(), h.X, h.stream);
+    loadParameters(h, d);
+    h.exceptionAtomsD.upload(h.exceptionAtoms.data(), h.X, h.stream);
+    CUDA_CHECK(cudaStreamSynchronize(h.stream));
+    if (d.use_dispersion_correction && (d.method == SNB_CUTOFF_PERIODIC || d.method == SNB_EWALD || d.method == SNB_PME))
+        h.dispersionCoef = calcDispersionCorrections(d);
+}
+
+// computeParameters (:332-385): lambdas, particle and exception parameters with offsets
+void computeParameters(snb_handle& h, const double* globals) {
+    for (int s = 0; s < h.L; s++) {
+        h.lambdaC[s] = h.sliceParam[s][0] < 0 ? 1.0 : globals[h.sliceParam[s][0]];
+        h.lambdaV[s] = h.sliceParam[s][1] < 0 ? 1.0 : globals[h.sliceParam[s][1]];
+    }
+    std::vector<double> offsetValues;
+    for (int p : h.offsetParams)
+        offsetValues.push_back(globals[p]);
+    if (!h.paramsDirty && offsetValues == h.lastOffsetValues)
+        return;
+    h.lastOffsetValues = offsetValues;
+    h.paramsDirty = false;
+    std::vector<std::array<double, 3>> part = h.baseParticle, exc = h.baseException;
+    // map semantics of the reference: one entry per (parameter, index); a repeated key keeps the last scale
+    std::map<std::pair<int, int>, std::array<double, 3>> pOff, eOff;
+    for (size_t k = 0; k < h.particleOffsetIdx.size(); k++)
+        pOff[{h.particleOffsetIdx[k][0], h.particleOffsetIdx[k][1]}] = h.particleOffsetScale[k];
+    for (size_t k = 0; k < h.exceptionOffsetIdx.size(); k++)
+        eOff[{h.exceptionOffsetIdx[k][0], h.exceptionOffsetIdx[k][1]}] = h.exceptionOffsetScale[k];
+    for (auto& o : pOff)
+        for (int c = 0; c < 3; c++)
+            part[o.first.second][c] += globals[o.first.first]*o.second[c];
+    for (auto& o : eOff)
+        for (int c = 0; c < 3; c++)
+            exc[o.first.second][c] += globals[o.first.first]*o.second[c];
+    std::vector<double> pd(3*(size_t) h.N), e14(3*(size_t) h.X);
+    std::vector<float4> p4(h.N);
+    h.selfC.assign(h.S, 0.0);
+    h.selfV.assign(h.S, 0.0);
+    for (int i = 0; i < h.N; i++) {
+        double q = part[i][0], sig = 0.5*part[i][1], eps = 2.0*sqrt(part[i][2]);
+        pd[3*i] = sig; pd[3*i+1] = eps; pd[3*i+2] = q;
+        p4[i] = make_float4((float) q, (float) sig, (float) eps, 0.f);
+        int sub = h.subsets[i];
+        memcpy(&p4[i].w, &sub, 4);
+        // self energies (ReferenceSlicedLJCoulombIxn.cpp:198-206)
+        h.selfC[sub] -= SNB_ONE_4PI_EPS0*q*q*h.alpha/sqrt(M_PI);
+        if (h.method == SNB_LJPME)
+            h.selfV[sub] += pow(h.dalpha, 6.0)*64.0*pow(sig, 6.0)*pow(eps, 2.0)/12.0;
+    }
+    for (int e = 0; e < h.X; e++) {
+        e14[3*e] = exc[e][1]; e14[3*e+1] = 4.0*exc[e][2]; e14[3*e+2] = exc[e][0];
+    }
+    h.paramsD.upload(pd.data(), pd.size(), h.stream);
+    h.params4.upload(p4.data(), p4.size(), h.stream);
+    h.subsetD.upload(h.subsets.data(), h.N, h.stream);
+    h.exception14.upload(e14.data(), e14.size(), h.stream);
+    CUDA_CHECK(cudaStreamSynchronize(h.stream));    // the staging vectors die with this scope
+}
+
+void makeBox(const double* box, BoxD& bd, BoxF& bf) {
+    bd.ax = box[0]; bd.bx = box[3]; bd.by = box[4]; bd.cx = box[6]; bd.cy = box[7]; bd.cz = box[8];
+    double det = bd.ax*bd.by*bd.cz;
+    memset(bd.recip, 0, sizeof(bd.recip));
+    bd.recip[0][0] = bd.by*bd.cz/det;
+    bd.recip[1][0] = -bd.bx*bd.cz/det;
+    bd.recip[1][1] = bd.ax*bd.cz/det;
+    bd.recip[2][0] = (bd.bx*bd.cy-bd.by*bd.cx)/det;
+    bd.recip[2][1] = -bd.ax*bd.cy/det;
+    bd.recip[2][2] = bd.ax*bd.by/det;
+    bf.ax = (float) bd.ax; bf.bx = (float) bd.bx; bf.by = (float) bd.by;
+    bf.cx = (float) bd.cx; bf.cy = (float) bd.cy; bf.cz = (float) bd.cz;
+    bf.invAx = (float) (1.0/bd.ax); bf.invBy = (float) (1.0/bd.by); bf.invCz = (float) (1.0/bd.cz);
+}
+
+void setupCells(snb_handle& h, const double* box, bool periodic) {
+    int dim[3];
+    if (periodic) {
+        double volume = box[0]*box[4]*box[8];
+        double cs = cbrt(4.0*volume/std::max(h.N, 1));
+        for (int k = 0; k < 3; k++)
+            dim[k] = std::max(1, std::min(256, (int) floor(box[4*k]/cs+0.5)));
+    }
+    else {
+        int m = std::max(1, std::min(256, (int) floor(cbrt(std::max(h.N, 1)/4.0)+0.5)));
+        dim[0] = dim[1] = dim[2] = m;
+    }
+    if (dim[0] == h.cellDim[0] && dim[1] == h.cellDim[1] && dim[2] == h.cellDim[2])
+        return;
+    for (int k = 0; k < 3; k++) h.cellDim[k] = dim[k];
+    h.numCells = dim[0]*dim[1]*dim[2];
+    int bits = 1;
+    while ((1<<bits) < std::max(dim[0], std::max(dim[1], dim[2]))) bits++;
+    std::vector<std::pair<uint64_t, int>> keyed(h.numCells);
+    for (int x = 0; x < dim[0]; x++)
+        for (int y = 0; y < dim[1]; y++)
+            for (int z = 0; z < dim[2]; z++) {
+                int c = (x*dim[1]+y)*dim[2]+z;
+                keyed[c] = {hilbertIndex(x, y, z, bits), c};
+            }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<int> rank(h.numCells);
+    for (int r = 0; r < h.numCells; r++)
+        rank[keyed[r].second] = r;
+    h.cellRank.upload(rank.data(), rank.size(), h.stream);
+    CUDA_CHECK(cudaStreamSynchronize(h.stream));
+    h.cellCount.alloc(h.numCells);
+    h.cellStart.alloc(h.numCells+1);
+}
+
+void ensureListCapacity(snb_handle& h, const double* box, bool periodic) {
+    if (h.maxChunks > 0)
+        return;
+    size_t perBlock;
+    if (h.method == SNB_NO_CUTOFF)
+        perBlock = h.NB+1;
+    else {
+        double density = periodic ? h.N/(box[0]*box[4]*box[8]) : 100.0;
+        double reach = h.cutoff+0.45;
+        double atoms = 0.5*density*(4.0/3.0*M_PI*reach*reach*reach)*1.3+96;
+        perBlock = std::min<size_t>((size_t) (atoms/32)+2, (size_t) h.NB+1);
+    }
+    h.maxChunks = std::max<size_t>(64, perBlock*h.NB);
+    h.maxItems = h.maxChunks/2+h.NB+16;
+    h.jList.alloc(h.maxChunks*32);
+    h.workItems.alloc(h.maxItems);
+}
+
+struct Timer {
+    snb_handle& h;
+    explicit Timer(snb_handle& h) : h(h) {
+        if (h.timing && !h.evCreated) {
+            for (auto& e : h.ev) CUDA_CHECK(cudaEventCreate(&e));
+            h.evCreated = true;
+        }
+    }
+    void mark(int k) { if (h.timing) CUDA_CHECK(cudaEventRecord(h.ev[k], h.stream)); }
+};
+
+// One stream-ordered evaluation.  Returns false when a device-side capacity or mode check asks
+// for a repeat (buffers were grown / the PBC mode was changed).
+bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, void* forcesFixedOut) {
+    const bool includeForces = flags&SNB_INCLUDE_FORCES, includeDirect = flags&SNB_INCLUDE_DIRECT,
+               includeRecip = flags&SNB_INCLUDE_RECIPROCAL;
+    const bool periodic = h.method >= SNB_CUTOFF_PERIODIC;
+    const bool pmeFamily = h.method == SNB_PME || h.method == SNB_LJPME;
+    bool needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
+    cudaStream_t st = h.stream;
+    Timer tm(h);
+    BoxD bd;
+    BoxF bf;
+    double unitBox[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    makeBox(periodic ? box : unitBox, bd, bf);
+    setupCells(h, box, periodic);
+    ensureListCapacity(h, box, periodic);
+
+    int pbcMode = PBC_NONE;
+    if (periodic) {
+        bool triclinic = bd.bx != 0 || bd.cx != 0 || bd.cy != 0;
+        double room = std::min(bd.ax, std::min(bd.by, bd.cz))*0.5-h.cutoff;
+        if (triclinic) pbcMode = PBC_PAIR_TRICLINIC;
+        else if (h.pbcModeOverride >= 0) pbcMode = h.pbcModeOverride;
+        else pbcMode = room > 0.75 ? PBC_SHIFT : PBC_PAIR_ORTHO;
+    }
+
+    CUDA_CHECK(cudaMemsetAsync(h.forceSorted.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
+    CUDA_CHECK(cudaMemsetAsync(h.forceOrig.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
+    CUDA_CHECK(cudaMemsetAsync(h.energyBuf.p, 0, sizeof(double)*2*SNB_MAX_SLICES, st));
+    CUDA_CHECK(cudaMemsetAsync(h.counters.p, 0, sizeof(int)*8, st));
+    tm.mark(0);
+
+    DirectArgs da;
+    memset(&da, 0, sizeof(da));
+    if (includeDirect) {
+        SortArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.numAtoms = h.N; sa.paddedAtoms = h.NP; sa.numBlocks = h.NB; sa.numCells = h.numCells; sa.periodic = periodic;
+        for (int k = 0; k < 3; k++) sa.cellDim[k] = h.cellDim[k];
+        sa.checkShift = pbcMode == PBC_SHIFT;
+        sa.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); sa.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); sa.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
+        sa.counters = h.counters.p;
+        sa.sqrtK = (float) sqrt(SNB_ONE_4PI_EPS0);
+        sa.boxd = bd;
+        sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
+        sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p;
+        sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
+        sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p;
+        launchSort(sa, st);
+        tm.mark(1);
+
+        ListArgs la;
+        memset(&la, 0, sizeof(la));
+        la.numAtoms = h.N; la.numBlocks = h.NB; la.pbcMode = pbcMode; la.periodic = periodic;
+        la.useCutoff = h.method != SNB_NO_CUTOFF;
+        la.cutoff = (float) (h.cutoff*(1.0+1e-5)+1e-5);
+        la.box = bf; la.boxd = bd;
+        la.sortedAtom = h.sortedAtom.p; la.sortedPos = h.sortedPos.p; la.posqLocal = h.posqLocal.p;
+        la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p;
+        la.exclStart = h.exclStart.p; la.exclList = h.exclList.p;
+        la.jList = h.jList.p; la.workItems = h.workItems.p; la.counters = h.counters.p;
+        la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems;
+        launchBuildList(la, st, h.numSMs);
+        tm.mark(2);
+
+        DirectParams& p = da.p;
+        p.numAtoms = h.N; p.numBlocks = h.NB; p.pbcMode = pbcMode; p.periodic = periodic;
+        p.cutoff2 = (float) (h.cutoff*h.cutoff);
+        p.cutoff2d = h.cutoff*h.cutoff;
+        p.bandTol = (float) (4e-5*h.cutoff*h.cutoff);
+        p.alpha = (float) h.alpha; p.alpha2 = (float) (h.alpha*h.alpha);
+        p.twoAlphaOverSqrtPi = (float) (2.0*h.alpha/sqrt(M_PI));
+        p.krf = (float) (pow(h.cutoff, -3.0)*(h.rfDielectric-1.0)/(2.0*h.rfDielectric+1.0));
+        p.crf = (float) ((1.0/h.cutoff)*(3.0*h.rfDielectric)/(2.0*h.rfDielectric+1.0));
+        p.switchDist = (float) h.switchDist;
+        p.invSwitchWidth = h.useSwitch ? (float) (1.0/(h.cutoff-h.switchDist)) : 0.f;
+        double dc2 = h.dalpha*h.cutoff*h.dalpha*h.cutoff;
+        p.dalpha2 = (float) (h.dalpha*h.dalpha);
+        p.dispShiftExp = (float) (1.0-exp(-dc2)*(1.0+dc2+0.5*dc2*dc2));
+        p.invCut6 = (float) pow(h.cutoff, -6.0);
+        for (int s = 0; s < h.L; s++) { p.lambdaC[s] = (float) h.lambdaC[s]; p.lambdaV[s] = (float) h.lambdaV[s]; }
+        p.box = bf; p.boxd = bd;
+        da.kind = h.method == SNB_NO_CUTOFF ? KIND_PLAIN : h.method <= SNB_CUTOFF_PERIODIC ? KIND_RF : h.method == SNB_LJPME ? KIND_LJPME : KIND_EWALD;
+        da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy;
+        da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
+        da.blockCenter = h.blockCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.workItems = h.workItems.p;
+        da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
+        launchDirect(da, st, h.numSMs);
+        tm.mark(3);
+
+        BondedArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        ba.numExceptions = h.X; ba.periodicExceptions = h.exceptionsPeriodic; ba.ewald = pmeFamily; ba.ljpme = h.method == SNB_LJPME;
+        ba.includeForces = 1;
+        ba.alpha = h.alpha; ba.dalpha = h.dalpha; ba.boxd = bd;
+        ba.posd = h.posd.p; ba.paramsD = h.paramsD.p; ba.subset = h.subsetD.p; ba.exceptionAtoms = h.exceptionAtomsD.p;
+        ba.exception14 = h.exception14.p; ba.exceptionIs14 = h.is14D.p;
+        for (int s = 0; s < h.L; s++) { ba.lambdaC[s] = h.lambdaC[s]; ba.lambdaV[s] = h.lambdaV[s]; }
+        ba.forceOrig = h.forceOrig.p; ba.paddedAtoms = h.NP; ba.energyBuf = h.energyBuf.p;
+        launchBonded(ba, st);
+        tm.mark(4);
+    }
+    else {
+        // the sorted order is still needed by the reciprocal kernels and the final gather:
+        // identity order is enough there
+        tm.mark(1); tm.mark(2); tm.mark(3); tm.mark(4);
+    }
+
+    if (includeRecip && pmeFamily) {
+        for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
+            PmeGrid& g = term == 0 ? h.pme : h.dpme;
+            PmeArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.numAtoms = h.N; pa.numSubsets = h.S; pa.term = term;
+            pa.nx = g.n[0]; pa.ny = g.n[1]; pa.nz = g.n[2];
+            pa.alpha = g.alpha; pa.boxd = bd; pa.posd = h.posd.p;
+            pa.sortedAtom = includeDirect ? h.sortedAtom.p : nullptr;
+            pa.params4 = h.params4.p; pa.grid = g.real.p; pa.cgrid = g.cplx.p; pa.eterm = g.eterm.p;
+            for (int k = 0; k < 3; k++) pa.moduli[k] = g.moduli[k].p;
+            for (int s = 0; s < h.L; s++) pa.lambda[s] = (float) (term == 0 ? h.lambdaC[s] : h.lambdaV[s]);
+            pa.forceOrig = h.forceOrig.p; pa.paddedAtoms = h.NP; pa.energyBuf = h.energyBuf.p;
+            double key[6] = {bd.ax, bd.bx, bd.by, bd.cx, bd.cy, bd.cz};
+            if (!g.etermValid || memcmp(key, g.etermBox, sizeof(key)) != 0) {
+                launchPmeEterm(pa, g.eterm.p, st);
+                memcpy(g.etermBox, key, sizeof(key));
+                g.etermValid = true;
+            }
+            launchPmeSpread(pa, st);
+            if (term == 0) tm.mark(5);
+            CUFFT_CHECK(cufftExecR2C(g.fwd, g.real.p, (cufftComplex*) g.cplx.p));
+            if (term == 0) tm.mark(6);
+            launchPmeConvolution(pa, st);
+            if (term == 0) tm.mark(7);
+            CUFFT_CHECK(cufftExecC2R(g.inv, (cufftComplex*) g.cplx.p, g.real.p));
+            launchPmeInterpolate(pa, st);
+            if (term == 0) tm.mark(8);
+        }
+    }
+    else {
+        tm.mark(5); tm.mark(6); tm.mark(7); tm.mark(8);
+    }
+
+    if (includeForces) {
+        FinishArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.numAtoms = h.N; fa.paddedAtoms = h.NP;
+        fa.sortedPos = includeDirect ? h.sortedPos.p : nullptr;
+        fa.forceSorted = h.forceSorted.p; fa.forceOrig = h.forceOrig.p;
+        fa.forcesOut = hostPositions ? h.forcesOutD.p : nullptr;
+        fa.forcesFixedOut = (long long*) forcesFixedOut;
+        launchFinish(fa, st);
+        if (hostPositions)
+            CUDA_CHECK(cudaMemcpyAsync(h.hForces.p, h.forcesOutD.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyDeviceToHost, st));
+    }
+    tm.mark(9);
+    CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, h.energyBuf.p, sizeof(double)*2*SNB_MAX_SLICES, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(cudaGetLastError());
+    h.lastDirect = da;
+    h.listValid = includeDirect;
+    if (includeDirect) {
+        if (h.hCounters.p[2]) {
+            // list buffers too small: grow to what the device asked for and repeat
+            h.maxChunks = (size_t) (h.hCounters.p[0]*1.25)+64;
+            h.maxItems = std::max<size_t>(h.maxItems, (size_t) (h.hCounters.p[1]*1.25)+64);
+            h.jList.alloc(h.maxChunks*32);
+            h.workItems.alloc(h.maxItems);
+            return false;
+        }
+        if (h.hCounters.p[4]) {
+            h.pbcModeOverride = PBC_PAIR_ORTHO;
+            return false;
+        }
+    }
+    if (h.timing) {
+        for (int k = 0; k < 9; k++)
+            CUDA_CHECK(cudaEventElapsedTime(&h.phaseMs[k], h.ev[k], h.ev[k+1]));
+        CUDA_CHECK(cudaEventElapsedTime(&h.phaseMs[SNB_PHASE_TOTAL], h.ev[0], h.ev[9]));
+    }
+    h.countersOut[1] = h.hCounters.p[0];
+    h.countersOut[3] = h.hCounters.p[1];
+    return true;
+}
+
+void finishEnergies(snb_handle& h, const double* box, int flags) {
+    const bool includeDirect = flags&SNB_INCLUDE_DIRECT, includeRecip = flags&SNB_INCLUDE_RECIPROCAL;
+    for (int k = 0; k < 2*h.L; k++)
+        h.sliceEnergies[k] = h.hEnergy.p[k];
+    if (includeRecip && (h.method == SNB_PME || h.method == SNB_LJPME))
+        for (int s = 0; s < h.S; s++) {
+            h.sliceEnergies[2*(s*(s+3)/2)] += h.selfC[s];
+            h.sliceEnergies[2*(s*(s+3)/2)+1] += h.selfV[s];
+        }
+    if (includeDirect && (h.method == SNB_CUTOFF_PERIODIC || h.method == SNB_EWALD || h.method == SNB_PME)) {
+        double volume = box[0]*box[4]*box[8];
+        for (int s = 0; s < h.L; s++)
+            h.sliceEnergies[2*s+1] += h.dispersionCoef[s]/volume;
+    }
+    h.lastEnergy = 0;
+    if (flags&SNB_INCLUDE_ENERGY)
+        for (int s = 0; s < h.L; s++)
+            h.lastEnergy += h.lambdaC[s]*h.sliceEnergies[2*s]+h.lambdaV[s]*h.sliceEnergies[2*s+1];
+}
+
+void evaluate(snb_handle& h, const double* positions, const void* posqDev, const double* box, const double* globals,
+              int flags, void* forcesFixedOut) {
+    CUDA_CHECK(cudaSetDevice(h.device));
+    const bool periodic = h.method >= SNB_CUTOFF_PERIODIC;
+    if (periodic) {
+        if (!box)
+            throw SnbException(SNB_ERR_INVALID, "periodic method needs box vectors");
+        double minAllowedSize = 1.999999*h.cutoff;
+        if (box[0] < minAllowedSize || box[4] < minAllowedSize || box[8] < minAllowedSize)
+            throw SnbException(SNB_ERR_BOX_TOO_SMALL, "The periodic box size has decreased to less than twice the nonbonded cutoff.");
+    }
+    std::vector<double> noGlobals(1, 0.0);
+    computeParameters(h, globals ? globals : noGlobals.data());
+    if (h.N == 0) {
+        std::fill(h.sliceEnergies.begin(), h.sliceEnergies.end(), 0.0);
+        h.lastEnergy = 0;
+        return;
+    }
+    if (positions) {
+        memcpy(h.hPos.p, positions, sizeof(double)*3*(size_t) h.N);
+        CUDA_CHECK(cudaMemcpyAsync(h.posd.p, h.hPos.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, h.stream));
+    }
+    else
+        launchConvertPositions((const float4*) posqDev, h.posd.p, h.N, h.stream);
+    double unitBox[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const double* b = periodic ? box : unitBox;
+    for (int attempt = 0; attempt < 4; attempt++)
+        if (runOnce(h, b, flags, positions != nullptr, forcesFixedOut)) {
+            finishEnergies(h, b, flags);
+            h.lastFlags = flags;
+            return;
+        }
+    throw SnbException(SNB_ERR_CUDA, "tile list capacity did not converge");
+}
+
+int fail(const SnbException& e) {
+    g_lastError = e.msg;
+    return e.code;
+}
+
+}  // namespace
+
+#define SNB_TRY try {
+#define SNB_CATCH } catch (const SnbException& e) { return fail(e); } \
+    catch (const std::exception& e) { g_lastError = e.what(); return SNB_ERR_INVALID; }
+
+extern "C" {
+
+int snb_create(const snb_desc* desc, snb_handle** out) {
+    SNB_TRY
+    if (!desc || !out) throw SnbException(SNB_ERR_INVALID, "null argument");
+    *out = createHandle(*desc);
+    return SNB_OK;
+    SNB_CATCH
+}
+
+void snb_destroy(snb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->evCreated)
+        for (auto& e : h->ev) cudaEventDestroy(e);
+    cudaStream_t s = h->stream;
+    delete h;
+    if (s) cudaStreamDestroy(s);
+}
+
+int snb_update_parameters(snb_handle* h, const snb_desc* desc) {
+    SNB_TRY
+    updateHandle(*h, *desc);
+    return SNB_OK;
+    SNB_CATCH
+}
+
+int snb_execute(snb_handle* h, const double* positions, const double* box, const double* globals, int flags,
+                double* forces, double* energy, double* slice_energies, double* derivatives) {
+    SNB_TRY
+    if (!positions) throw SnbException(SNB_ERR_INVALID, "positions are null");
+    evaluate(*h, positions, nullptr, box, globals, flags, nullptr);
+    if ((flags&SNB_INCLUDE_FORCES) && forces)
+        for (size_t k = 0; k < 3*(size_t) h->N; k++)
+            forces[k] += h->hForces.p[k];
+    return snb_read_energies(h, flags, energy, slice_energies, derivatives);
+    SNB_CATCH
+}
+
+int snb_execute_device(snb_handle* h, const void* posq_dev, const double* box, const double* globals, int flags, void* forces_dev) {
+    SNB_TRY
+    if (!posq_dev) throw SnbException(SNB_ERR_INVALID, "positions are null");
+    evaluate(*h, nullptr, posq_dev, box, globals, flags, forces_dev);
+    return SNB_OK;
+    SNB_CATCH
+}
+
+int snb_read_energies(snb_handle* h, int flags, double* energy, double* slice_energies, double* derivatives) {
+    if (energy) *energy = (flags&SNB_INCLUDE_ENERGY) ? h->lastEnergy : 0.0;
+    if (slice_energies)
+        std::copy(h->sliceEnergies.begin(), h->sliceEnergies.end(), slice_energies);
+    // derivatives: raw slice energies of every (slice, term) bound to the parameter, regardless of
+    // includeEnergy (ReferenceOpenMMLabKernels.cpp:252-258)
+    if (derivatives)
+        for (int s = 0; s < h->L; s++)
+            for (int t = 0; t < 2; t++)
+                if (h->sliceHasDeriv[s][t])
+                    for (size_t k = 0; k < h->derivativeParams.size(); k++)
+                        if (h->derivativeParams[k] == h->sliceParam[s][t])
+                            derivatives[k] += h->sliceEnergies[2*s+t];
+    return SNB_OK;
+}
+
+int snb_get_pme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz) {
+    if (h->method != SNB_PME && h->method != SNB_LJPME) {
+        g_lastError = "getPMEParametersInContext: This Context is not using PME or LJPME";
+        return SNB_ERR_WRONG_METHOD;
+    }
+    *alpha = h->alpha; *nx = h->grid[0]; *ny = h->grid[1]; *nz = h->grid[2];
+    return SNB_OK;
+}
+
+int snb_get_ljpme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz) {
+    if (h->method != SNB_LJPME) {
+        g_lastError = "getPMEParametersInContext: This Context is not using LJPME";
+        return SNB_ERR_WRONG_METHOD;
+    }
+    *alpha = h->dalpha; *nx = h->dgrid[0]; *ny = h->dgrid[1]; *nz = h->dgrid[2];
+    return SNB_OK;
+}
+
+int snb_dump_pairs(snb_handle* h, int32_t** pairs, int64_t* num_pairs) {
+    SNB_TRY
+    if (!h->listValid) throw SnbException(SNB_ERR_INVALID, "no tile list has been built (run an execute with direct space first)");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    DevBuf<unsigned long long> count;
+    DevBuf<int2> buf;
+    count.alloc(1);
+    long long capacity = 0;
+    unsigned long long found = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        CUDA_CHECK(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long), h->stream));
+        CUDA_CHECK(cudaMemsetAsync(h->counters.p+3, 0, sizeof(int), h->stream));
+        DirectArgs da = h->lastDirect;
+        buf.alloc(std::max<long long>(capacity, 1));
+        da.pairDump = buf.p; da.pairDumpCount = count.p; da.pairDumpCapacity = capacity;
+        launchDirect(da, h->stream, h->numSMs);
+        CUDA_CHECK(cudaMemcpyAsync(&found, count.p, sizeof(found), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        capacity = (long long) found;
+    }
+    std::vector<int2> host(std::max<size_t>(found, 1));
+    if (found)
+        CUDA_CHECK(cudaMemcpy(host.data(), buf.p, sizeof(int2)*found, cudaMemcpyDeviceToHost));
+    host.resize(found);
+    std::sort(host.begin(), host.end(), [](const int2& a, const int2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    *num_pairs = (int64_t) found;
+    *pairs = (int32_t*) malloc(std::max<size_t>(found, 1)*2*sizeof(int32_t));
+    for (size_t k = 0; k < found; k++) { (*pairs)[2*k] = host[k].x; (*pairs)[2*k+1] = host[k].y; }
+    return SNB_OK;
+    SNB_CATCH
+}
+
+void snb_free(void* p) { free(p); }
+
+int snb_set_timing(snb_handle* h, int enabled) { h->timing = enabled != 0; return SNB_OK; }
+
+int snb_get_phase_times(snb_handle* h, float* ms) {
+    for (int k = 0; k < SNB_NUM_PHASES; k++) ms[k] = h->phaseMs[k];
+    return SNB_OK;
+}
+
+int snb_get_counters(snb_handle* h, int64_t* out) {
+    for (int k = 0; k < 8; k++) out[k] = h->countersOut[k];
+    return SNB_OK;
+}
+
+int snb_nccl_unique_id(void*) { g_lastError = "multi-GPU support is not built into this library yet"; return SNB_ERR_UNSUPPORTED; }
+int snb_comm_init(snb_handle*, const void*, int, int) { g_lastError = "multi-GPU support is not built into this library yet"; return SNB_ERR_UNSUPPORTED; }
+
+const char* snb_last_error(void) { return g_lastError.c_str(); }
+const char* snb_version(void) { return "slicednb-b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

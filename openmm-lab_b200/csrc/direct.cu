@@ -1,0 +1,14 @@
+// Dispatch of the direct-space tile kernel over interaction kinds (kernels live in direct_impl.cuh).
+#include "kernels.cuh"
+
+template <int KIND> void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid);
+
+void launchDirect(const DirectArgs& a, cudaStream_t st, int numSMs) {
+    int grid = numSMs*2;
+    switch (a.kind) {
+        case KIND_PLAIN: launchDirectKind<KIND_PLAIN>(a, st, grid); break;
+        case KIND_RF: launchDirectKind<KIND_RF>(a, st, grid); break;
+        case KIND_EWALD: launchDirectKind<KIND_EWALD>(a, st, grid); break;
+        default: launchDirectKind<KIND_LJPME>(a, st, grid); break;
+    }
+}

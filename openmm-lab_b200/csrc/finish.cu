@@ -1,0 +1,36 @@
+// Final pass: gather the two fixed-point force accumulators (sorted-order tile forces and
+// original-order bonded / reciprocal forces) into the caller's layout, and the small helper that
+// widens device float4 positions to the double array the exact predicates read.
+#include "kernels.cuh"
+
+__global__ void k_finish(FinishArgs a) {
+    int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (i >= a.numAtoms)
+        return;
+    const int k = a.sortedPos ? a.sortedPos[i] : i;
+    for (int c = 0; c < 3; c++) {
+        long long f = a.forceSorted[c*a.paddedAtoms+k]+a.forceOrig[c*a.paddedAtoms+i];
+        if (a.forcesOut)
+            a.forcesOut[3*i+c] = (double) f*(1.0/SNB_FORCE_SCALE_D);
+        if (a.forcesFixedOut)
+            a.forcesFixedOut[(size_t) c*a.numAtoms+i] += f;
+    }
+}
+
+__global__ void k_convertPositions(const float4* posq, double* posd, int numAtoms) {
+    int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (i >= numAtoms)
+        return;
+    float4 p = posq[i];
+    posd[3*i] = p.x; posd[3*i+1] = p.y; posd[3*i+2] = p.z;
+}
+
+void launchFinish(const FinishArgs& a, cudaStream_t stream) {
+    if (a.numAtoms > 0)
+        k_finish<<<(a.numAtoms+255)/256, 256, 0, stream>>>(a);
+}
+
+void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream) {
+    if (numAtoms > 0)
+        k_convertPositions<<<(numAtoms+255)/256, 256, 0, stream>>>(posq, posd, numAtoms);
+}

@@ -1,0 +1,115 @@
+// Argument blocks and launchers of the device stages (one .cu per stage).
+#ifndef SNB_KERNELS_CUH_
+#define SNB_KERNELS_CUH_
+
+#include "snb_core.cuh"
+
+struct SortArgs {
+    int numAtoms, paddedAtoms, numBlocks, numCells, periodic;
+    int cellDim[3];
+    float shiftLimit[3];    // halfBox - cutoff per axis: PBC_SHIFT needs every block's half extent below it
+    int checkShift;
+    int* counters;          // [4] set when a block violates shiftLimit
+    float sqrtK;            // sqrt(ONE_4PI_EPS0): direct-space charges carry it
+    BoxD boxd;
+    const double* posd;
+    const float4* params4;
+    const int* cellRank;
+    double* extent;
+    int *cellCount, *cellStart, *atomCell, *atomSlot, *sortedAtom, *sortedPos;
+    float4 *posqLocal, *sparams;
+    double* blockCenter;
+    float4* blockExt;
+};
+void launchSort(const SortArgs& a, cudaStream_t stream);
+
+struct ListArgs {
+    int numAtoms, numBlocks, pbcMode, periodic, useCutoff;
+    float cutoff;           // padded by a safety margin for the single-precision tests
+    BoxF box;
+    BoxD boxd;
+    const int* sortedAtom;
+    const int* sortedPos;
+    const float4* posqLocal;
+    const double* blockCenter;
+    const float4* blockExt;
+    const int* exclStart;   // CSR over ORIGINAL atom indices: partners of each atom (both directions)
+    const int* exclList;
+    int2* jList;
+    int4* workItems;
+    int* counters;          // [0] chunks allocated, [1] work items, [2] overflow flag, [3] next work item
+    int maxChunks, maxItems;
+};
+void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
+
+struct DirectArgs {
+    DirectParams p;
+    int kind, useSwitch, numSubsets, needEnergy;
+    const int* sortedAtom;
+    const float4* posqLocal;
+    const float4* sparams;
+    const double* blockCenter;
+    const double* posd;
+    const int2* jList;
+    const int4* workItems;
+    int* counters;
+    long long* forceSorted;     // [3][paddedAtoms]
+    int paddedAtoms;
+    double* energyBuf;          // [numSlices][2]
+    int2* pairDump;             // optional (tests): original-index pairs
+    unsigned long long* pairDumpCount;
+    long long pairDumpCapacity;
+};
+void launchDirect(const DirectArgs& a, cudaStream_t stream, int numSMs);
+
+struct BondedArgs {
+    int numExceptions, periodicExceptions, ewald, ljpme, includeForces;
+    double alpha, dalpha;
+    BoxD boxd;
+    const double* posd;
+    const double* paramsD;          // [N][3] sigma/2, 2 sqrt(eps), q
+    const int* subset;
+    const int2* exceptionAtoms;     // [X]
+    const double* exception14;      // [X][3] sigma, 4 eps, chargeProd (after offsets)
+    const int* exceptionIs14;       // [X]
+    double lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
+    long long* forceOrig;           // [3][paddedAtoms]
+    int paddedAtoms;
+    double* energyBuf;
+};
+void launchBonded(const BondedArgs& a, cudaStream_t stream);
+
+struct PmeArgs {
+    int numAtoms, numSubsets, term;  // term 0 Coulomb, 1 dispersion
+    int nx, ny, nz;
+    double alpha;
+    BoxD boxd;
+    const double* posd;
+    const int* sortedAtom;
+    const float4* params4;          // q in .x ; sigma/2, 2 sqrt(eps) in .y .z (dispersion "charge" = 8 s^3 e)
+    float* grid;                    // [S][nx][ny][nz] real
+    float2* cgrid;                  // [S][nx][ny][nz/2+1]
+    const float* eterm;             // [nx][ny][nz/2+1]
+    const double* moduli[3];
+    float lambda[SNB_MAX_SLICES];   // of this term
+    long long* forceOrig;
+    int paddedAtoms;
+    double* energyBuf;
+};
+void launchPmeEterm(const PmeArgs& a, float* eterm, cudaStream_t stream);
+void launchPmeSpread(const PmeArgs& a, cudaStream_t stream);
+void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
+void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);
+
+struct FinishArgs {
+    int numAtoms, paddedAtoms;
+    const int* sortedPos;
+    const long long* forceSorted;
+    const long long* forceOrig;
+    double* forcesOut;              // [N][3] host-visible staging (device), or null
+    long long* forcesFixedOut;      // [3][N] added to, or null
+};
+void launchFinish(const FinishArgs& a, cudaStream_t stream);
+void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream);
+
+#endif

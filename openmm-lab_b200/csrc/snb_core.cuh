@@ -1,0 +1,120 @@
+// Internal declarations of the B200 SlicedNonbondedForce core (sm_100a).
+//
+// Layout in HBM (per handle), N atoms padded to NP = 32*numBlocks:
+//   posd      double[N][3]   positions as given (original order) -- exact cutoff predicate, PME, bonded
+//   params4   float4[N]      (q, sigma/2, 2 sqrt(eps), bitcast subset)         original order
+//   paramsD   double[N][3]   (sigma/2, 2 sqrt(eps), q) in double               original order (bonded kernel)
+//   sortedAtom int[NP]       original index of sorted slot k (-1 = padding)
+//   sortedPos  int[N]        inverse permutation
+//   posqLocal float4[NP]     (x,y,z relative to the block centre, q)           sorted order
+//   sparams   float4[NP]     (sigma/2, 2 sqrt(eps), bitcast subset, c6)        sorted order
+//   blockCenter double[NB][3], blockExt float4[NB] (half extents)
+//   jList     int2[cap]      (sorted j, exclusion mask over the 32 i lanes), 32 entries per chunk
+//   workItems int4[cap]      (i-block, first chunk, number of chunks, unused)
+//   forceSorted / forceOrig  long long[3][NP]  2^32 fixed point
+//   energyBuf double[numSlices][2] (+ counters)
+#ifndef SNB_CORE_CUH_
+#define SNB_CORE_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slicednb.h"
+#include "../../include/snb_constants.h"
+
+#define SNB_MAX_SUBSETS 8
+#define SNB_MAX_SLICES (SNB_MAX_SUBSETS*(SNB_MAX_SUBSETS+1)/2)
+#define SNB_BLOCK 32
+#define SNB_FORCE_SCALE 4294967296.0f       /* 2^32, as the reference's fixed-point forces (realToFixedPoint.cu:1-2) */
+#define SNB_FORCE_SCALE_D 4294967296.0
+#define SNB_ITEM_CHUNKS 8                   /* chunks of 32 j atoms per work item */
+
+enum { PBC_NONE = 0, PBC_SHIFT = 1, PBC_PAIR_ORTHO = 2, PBC_PAIR_TRICLINIC = 3 };
+enum { KIND_PLAIN = 0, KIND_RF = 1, KIND_EWALD = 2, KIND_LJPME = 3 };
+
+struct BoxF {
+    float ax, bx, by, cx, cy, cz;       // a=(ax,0,0) b=(bx,by,0) c=(cx,cy,cz)
+    float invAx, invBy, invCz;
+};
+struct BoxD {
+    double ax, bx, by, cx, cy, cz;
+    double recip[3][3];                 // lower triangular, frac = pos * recip (ReferencePME.cpp:186-194)
+};
+
+struct DirectParams {
+    int numAtoms, numBlocks, pbcMode, periodic;
+    float cutoff2, bandTol;             // |r2 - cutoff2| < bandTol -> exact double predicate
+    double cutoff2d;
+    float alpha, alpha2, twoAlphaOverSqrtPi;
+    float krf, crf;
+    float switchDist, invSwitchWidth;
+    float dalpha2, dispShiftExp, invCut6; // LJPME: alpha_d^2, [1-exp(-d_c^2)(1+d_c^2+d_c^4/2)], rc^-6
+    float lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
+    BoxF box;
+    BoxD boxd;
+};
+
+// ---- small device helpers ---------------------------------------------------------
+__device__ __forceinline__ int sliceOf(int a, int b) { return a > b ? a*(a+1)/2+b : b*(b+1)/2+a; }
+
+__device__ __forceinline__ float fastExp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fastRsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fastRcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// erfc(x) = exp(-x^2) * P(u), u = (t - m)/h, t = 1/(1 + x/2); degree-9 Chebyshev fit of erfcx on
+// x in [0,4]: fit error 6e-10, float evaluation error < 5e-7 relative (the reference's single-precision
+// kernel uses an Abramowitz-Stegun form with 1.5e-7 ABSOLUTE error, coulombLennardJones.cc:18-23,
+// which is ~1e-3 relative at the cutoff and cannot meet the 1e-5 parity bar).
+__device__ __forceinline__ float erfcxPoly(float x) {
+    const float m = 0.66666666666666663f, h = 0.33333333333333337f;   // t in [1/3, 1]
+    float t = fastRcp(fmaf(0.5f, x, 1.0f));
+    float u = (t-m)*(1.0f/h);
+    float p = -7.5385177448e-07f;
+    p = fmaf(p, u, -8.2052179778e-06f);
+    p = fmaf(p, u, 3.4861879002e-05f);
+    p = fmaf(p, u, 9.8919924926e-05f);
+    p = fmaf(p, u, -8.6138957608e-04f);
+    p = fmaf(p, u, -1.6015017984e-03f);
+    p = fmaf(p, u, 2.2509531568e-02f);
+    p = fmaf(p, u, 1.4242693719e-01f);
+    p = fmaf(p, u, 4.0981802125e-01f);
+    p = fmaf(p, u, 4.2758357745e-01f);
+    return p;
+}
+
+__device__ __forceinline__ long long toFixed(float f) { return __float2ll_rn(f*SNB_FORCE_SCALE); }
+__device__ __forceinline__ long long toFixedD(double f) { return __double2ll_rn(f*SNB_FORCE_SCALE_D); }
+__device__ __forceinline__ void addFixed(long long* p, long long v) {
+    atomicAdd((unsigned long long*) p, (unsigned long long) v);
+}
+
+// OpenMM-style periodic displacement in double (ReferenceForce::getDeltaRPeriodic semantics),
+// evaluated without FMA contraction so it matches the CPU oracle bit for bit.
+__device__ __forceinline__ void deltaExact(const double* pi, const double* pj, const BoxD& b, bool periodic, double d[3]) {
+    d[0] = __dsub_rn(pj[0], pi[0]); d[1] = __dsub_rn(pj[1], pi[1]); d[2] = __dsub_rn(pj[2], pi[2]);
+    if (periodic) {
+        double s = floor(__dadd_rn(__ddiv_rn(d[2], b.cz), 0.5));
+        d[0] = __dsub_rn(d[0], __dmul_rn(b.cx, s)); d[1] = __dsub_rn(d[1], __dmul_rn(b.cy, s)); d[2] = __dsub_rn(d[2], __dmul_rn(b.cz, s));
+        s = floor(__dadd_rn(__ddiv_rn(d[1], b.by), 0.5));
+        d[0] = __dsub_rn(d[0], __dmul_rn(b.bx, s)); d[1] = __dsub_rn(d[1], __dmul_rn(b.by, s));
+        s = floor(__dadd_rn(__ddiv_rn(d[0], b.ax), 0.5));
+        d[0] = __dsub_rn(d[0], __dmul_rn(b.ax, s));
+    }
+}
+__device__ __forceinline__ double dot3Exact(const double d[3]) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
+}
+
+#endif

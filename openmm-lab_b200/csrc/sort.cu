@@ -1,0 +1,202 @@
+// Spatial sort of the atoms (north-star subsystem 1a): bin into small cells ordered along a
+// Hilbert curve, counting-sort, then cut the sorted sequence into blocks of 32 atoms with
+// bounding boxes and block-local single-precision coordinates.
+//
+// The reference has no counterpart source for this stage: its CUDA platform leans on OpenMM's
+// CudaNonbondedUtilities / ComputeContext::reorderAtoms (un-vendored; call sites
+// platforms/cuda/src/CudaOpenMMLabKernels.cpp:736-758).  Written from the north-star description.
+#include "snb_core.cuh"
+#include "kernels.cuh"
+
+// ---- 1. cell assignment -------------------------------------------------------------
+// One thread per atom.  cellRank[] maps a linear cell index to its position along the Hilbert
+// curve (host-built table).  The slot within the cell comes from an atomic counter; the
+// within-cell order is made deterministic afterwards by sortCells.
+__global__ void k_assignCells(SortArgs a) {
+    int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (i >= a.numAtoms)
+        return;
+    double x = a.posd[3*i], y = a.posd[3*i+1], z = a.posd[3*i+2];
+    int c[3];
+    if (a.periodic) {
+        // fractional coordinates, frac = pos * recip (lower triangular)
+        double f[3];
+        f[0] = x*a.boxd.recip[0][0]+y*a.boxd.recip[1][0]+z*a.boxd.recip[2][0];
+        f[1] = y*a.boxd.recip[1][1]+z*a.boxd.recip[2][1];
+        f[2] = z*a.boxd.recip[2][2];
+        for (int d = 0; d < 3; d++) {
+            double w = f[d]-floor(f[d]);
+            c[d] = min(a.cellDim[d]-1, (int) (w*a.cellDim[d]));
+        }
+    }
+    else {
+        // non-periodic: the bounding box of all atoms was reduced into a.extent by k_extent
+        const double* e = a.extent;
+        double p[3] = {x, y, z};
+        for (int d = 0; d < 3; d++) {
+            double span = e[3+d]-e[d];
+            double w = span > 0 ? (p[d]-e[d])/span : 0.0;
+            c[d] = max(0, min(a.cellDim[d]-1, (int) (w*a.cellDim[d])));
+        }
+    }
+    int rank = a.cellRank[(c[0]*a.cellDim[1]+c[1])*a.cellDim[2]+c[2]];
+    a.atomCell[i] = rank;
+    a.atomSlot[i] = atomicAdd(&a.cellCount[rank], 1);
+}
+
+// bounding box of all atoms (non-periodic methods): extent[0..2] = min, [3..5] = max.
+// Ordered-int trick on doubles is avoided: two-stage reduction with one block.
+__global__ void k_extent(const double* posd, int numAtoms, double* extent) {
+    __shared__ double smin[3][256], smax[3][256];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = threadIdx.x; i < numAtoms; i += blockDim.x)
+        for (int d = 0; d < 3; d++) {
+            double v = posd[3*i+d];
+            lo[d] = fmin(lo[d], v);
+            hi[d] = fmax(hi[d], v);
+        }
+    for (int d = 0; d < 3; d++) { smin[d][threadIdx.x] = lo[d]; smax[d][threadIdx.x] = hi[d]; }
+    __syncthreads();
+    for (int s = blockDim.x/2; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int d = 0; d < 3; d++) {
+                smin[d][threadIdx.x] = fmin(smin[d][threadIdx.x], smin[d][threadIdx.x+s]);
+                smax[d][threadIdx.x] = fmax(smax[d][threadIdx.x], smax[d][threadIdx.x+s]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) {
+        extent[threadIdx.x] = smin[threadIdx.x][0];
+        extent[3+threadIdx.x] = smax[threadIdx.x][0];
+    }
+}
+
+// ---- 2. exclusive scan of the cell counts (single block, 1024 threads, tiled) ---------
+__global__ void k_scanCells(const int* __restrict__ count, int* __restrict__ start, int numCells) {
+    __shared__ int warpSums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x&31, warp = threadIdx.x>>5;
+    for (int base = 0; base < numCells; base += blockDim.x) {
+        int i = base+threadIdx.x;
+        int v = i < numCells ? count[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warpSums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warpSums[lane] = w;
+        }
+        __syncthreads();
+        int prefix = carry+(warp > 0 ? warpSums[warp-1] : 0)+incl-v;
+        if (i < numCells) start[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x-1) carry = prefix+v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        start[numCells] = carry;
+}
+
+// ---- 3. scatter + deterministic order inside each cell --------------------------------
+__global__ void k_scatterAtoms(SortArgs a) {
+    int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (i < a.numAtoms)
+        a.sortedAtom[a.cellStart[a.atomCell[i]]+a.atomSlot[i]] = i;
+    // padding slots of the last block
+    int pad = a.numAtoms+i;
+    if (i < a.paddedAtoms-a.numAtoms)
+        a.sortedAtom[pad] = -1;
+}
+
+__global__ void k_sortCells(SortArgs a) {
+    int c = blockIdx.x*blockDim.x+threadIdx.x;
+    if (c >= a.numCells)
+        return;
+    int s = a.cellStart[c], e = a.cellStart[c+1];
+    for (int i = s+1; i < e; i++) {
+        int v = a.sortedAtom[i], j = i-1;
+        while (j >= s && a.sortedAtom[j] > v) {
+            a.sortedAtom[j+1] = a.sortedAtom[j];
+            j--;
+        }
+        a.sortedAtom[j+1] = v;
+    }
+}
+
+// ---- 4. blocks of 32: bounding box, centre, local coordinates -------------------------
+// One warp per block.  Positions are wrapped into the unit cell in double (same floor as the
+// binning), the block centre is the middle of the axis-aligned bounding box, and every atom
+// stores its offset from that centre in single precision: |offset| < ~1 nm, so the absolute
+// coordinate error is ~3e-8 nm whatever the size of the system.
+__global__ void k_blockBounds(SortArgs a) {
+    int warp = (blockIdx.x*blockDim.x+threadIdx.x)>>5, lane = threadIdx.x&31;
+    if (warp >= a.numBlocks)
+        return;
+    int k = warp*SNB_BLOCK+lane;
+    int atom = a.sortedAtom[k];
+    double p[3] = {0, 0, 0};
+    float4 prm = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (atom >= 0) {
+        p[0] = a.posd[3*atom]; p[1] = a.posd[3*atom+1]; p[2] = a.posd[3*atom+2];
+        if (a.periodic) {
+            double fz = floor(p[2]*a.boxd.recip[2][2]);
+            double fy = floor(p[1]*a.boxd.recip[1][1]+p[2]*a.boxd.recip[2][1]);
+            double fx = floor(p[0]*a.boxd.recip[0][0]+p[1]*a.boxd.recip[1][0]+p[2]*a.boxd.recip[2][0]);
+            p[0] -= fx*a.boxd.ax+fy*a.boxd.bx+fz*a.boxd.cx;
+            p[1] -= fy*a.boxd.by+fz*a.boxd.cy;
+            p[2] -= fz*a.boxd.cz;
+        }
+        prm = a.params4[atom];
+        a.sortedPos[atom] = k;
+    }
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) {
+        lo[d] = atom >= 0 ? p[d] : 1e300;
+        hi[d] = atom >= 0 ? p[d] : -1e300;
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    }
+    double c[3];
+    for (int d = 0; d < 3; d++)
+        c[d] = 0.5*(lo[d]+hi[d]);
+    float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (atom >= 0)
+        pl = make_float4((float) (p[0]-c[0]), (float) (p[1]-c[1]), (float) (p[2]-c[2]), prm.x*a.sqrtK);
+    a.posqLocal[k] = pl;
+    float sig = prm.y, eps = prm.z;
+    a.sparams[k] = make_float4(sig, eps, prm.w, 8.0f*sig*sig*sig*eps);
+    if (lane == 0) {
+        a.blockCenter[3*warp] = c[0]; a.blockCenter[3*warp+1] = c[1]; a.blockCenter[3*warp+2] = c[2];
+        // half extents, rounded up so the box is conservative in single precision
+        a.blockExt[warp] = make_float4(__double2float_ru(0.5*(hi[0]-lo[0])), __double2float_ru(0.5*(hi[1]-lo[1])),
+                                       __double2float_ru(0.5*(hi[2]-lo[2])), 0.f);
+        if (a.checkShift && (0.5*(hi[0]-lo[0]) >= a.shiftLimit[0] || 0.5*(hi[1]-lo[1]) >= a.shiftLimit[1] || 0.5*(hi[2]-lo[2]) >= a.shiftLimit[2]))
+            a.counters[4] = 1;
+    }
+}
+
+void launchSort(const SortArgs& a, cudaStream_t stream) {
+    int threads = 256;
+    int atomBlocks = (a.paddedAtoms+threads-1)/threads;
+    cudaMemsetAsync(a.cellCount, 0, sizeof(int)*a.numCells, stream);
+    if (!a.periodic)
+        k_extent<<<1, 256, 0, stream>>>(a.posd, a.numAtoms, a.extent);
+    k_assignCells<<<atomBlocks, threads, 0, stream>>>(a);
+    k_scanCells<<<1, 1024, 0, stream>>>(a.cellCount, a.cellStart, a.numCells);
+    k_scatterAtoms<<<atomBlocks, threads, 0, stream>>>(a);
+    k_sortCells<<<(a.numCells+threads-1)/threads, threads, 0, stream>>>(a);
+    k_blockBounds<<<(a.numBlocks*32+threads-1)/threads, threads, 0, stream>>>(a);
+}

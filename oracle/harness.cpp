@@ -411,16 +411,18 @@ void buildNeighborList(const Oracle& o, const double* pos, const double box[3][3
                 int i = order[a];
                 for (int b = (c2 == c ? a+1 : cellStart[c2]); b < cellStart[c2+1]; b++) {
                     int j = order[b];
+                    // the displacement is always taken from the lower to the higher index, so that the
+                    // predicate is a function of the unordered pair (the CUDA path does the same)
+                    int lo_ = std::min(i, j), hi_ = std::max(i, j);
                     double d[3];
                     if (periodic)
-                        deltaPeriodic(pos+3*i, pos+3*j, box, d);
+                        deltaPeriodic(pos+3*lo_, pos+3*hi_, box, d);
                     else {
-                        d[0] = pos[3*j]-pos[3*i]; d[1] = pos[3*j+1]-pos[3*i+1]; d[2] = pos[3*j+2]-pos[3*i+2];
+                        d[0] = pos[3*hi_]-pos[3*lo_]; d[1] = pos[3*hi_+1]-pos[3*lo_+1]; d[2] = pos[3*hi_+2]-pos[3*lo_+2];
                     }
                     double r2 = d[0]*d[0]+d[1]*d[1]+d[2]*d[2];
                     if (r2 > cutoff2)
                         continue;
-                    int lo_ = std::min(i, j), hi_ = std::max(i, j);
                     if (!o.exclusions[lo_].empty() && o.exclusions[lo_].count(hi_))
                         continue;
                     out.push_back(std::make_pair(lo_, hi_));

@@ -1,0 +1,123 @@
+"""Parity of the CUDA path (platform "B200", through the C-ABI) with the CPU oracle on the same
+seeded inputs: bit-exact interacting-pair sets, and total energy / per-slice energies / derivatives /
+forces within 1e-5 by the reference's own metric (north-star tolerance, mixed precision)."""
+import numpy as np
+import pytest
+
+import openmmlab_b200 as mm
+from openmmlab_b200 import SlicedNonbondedForce as F
+from openmmlab_b200 import systems
+
+from util import assert_parity, evaluate
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # BASELINE.json north_star: "within 1e-5 relative error in mixed precision"
+
+
+def _check(w, tol=TOL, pairs=True, **kw):
+    ref = evaluate("Reference", w, pairs=pairs and w.force.getNonbondedMethod() != F.NoCutoff, **kw)
+    got = evaluate("B200", w, pairs=pairs and kw.get("direct", True), **kw)
+    if pairs and kw.get("direct", True) and "pairs" in ref:
+        assert ref["pairs"].shape == got["pairs"].shape, "pair count %d vs %d" % (len(ref["pairs"]), len(got["pairs"]))
+        assert np.array_equal(ref["pairs"], got["pairs"]), "interacting pair sets differ"
+    return assert_parity(ref, got, tol, w.name)
+
+
+@pytest.mark.parametrize("method", [F.CutoffPeriodic, F.PME])
+def test_water_box(method):
+    # BASELINE.json configs[0]: 648-atom water box, 2 subsets, CutoffPeriodic and PME
+    _check(systems.water_box(method=method))
+
+
+@pytest.mark.parametrize("direct,reciprocal", [(True, False), (False, True)])
+def test_water_box_direct_reciprocal_split(direct, reciprocal):
+    _check(systems.water_box(), direct=direct, reciprocal=reciprocal)
+
+
+@pytest.mark.parametrize("method", [F.CutoffPeriodic, F.PME, F.LJPME])
+@pytest.mark.parametrize("groups", [1, 2, 3])
+def test_small_mixed(method, groups):
+    kw = {}
+    if method == F.LJPME:
+        kw["ljpme"] = (systems.ALPHA, 12, 12, 12)
+    scaling = [("lam_a", 0.3, 0, 1, True, True), ("lam_b", 0.65, 1, 1, True, False)]
+    if groups >= 2:
+        scaling.append(("lam_c", 0.9, 0, 2, False, True))
+    w = systems.small_mixed(method=method, num_groups=groups, scaling=scaling, derivatives=["lam_a", "lam_b"], **kw)
+    _check(w)
+
+
+def test_switching_function():
+    w = systems.small_mixed(method=F.PME, switch=0.75, scaling=[("lam", 0.5, 0, 1, True, True)], derivatives=["lam"])
+    _check(w)
+    w = systems.small_mixed(method=F.CutoffPeriodic, switch=0.8, dispersion_correction=True)
+    _check(w)
+
+
+def test_nonperiodic_methods():
+    for method in (F.NoCutoff, F.CutoffNonPeriodic):
+        w = systems.small_mixed(method=method, scaling=[("lam", 0.5, 0, 1, True, True)], derivatives=["lam"])
+        _check(w)
+
+
+def test_triclinic():
+    w = systems.small_mixed(method=F.PME, scaling=[("lam", 0.5, 0, 1, True, True)], derivatives=["lam"])
+    L = w.box[0][0]
+    box = np.array([[L, 0, 0], [0.25*L, L, 0], [-0.15*L, 0.3*L, L]]).astype(np.float32).astype(np.float64)
+    w.box = box
+    w.system.setDefaultPeriodicBoxVectors(*box)
+    _check(w)
+
+
+def test_periodic_exceptions_and_many_subsets():
+    w = systems.small_mixed(method=F.PME, num_groups=5, scaling=[("lam", 0.5, 2, 4, True, True)], derivatives=["lam"])
+    w.force.setExceptionsUsePeriodicBoundaryConditions(True)
+    _check(w)
+
+
+def test_fep_ljpme():
+    # BASELINE.json configs[3]
+    _check(systems.fep_ligand())
+
+
+def test_dhfr_size():
+    # BASELINE.json configs[1]
+    _check(systems.dhfr_like())
+
+
+def test_lambda_changes_and_offsets():
+    w = systems.small_mixed(method=F.PME, scaling=[("lam", 0.5, 0, 1, True, True)], derivatives=["lam"])
+    w.force.addGlobalParameter("off", 0.0)
+    w.force.addParticleParameterOffset("off", 3, 0.2, 0.01, 0.1)
+    w.force.addParticleParameterOffset("off", 40, -0.2, 0.0, 0.05)
+    for lam, off in ((0.0, 0.0), (1.0, 0.5), (0.37, 1.0)):
+        _check(w, parameters={"lam": lam, "off": off})
+
+
+def test_update_parameters():
+    w = systems.water_box()
+    results = {}
+    for platform in ("Reference", "B200"):
+        ctx = mm.Context(w.system, platform)
+        ctx.setPositions(w.positions)
+        ctx.getState()
+        for i in range(0, w.num_particles, 5):
+            q, s, e = w.force.getParticleParameters(i)
+            w.force.setParticleParameters(i, 1.5*q, 1.1*s, 1.7*e)
+        w.force.updateParametersInContext(ctx)
+        st = ctx.getState(mm.State.Energy | mm.State.Forces | mm.State.ParameterDerivatives)
+        results[platform] = {"energy": st.getPotentialEnergy(), "forces": st.getForces(), "derivs": st.getEnergyParameterDerivatives(),
+                             "slices": ctx._kernels[0][1].sliceEnergies.copy()}
+        for i in range(0, w.num_particles, 5):
+            q, s, e = w.force.getParticleParameters(i)
+            w.force.setParticleParameters(i, q/1.5, s/1.1, e/1.7)
+    assert_parity(results["Reference"], results["B200"], TOL, "updated parameters")
+
+
+def test_deterministic_forces():
+    # fixed-point accumulation: two evaluations give bit-identical forces (reference test idea:
+    # platforms/cuda/tests/TestCudaSlicedNonbondedForce.cpp:109-141)
+    w = systems.water_box()
+    a = evaluate("B200", w)
+    b = evaluate("B200", w)
+    assert np.array_equal(a["forces"], b["forces"])

@@ -44,3 +44,39 @@ def max_force_error(expected, found):
 
 def rel_err(expected, found):
     return abs(expected-found)/max(abs(expected), 1.0)
+
+
+def evaluate(platform, w, direct=True, reciprocal=True, forces=True, energy=True, parameters=None, pairs=False):
+    """One kernel.execute on `platform` for workload `w`; returns energies, forces, derivatives (and pairs)."""
+    import openmmlab_b200 as mm
+    ctx = mm.Context(w.system, platform)
+    ctx.setPositions(w.positions)
+    if w.box is not None:
+        ctx.setPeriodicBoxVectors(*w.box)
+    for k, v in dict(w.parameters, **(parameters or {})).items():
+        ctx.setParameter(k, v)
+    kernel = ctx._kernels[0][1]
+    ctx._forces = np.zeros((w.num_particles, 3))
+    ctx._energyParameterDerivatives = {}
+    e = kernel.execute(ctx, forces, energy, direct, reciprocal)
+    out = {"energy": e, "forces": ctx._forces.copy(), "slices": kernel.sliceEnergies.copy(),
+           "derivs": dict(ctx._energyParameterDerivatives), "kernel": kernel, "context": ctx}
+    if pairs:
+        out["pairs"] = kernel.dumpPairs()
+    return out
+
+
+def assert_parity(ref, got, tol=1e-5, what=""):
+    """The reference's own metric (AssertionUtilities.h:7-37) on total energy, every slice energy,
+    every derivative and every force component."""
+    assert rel_err(ref["energy"], got["energy"]) <= tol, "%s energy %r vs %r" % (what, ref["energy"], got["energy"])
+    for s in range(ref["slices"].shape[0]):
+        for t in range(2):
+            assert rel_err(ref["slices"][s, t], got["slices"][s, t]) <= tol, \
+                "%s slice %d term %d: %r vs %r" % (what, s, t, ref["slices"][s, t], got["slices"][s, t])
+    assert set(ref["derivs"]) == set(got["derivs"])
+    for k in ref["derivs"]:
+        assert rel_err(ref["derivs"][k], got["derivs"][k]) <= tol, "%s derivative %s: %r vs %r" % (what, k, ref["derivs"][k], got["derivs"][k])
+    err = max_force_error(ref["forces"], got["forces"])
+    assert err <= tol, "%s max force error %g > %g" % (what, err, tol)
+    return err
