@@ -770,6 +770,13 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
     }
     h.countersOut[1] = h.hCounters.p[0];
     h.countersOut[3] = h.hCounters.p[1];
+    // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
+    long long launches = 0;
+    if (includeDirect) launches += (periodic ? 5 : 6)+1+1+(h.X > 0 ? 1 : 0);
+    if (includeRecip && pmeFamily) launches += 3*(h.method == SNB_LJPME ? 2 : 1);
+    if (includeForces) launches += 1;
+    if (!hostPositions) launches += 1;
+    h.countersOut[2] = launches;
     return true;
 }
 
@@ -954,6 +961,30 @@ int snb_dump_pairs(snb_handle* h, int32_t** pairs, int64_t* num_pairs) {
 }
 
 void snb_free(void* p) { free(p); }
+
+/* debugging aid: print the sorted order and the tile list of the last execute (small systems) */
+int snb_debug_dump(snb_handle* h) {
+    SNB_TRY
+    std::vector<int> sa(h->NP), cnt(8);
+    std::vector<float4> sp(h->NP), pq(h->NP);
+    CUDA_CHECK(cudaMemcpy(sa.data(), h->sortedAtom.p, sizeof(int)*h->NP, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(sp.data(), h->sparams.p, sizeof(float4)*h->NP, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(pq.data(), h->posqLocal.p, sizeof(float4)*h->NP, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(cnt.data(), h->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost));
+    printf("counters:"); for (int k = 0; k < 8; k++) printf(" %d", cnt[k]); printf("\n");
+    for (int k = 0; k < std::min(h->NP, 64); k++) {
+        int sub; memcpy(&sub, &sp[k].z, 4);
+        printf("k=%d atom=%d local=(%g %g %g) q=%g sig=%g eps=%g subset=%d\n", k, sa[k], pq[k].x, pq[k].y, pq[k].z, pq[k].w, sp[k].x, sp[k].y, sub);
+    }
+    int nch = std::min(cnt[0], 4);
+    std::vector<int2> jl(32*(size_t) std::max(nch, 1));
+    CUDA_CHECK(cudaMemcpy(jl.data(), h->jList.p, sizeof(int2)*32*nch, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < nch; c++)
+        for (int l = 0; l < 32; l++)
+            printf("chunk %d slot %d j=%d mask=%08x\n", c, l, jl[32*c+l].x, (unsigned) jl[32*c+l].y);
+    return SNB_OK;
+    SNB_CATCH
+}
 
 int snb_set_timing(snb_handle* h, int enabled) { h->timing = enabled != 0; return SNB_OK; }
 

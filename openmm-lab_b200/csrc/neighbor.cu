@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
         unsigned mask = full<<lane;
         if (atomJ >= 0)
             mask |= exclusionMask(atomJ, I, a);
-        buf[lane] = make_int2(atomJ >= 0 ? j : -1, (int) mask);
+        buf[lane] = atomJ >= 0 ? make_int2(j, (int) mask) : make_int2(-1, -1);
         int count = 32;
         for (int J0 = I+1; J0 < a.numBlocks; J0 += 32) {
             int J = J0+lane;

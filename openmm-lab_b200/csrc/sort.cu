@@ -146,7 +146,7 @@ __global__ void k_blockBounds(SortArgs a) {
     int k = warp*SNB_BLOCK+lane;
     int atom = a.sortedAtom[k];
     double p[3] = {0, 0, 0};
-    float4 prm = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    float4 prm = make_float4(0.f, 0.f, 0.f, 0.f);
     if (atom >= 0) {
         p[0] = a.posd[3*atom]; p[1] = a.posd[3*atom+1]; p[2] = a.posd[3*atom+2];
         if (a.periodic) {
@@ -177,7 +177,11 @@ __global__ void k_blockBounds(SortArgs a) {
         pl = make_float4((float) (p[0]-c[0]), (float) (p[1]-c[1]), (float) (p[2]-c[2]), prm.x*a.sqrtK);
     a.posqLocal[k] = pl;
     float sig = prm.y, eps = prm.z;
-    a.sparams[k] = make_float4(sig, eps, prm.w, 8.0f*sig*sig*sig*eps);
+    // the subset travels as raw int bits (-1 = padding lane); stored through an int view so that no
+    // floating-point move can canonicalise the bit pattern
+    int4 sp = make_int4(__float_as_int(sig), __float_as_int(eps), atom >= 0 ? __float_as_int(prm.w) : -1,
+                        __float_as_int(8.0f*sig*sig*sig*eps));
+    reinterpret_cast<int4*>(a.sparams)[k] = sp;
     if (lane == 0) {
         a.blockCenter[3*warp] = c[0]; a.blockCenter[3*warp+1] = c[1]; a.blockCenter[3*warp+2] = c[2];
         // half extents, rounded up so the box is conservative in single precision
