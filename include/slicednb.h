@@ -68,9 +68,12 @@ enum {
     SNB_ERR_UNSUPPORTED = 7
 };
 
-/* creation flags (product only; ignored by the oracle) */
+/* creation flags (product only; ignored by the oracle).  They mirror the platform properties the
+ * reference's CUDA platform reads (platforms/cuda/src/CudaOpenMMLabKernels.cpp:483,496):
+ * Precision = mixed (default) | double, and DeterministicForces. */
 enum {
-    SNB_FLAG_DETERMINISTIC = 1  /* reserved: forces are always accumulated in 64-bit fixed point */
+    SNB_FLAG_DETERMINISTIC = 1,     /* PME spreading in 64-bit fixed point: bit-reproducible forces      */
+    SNB_FLAG_DOUBLE_PRECISION = 2   /* all pair / grid arithmetic in FP64 (implies deterministic)        */
 };
 
 typedef struct snb_desc {

@@ -91,9 +91,12 @@ class State:
 
 
 class Context:
-    def __init__(self, system, platform):
+    def __init__(self, system, platform, properties=None):
         self._system = system
         self._platform = Platform.getPlatformByName(platform) if isinstance(platform, str) else platform
+        # platform properties of this Context (OpenMM: Context(system, integrator, platform, properties))
+        self._properties = dict(self._platform._properties)
+        self._properties.update(properties or {})
         self._positions = np.zeros((system.getNumParticles(), 3))
         self._parameters = {}
         self._initialize()

@@ -143,9 +143,8 @@ struct PmeGrid {
     double alpha = 0;
     cufftHandle fwd = 0, inv = 0;
     bool planned = false;
-    DevBuf<float> real;
-    DevBuf<float2> cplx;
-    DevBuf<float> eterm;
+    DevBuf<char> real, cplx, eterm;     // float or double, by the handle's precision
+    DevBuf<long long> fixed;            // deterministic spreading
     DevBuf<double> moduli[3];
     double etermBox[6] = {0, 0, 0, 0, 0, 0};
     bool etermValid = false;
@@ -159,6 +158,8 @@ struct snb_handle {
     int N = 0, NP = 0, NB = 0, S = 1, L = 1, G = 0, method = 0, device = 0;
     double cutoff = 1, switchDist = 0, rfDielectric = 78.3, alpha = 0, dalpha = 0;
     bool useSwitch = false, exceptionsPeriodic = false, useDispersion = false;
+    bool doublePrecision = false, deterministic = false;
+    int itemChunks = SNB_ITEM_CHUNKS;
     int grid[3] = {0, 0, 0}, dgrid[3] = {0, 0, 0};
     std::vector<int> subsets;
     std::vector<std::array<double, 3>> baseParticle;          // q, sigma, eps
@@ -185,6 +186,7 @@ struct snb_handle {
     int numSMs = 148;
     DevBuf<double> posd, paramsD, exception14, blockCenter, extent, energyBuf, forcesOutD;
     DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn;
+    DevBuf<double4> posqLocalD, sparamsD;
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
                 exclStart, exclList, is14D, counters;
     DevBuf<int2> exceptionAtomsD, jList;
@@ -314,12 +316,15 @@ void setupPme(snb_handle& h, PmeGrid& g, const int n[3], double alpha) {
     g.alpha = alpha;
     for (int k = 0; k < 3; k++) g.n[k] = n[k];
     size_t G = (size_t) n[0]*n[1]*n[2], GC = (size_t) n[0]*n[1]*(n[2]/2+1);
-    g.real.alloc(G*h.S);
-    g.cplx.alloc(GC*h.S);
-    g.eterm.alloc(GC);
+    const size_t rb = h.doublePrecision ? 8 : 4;
+    g.real.alloc(G*h.S*rb);
+    g.cplx.alloc(GC*h.S*2*rb);
+    g.eterm.alloc(GC*rb);
+    if (h.deterministic)
+        g.fixed.alloc(G*h.S);
     int dims[3] = {n[0], n[1], n[2]};
-    CUFFT_CHECK(cufftPlanMany(&g.fwd, 3, dims, nullptr, 1, (int) G, nullptr, 1, (int) GC, CUFFT_R2C, h.S));
-    CUFFT_CHECK(cufftPlanMany(&g.inv, 3, dims, nullptr, 1, (int) GC, nullptr, 1, (int) G, CUFFT_C2R, h.S));
+    CUFFT_CHECK(cufftPlanMany(&g.fwd, 3, dims, nullptr, 1, (int) G, nullptr, 1, (int) GC, h.doublePrecision ? CUFFT_D2Z : CUFFT_R2C, h.S));
+    CUFFT_CHECK(cufftPlanMany(&g.inv, 3, dims, nullptr, 1, (int) GC, nullptr, 1, (int) G, h.doublePrecision ? CUFFT_Z2D : CUFFT_C2R, h.S));
     g.planned = true;
     CUFFT_CHECK(cufftSetStream(g.fwd, h.stream));
     CUFFT_CHECK(cufftSetStream(g.inv, h.stream));
@@ -336,6 +341,8 @@ snb_handle* createHandle(const snb_desc& d) {
     snb_handle& h = *hp;
     try {
         h.device = d.device_index;
+        h.doublePrecision = (d.flags&SNB_FLAG_DOUBLE_PRECISION) != 0;
+        h.deterministic = h.doublePrecision || (d.flags&SNB_FLAG_DETERMINISTIC) != 0;
         CUDA_CHECK(cudaSetDevice(h.device));
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, h.device));
@@ -418,6 +425,7 @@ snb_handle* createHandle(const snb_desc& d) {
         h.atomCell.alloc(h.N); h.atomSlot.alloc(h.N);
         h.sortedAtom.alloc(h.NP); h.sortedPos.alloc(h.N);
         h.posqLocal.alloc(h.NP); h.sparams.alloc(h.NP);
+        if (h.doublePrecision) { h.posqLocalD.alloc(h.NP); h.sparamsD.alloc(h.NP); }
         h.blockCenter.alloc(3*(size_t) h.NB); h.blockExt.alloc(h.NB);
         h.extent.alloc(6);
         h.energyBuf.alloc(2*SNB_MAX_SLICES);
@@ -632,7 +640,8 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         sa.counters = h.counters.p;
         sa.sqrtK = (float) sqrt(SNB_ONE_4PI_EPS0);
         sa.boxd = bd;
-        sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
+        sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.paramsD = h.paramsD.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
+        sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
         sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p;
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p;
@@ -655,23 +664,22 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
 
         DirectParams& p = da.p;
         p.numAtoms = h.N; p.numBlocks = h.NB; p.pbcMode = pbcMode; p.periodic = periodic;
-        p.cutoff2 = (float) (h.cutoff*h.cutoff);
         p.cutoff2d = h.cutoff*h.cutoff;
         p.bandTol = (float) (4e-5*h.cutoff*h.cutoff);
-        p.alpha = (float) h.alpha; p.alpha2 = (float) (h.alpha*h.alpha);
-        p.twoAlphaOverSqrtPi = (float) (2.0*h.alpha/sqrt(M_PI));
-        p.krf = (float) (pow(h.cutoff, -3.0)*(h.rfDielectric-1.0)/(2.0*h.rfDielectric+1.0));
-        p.crf = (float) ((1.0/h.cutoff)*(3.0*h.rfDielectric)/(2.0*h.rfDielectric+1.0));
-        p.switchDist = (float) h.switchDist;
-        p.invSwitchWidth = h.useSwitch ? (float) (1.0/(h.cutoff-h.switchDist)) : 0.f;
+        p.alphad = h.alpha;
+        p.krfd = pow(h.cutoff, -3.0)*(h.rfDielectric-1.0)/(2.0*h.rfDielectric+1.0);
+        p.crfd = (1.0/h.cutoff)*(3.0*h.rfDielectric)/(2.0*h.rfDielectric+1.0);
+        p.switchDistd = h.switchDist;
+        p.invSwitchWidthd = h.useSwitch ? 1.0/(h.cutoff-h.switchDist) : 0.0;
         double dc2 = h.dalpha*h.cutoff*h.dalpha*h.cutoff;
-        p.dalpha2 = (float) (h.dalpha*h.dalpha);
-        p.dispShiftExp = (float) (1.0-exp(-dc2)*(1.0+dc2+0.5*dc2*dc2));
-        p.invCut6 = (float) pow(h.cutoff, -6.0);
-        for (int s = 0; s < h.L; s++) { p.lambdaC[s] = (float) h.lambdaC[s]; p.lambdaV[s] = (float) h.lambdaV[s]; }
-        p.box = bf; p.boxd = bd;
+        p.dalphad = h.dalpha;
+        p.dispShiftExpd = 1.0-exp(-dc2)*(1.0+dc2+0.5*dc2*dc2);
+        p.invCut6d = pow(h.cutoff, -6.0);
+        for (int s = 0; s < h.L; s++) { p.lambdaCd[s] = h.lambdaC[s]; p.lambdaVd[s] = h.lambdaV[s]; }
+        p.boxd = bd;
         da.kind = h.method == SNB_NO_CUTOFF ? KIND_PLAIN : h.method <= SNB_CUTOFF_PERIODIC ? KIND_RF : h.method == SNB_LJPME ? KIND_LJPME : KIND_EWALD;
-        da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy;
+        da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
+        da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
         da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
         da.blockCenter = h.blockCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.workItems = h.workItems.p;
         da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
@@ -703,25 +711,28 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
             memset(&pa, 0, sizeof(pa));
             pa.numAtoms = h.N; pa.numSubsets = h.S; pa.term = term;
             pa.nx = g.n[0]; pa.ny = g.n[1]; pa.nz = g.n[2];
-            pa.alpha = g.alpha; pa.boxd = bd; pa.posd = h.posd.p;
+            pa.alpha = g.alpha; pa.boxd = bd; pa.posd = h.posd.p; pa.doublePrecision = h.doublePrecision;
             pa.sortedAtom = includeDirect ? h.sortedAtom.p : nullptr;
-            pa.params4 = h.params4.p; pa.grid = g.real.p; pa.cgrid = g.cplx.p; pa.eterm = g.eterm.p;
+            pa.params4 = h.params4.p; pa.paramsD = h.paramsD.p; pa.grid = g.real.p; pa.cgrid = g.cplx.p; pa.eterm = g.eterm.p;
+            pa.gridFixed = h.deterministic ? g.fixed.p : nullptr;
             for (int k = 0; k < 3; k++) pa.moduli[k] = g.moduli[k].p;
-            for (int s = 0; s < h.L; s++) pa.lambda[s] = (float) (term == 0 ? h.lambdaC[s] : h.lambdaV[s]);
+            for (int s = 0; s < h.L; s++) pa.lambda[s] = term == 0 ? h.lambdaC[s] : h.lambdaV[s];
             pa.forceOrig = h.forceOrig.p; pa.paddedAtoms = h.NP; pa.energyBuf = h.energyBuf.p;
             double key[6] = {bd.ax, bd.bx, bd.by, bd.cx, bd.cy, bd.cz};
             if (!g.etermValid || memcmp(key, g.etermBox, sizeof(key)) != 0) {
-                launchPmeEterm(pa, g.eterm.p, st);
+                launchPmeEterm(pa, st);
                 memcpy(g.etermBox, key, sizeof(key));
                 g.etermValid = true;
             }
             launchPmeSpread(pa, st);
             if (term == 0) tm.mark(5);
-            CUFFT_CHECK(cufftExecR2C(g.fwd, g.real.p, (cufftComplex*) g.cplx.p));
+            if (h.doublePrecision) CUFFT_CHECK(cufftExecD2Z(g.fwd, (double*) g.real.p, (cufftDoubleComplex*) g.cplx.p));
+            else CUFFT_CHECK(cufftExecR2C(g.fwd, (float*) g.real.p, (cufftComplex*) g.cplx.p));
             if (term == 0) tm.mark(6);
             launchPmeConvolution(pa, st);
             if (term == 0) tm.mark(7);
-            CUFFT_CHECK(cufftExecC2R(g.inv, (cufftComplex*) g.cplx.p, g.real.p));
+            if (h.doublePrecision) CUFFT_CHECK(cufftExecZ2D(g.inv, (cufftDoubleComplex*) g.cplx.p, (double*) g.real.p));
+            else CUFFT_CHECK(cufftExecC2R(g.inv, (cufftComplex*) g.cplx.p, (float*) g.real.p));
             launchPmeInterpolate(pa, st);
             if (term == 0) tm.mark(8);
         }
@@ -773,7 +784,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
     if (includeDirect) launches += (periodic ? 5 : 6)+1+1+(h.X > 0 ? 1 : 0);
-    if (includeRecip && pmeFamily) launches += 3*(h.method == SNB_LJPME ? 2 : 1);
+    if (includeRecip && pmeFamily) launches += (h.deterministic ? 4 : 3)*(h.method == SNB_LJPME ? 2 : 1);
     if (includeForces) launches += 1;
     if (!hostPositions) launches += 1;
     h.countersOut[2] = launches;

@@ -20,18 +20,55 @@
 
 template <int KIND> void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid);
 
-template <int NSUB> struct SubsetTable {
+// Precision traits: R = float is the mixed-precision path (FP32 pair arithmetic, MUFU rsqrt/ex2,
+// polynomial erfc); R = double is the double-precision mode (the analogue of the reference CUDA
+// platform's Precision=double), used to prove parity to 1e-5 on every quantity.
+template <typename R> struct Real;
+template <> struct Real<float> {
+    typedef float4 vec4;
+    static __device__ __forceinline__ const float4* pos(const DirectArgs& a) { return a.posqLocal; }
+    static __device__ __forceinline__ const float4* prm(const DirectArgs& a) { return a.sparams; }
+    static __device__ __forceinline__ float rsqrt(float r2) {
+        // MUFU.RSQ (2 ulp) + one Newton step: the LJ force goes as invR^14, so the seed's error
+        // would otherwise dominate the pair error
+        float y = fastRsqrt(r2);
+        return y*fmaf(-0.5f*r2, y*y, 1.5f);
+    }
+    static __device__ __forceinline__ float expNeg(float x) { return fastExp2(-1.4426950408889634f*x); }    // exp(-x)
+    static __device__ __forceinline__ void erfcTerms(float ar, float a2r2, float& ex, float& erfcAR) {
+        ex = expNeg(a2r2);
+        erfcAR = ex*erfcxPoly(ar);
+    }
+    static __device__ __forceinline__ float rint(float x) { return rintf(x); }
+    static __device__ __forceinline__ long long fixed(float f) { return toFixed(f); }
+};
+template <> struct Real<double> {
+    typedef double4 vec4;
+    static __device__ __forceinline__ const double4* pos(const DirectArgs& a) { return a.posqLocalD; }
+    static __device__ __forceinline__ const double4* prm(const DirectArgs& a) { return a.sparamsD; }
+    static __device__ __forceinline__ double rsqrt(double r2) { return 1.0/sqrt(r2); }
+    static __device__ __forceinline__ double expNeg(double x) { return exp(-x); }
+    static __device__ __forceinline__ void erfcTerms(double ar, double a2r2, double& ex, double& erfcAR) {
+        ex = exp(-a2r2);
+        erfcAR = erfc(ar);
+    }
+    static __device__ __forceinline__ double rint(double x) { return ::rint(x); }
+    static __device__ __forceinline__ long long fixed(double f) { return toFixedD(f); }
+};
+
+template <typename R, int NSUB> struct SubsetTable {
     // lambda and energy tables indexed by the j atom's subset (the i subset is fixed per lane)
-    float lamC[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS], lamV[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS];
-    float eC[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS], eV[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS];
+    R lamC[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS], lamV[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS];
+    R eC[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS], eV[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS];
     double EC[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS], EV[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS];
 };
 
-template <int KIND, int PBC, int NSUB, bool ENERGY>
+template <typename R, int KIND, int PBC, int NSUB, bool ENERGY>
 __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
     constexpr int NS = NSUB > 0 ? NSUB : SNB_MAX_SUBSETS;
-    __shared__ float4 sPos[DIRECT_WARPS][32];
-    __shared__ float4 sPrm[DIRECT_WARPS][32];
+    typedef typename Real<R>::vec4 vec4;
+    __shared__ vec4 sPos[DIRECT_WARPS][32];
+    __shared__ vec4 sPrm[DIRECT_WARPS][32];
     __shared__ int2 sEnt[DIRECT_WARPS][32];
     __shared__ double sEnergy[2*SNB_MAX_SLICES];
     const int lane = threadIdx.x&31, w = threadIdx.x>>5;
@@ -40,6 +77,13 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
     const int numSub = NSUB > 0 ? NSUB : a.numSubsets;
     const bool SWITCH = a.useSwitch != 0, DUMP = a.pairDump != nullptr;
     const int numItems = a.counters[1];
+    const R cutoff2 = (R) p.cutoff2d, bandTol = (R) p.bandTol;
+    const R alpha = (R) p.alphad, alpha2 = alpha*alpha, twoAlphaOverSqrtPi = (R) (2.0*p.alphad/1.772453850905516);
+    const R krf = (R) p.krfd, crf = (R) p.crfd;
+    const R switchDist = (R) p.switchDistd, invSwitchWidth = (R) p.invSwitchWidthd;
+    const R dalpha2 = (R) (p.dalphad*p.dalphad), dispShiftExp = (R) p.dispShiftExpd, invCut6 = (R) p.invCut6d;
+    const R bAx = (R) p.boxd.ax, bBy = (R) p.boxd.by, bCz = (R) p.boxd.cz;
+    const R iAx = (R) (1.0/p.boxd.ax), iBy = (R) (1.0/p.boxd.by), iCz = (R) (1.0/p.boxd.cz);
     if (ENERGY) {
         for (int k = threadIdx.x; k < 2*SNB_MAX_SLICES; k += blockDim.x)
             sEnergy[k] = 0.0;
@@ -56,37 +100,38 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
         const int4 wi = a.workItems[item];
         const int I = wi.x;
         const int ki = I*32+lane;
-        const float4 pi = a.posqLocal[ki];
-        const float4 si4 = a.sparams[ki];
-        const int subI = __float_as_int(si4.z);
+        const vec4 pi = Real<R>::pos(a)[ki];
+        const vec4 si4 = Real<R>::prm(a)[ki];
+        const int subI = (int) si4.z;           // subsets travel as exact small reals, -1 = padding lane
         const bool iValid = subI >= 0;
         const int origI = a.sortedAtom[ki];
         const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
-        SubsetTable<NSUB> t;
+        SubsetTable<R, NSUB> t;
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             int sl = sliceOf(max(subI, 0), s);
-            t.lamC[s] = s < numSub ? p.lambdaC[sl] : 0.f;
-            t.lamV[s] = s < numSub ? p.lambdaV[sl] : 0.f;
+            t.lamC[s] = s < numSub ? (R) p.lambdaCd[sl] : (R) 0;
+            t.lamV[s] = s < numSub ? (R) p.lambdaVd[sl] : (R) 0;
             t.EC[s] = t.EV[s] = 0.0;
         }
         double Fx = 0, Fy = 0, Fz = 0;
         for (int c = 0; c < wi.z; c++) {
             // ---- gather and stage the chunk's j atoms -------------------------------------
             const int2 ent = a.jList[(size_t) (wi.y+c)*32+lane];
-            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f), sj4 = make_float4(0.f, 0.f, __int_as_float(0), 0.f);
+            vec4 pj, sj4;
+            pj.x = pj.y = pj.z = pj.w = 0; sj4.x = sj4.y = sj4.z = sj4.w = 0;
             if (ent.x >= 0) {
-                pj = a.posqLocal[ent.x];
-                sj4 = a.sparams[ent.x];
+                pj = Real<R>::pos(a)[ent.x];
+                sj4 = Real<R>::prm(a)[ent.x];
                 const int J = ent.x>>5;
-                float ox = (float) (a.blockCenter[3*J]-cIx), oy = (float) (a.blockCenter[3*J+1]-cIy), oz = (float) (a.blockCenter[3*J+2]-cIz);
+                R ox = (R) (a.blockCenter[3*J]-cIx), oy = (R) (a.blockCenter[3*J+1]-cIy), oz = (R) (a.blockCenter[3*J+2]-cIz);
                 pj.x += ox; pj.y += oy; pj.z += oz;
                 if (PBC == PBC_SHIFT) {
                     // one image per j atom, chosen relative to the i block's centre (valid while
                     // halfBox - cutoff exceeds the block's half extent; validated in k_blockBounds' caller)
-                    pj.x -= p.box.ax*rintf(pj.x*p.box.invAx);
-                    pj.y -= p.box.by*rintf(pj.y*p.box.invBy);
-                    pj.z -= p.box.cz*rintf(pj.z*p.box.invCz);
+                    pj.x -= bAx*Real<R>::rint(pj.x*iAx);
+                    pj.y -= bBy*Real<R>::rint(pj.y*iBy);
+                    pj.z -= bCz*Real<R>::rint(pj.z*iCz);
                 }
             }
             __syncwarp();
@@ -94,37 +139,37 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
             sPrm[w][lane] = sj4;
             sEnt[w][lane] = ent;
             __syncwarp();
-            float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
+            R fix = 0, fiy = 0, fiz = 0, fjx = 0, fjy = 0, fjz = 0;
 #pragma unroll
             for (int s = 0; s < NS; s++)
-                t.eC[s] = t.eV[s] = 0.f;
+                t.eC[s] = t.eV[s] = 0;
             // ---- 32 x 32 pair steps ------------------------------------------------------
 #pragma unroll 4
             for (int s = 0; s < 32; s++) {
                 const int slot = (lane+s)&31;
-                const float4 q = sPos[w][slot];
+                const vec4 q = sPos[w][slot];
                 const unsigned mj = (unsigned) sEnt[w][slot].y;
-                float dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
+                R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
                 if (PBC == PBC_PAIR_ORTHO) {
-                    dx -= p.box.ax*rintf(dx*p.box.invAx);
-                    dy -= p.box.by*rintf(dy*p.box.invBy);
-                    dz -= p.box.cz*rintf(dz*p.box.invCz);
+                    dx -= bAx*Real<R>::rint(dx*iAx);
+                    dy -= bBy*Real<R>::rint(dy*iBy);
+                    dz -= bCz*Real<R>::rint(dz*iCz);
                 }
                 else if (PBC == PBC_PAIR_TRICLINIC) {
-                    float k = rintf(dz*p.box.invCz);
-                    dx -= k*p.box.cx; dy -= k*p.box.cy; dz -= k*p.box.cz;
-                    k = rintf(dy*p.box.invBy);
-                    dx -= k*p.box.bx; dy -= k*p.box.by;
-                    k = rintf(dx*p.box.invAx);
-                    dx -= k*p.box.ax;
+                    R k = Real<R>::rint(dz*iCz);
+                    dx -= k*(R) p.boxd.cx; dy -= k*(R) p.boxd.cy; dz -= k*bCz;
+                    k = Real<R>::rint(dy*iBy);
+                    dx -= k*(R) p.boxd.bx; dy -= k*bBy;
+                    k = Real<R>::rint(dx*iAx);
+                    dx -= k*bAx;
                 }
-                const float r2 = dx*dx+dy*dy+dz*dz;
+                const R r2 = dx*dx+dy*dy+dz*dz;
                 bool in = iValid && !((mj>>lane)&1u);
                 if (KIND != KIND_PLAIN) {
-                    in = in && r2 < p.cutoff2;
+                    in = in && r2 < cutoff2;
                     // Borderline pairs are decided exactly as the CPU oracle decides them: in double,
                     // from the untouched input coordinates (bit-exact pair set).
-                    if (iValid && !((mj>>lane)&1u) && fabsf(r2-p.cutoff2) < p.bandTol) {
+                    if (iValid && !((mj>>lane)&1u) && fabs(r2-cutoff2) < bandTol) {
                         const int origJ = a.sortedAtom[sEnt[w][slot].x];
                         double d[3];
                         deltaExact(a.posd+3*(size_t) min(origI, origJ), a.posd+3*(size_t) max(origI, origJ), p.boxd, p.periodic != 0, d);
@@ -132,57 +177,56 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
                     }
                 }
                 if (in) {
-                    const float4 prm = sPrm[w][slot];
-                    const int subJ = __float_as_int(prm.z);
-                    const float invR = fastRsqrt(r2);
-                    const float invR2 = invR*invR;
-                    const float r = r2*invR;
-                    const float qq = pi.w*q.w;                  // charges carry sqrt(ONE_4PI_EPS0)
-                    float fc, ec;
+                    const vec4 prm = sPrm[w][slot];
+                    const int subJ = (int) prm.z;
+                    const R invR = Real<R>::rsqrt(r2);
+                    const R invR2 = invR*invR;
+                    const R r = r2*invR;
+                    const R qq = pi.w*q.w;                      // charges carry sqrt(ONE_4PI_EPS0)
+                    R fc, ec;
                     if (KIND == KIND_EWALD || KIND == KIND_LJPME) {
-                        const float ar = p.alpha*r;
-                        const float ex = fastExp2(-1.4426950408889634f*(p.alpha2*r2));
-                        const float erfcAR = ex*erfcxPoly(ar);
+                        R ex, erfcAR;
+                        Real<R>::erfcTerms(alpha*r, alpha2*r2, ex, erfcAR);
                         ec = qq*invR*erfcAR;
-                        fc = qq*invR*invR2*fmaf(p.twoAlphaOverSqrtPi*r, ex, erfcAR);
+                        fc = qq*invR*invR2*(twoAlphaOverSqrtPi*r*ex+erfcAR);
                     }
                     else if (KIND == KIND_RF) {
-                        ec = qq*(invR+p.krf*r2-p.crf);
-                        fc = qq*invR2*(invR-2.0f*p.krf*r2);
+                        ec = qq*(invR+krf*r2-crf);
+                        fc = qq*invR2*(invR-2*krf*r2);
                     }
                     else {
                         ec = qq*invR;
                         fc = ec*invR2;
                     }
-                    const float sig = si4.x+prm.x;
-                    const float eps = si4.y*prm.y;
-                    float s2 = sig*invR;
+                    const R sig = si4.x+prm.x;
+                    const R eps = si4.y*prm.y;
+                    R s2 = sig*invR;
                     s2 *= s2;
-                    const float s6 = s2*s2*s2;
-                    float fv = eps*(12.0f*s6-6.0f)*s6*invR2;
-                    float ev = eps*(s6-1.0f)*s6;
+                    const R s6 = s2*s2*s2;
+                    R fv = eps*(12*s6-6)*s6*invR2;
+                    R ev = eps*(s6-1)*s6;
                     if (KIND == KIND_LJPME) {
-                        const float c6 = si4.w*prm.w;
-                        const float dar2 = p.dalpha2*r2, dar4 = dar2*dar2;
-                        const float exd = fastExp2(-1.4426950408889634f*dar2);
-                        const float invR6 = invR2*invR2*invR2;
-                        const float pe = 1.0f+dar2+0.5f*dar4;
-                        ev += c6*invR6*(1.0f-exd*pe);
-                        fv += 6.0f*c6*invR6*invR2*(1.0f-exd*(pe+dar4*dar2*(1.0f/6.0f)));
-                        float sc2 = sig*sig;
-                        const float sc6 = sc2*sc2*sc2*p.invCut6;
-                        ev += eps*(1.0f-sc6)*sc6-c6*p.invCut6*p.dispShiftExp;
+                        const R c6 = si4.w*prm.w;
+                        const R dar2 = dalpha2*r2, dar4 = dar2*dar2;
+                        const R exd = Real<R>::expNeg(dar2);
+                        const R invR6 = invR2*invR2*invR2;
+                        const R pe = 1+dar2+(R) 0.5*dar4;
+                        ev += c6*invR6*(1-exd*pe);
+                        fv += 6*c6*invR6*invR2*(1-exd*(pe+dar4*dar2*((R) 1/(R) 6)));
+                        R sc2 = sig*sig;
+                        const R sc6 = sc2*sc2*sc2*invCut6;
+                        ev += eps*(1-sc6)*sc6-c6*invCut6*dispShiftExp;
                     }
                     if (SWITCH) {
-                        if (r > p.switchDist) {
-                            const float x = (r-p.switchDist)*p.invSwitchWidth;
-                            const float sw = 1.0f+x*x*x*(-10.0f+x*(15.0f-x*6.0f));
-                            const float dsw = x*x*(-30.0f+x*(60.0f-x*30.0f))*p.invSwitchWidth;
+                        if (r > switchDist) {
+                            const R x = (r-switchDist)*invSwitchWidth;
+                            const R sw = 1+x*x*x*(-10+x*(15-x*6));
+                            const R dsw = x*x*(-30+x*(60-x*30))*invSwitchWidth;
                             fv = sw*fv-ev*dsw*invR;
                             ev *= sw;
                         }
                     }
-                    float lc, lv;
+                    R lc, lv;
                     if (NSUB == 1) {
                         lc = t.lamC[0]; lv = t.lamV[0];
                     }
@@ -196,17 +240,17 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
                     }
                     else {
                         const int sl = sliceOf(subI, subJ);
-                        lc = p.lambdaC[sl]; lv = p.lambdaV[sl];
+                        lc = (R) p.lambdaCd[sl]; lv = (R) p.lambdaVd[sl];
                     }
-                    const float f = lv*fv+lc*fc;
-                    fix = fmaf(f, dx, fix); fiy = fmaf(f, dy, fiy); fiz = fmaf(f, dz, fiz);
-                    fjx = fmaf(-f, dx, fjx); fjy = fmaf(-f, dy, fjy); fjz = fmaf(-f, dz, fjz);
+                    const R f = lv*fv+lc*fc;
+                    fix += f*dx; fiy += f*dy; fiz += f*dz;
+                    fjx -= f*dx; fjy -= f*dy; fjz -= f*dz;
                     if (ENERGY) {
                         if (NSUB > 0) {
 #pragma unroll
                             for (int u = 0; u < NS; u++) {
-                                t.eC[u] += subJ == u ? ec : 0.f;
-                                t.eV[u] += subJ == u ? ev : 0.f;
+                                t.eC[u] += subJ == u ? ec : (R) 0;
+                                t.eV[u] += subJ == u ? ev : (R) 0;
                             }
                         }
                         else {
@@ -228,9 +272,9 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
                 fjz = __shfl_sync(full, fjz, (lane+1)&31);
             }
             if (ent.x >= 0) {
-                addFixed(&a.forceSorted[ent.x], toFixed(fjx));
-                addFixed(&a.forceSorted[a.paddedAtoms+ent.x], toFixed(fjy));
-                addFixed(&a.forceSorted[2*a.paddedAtoms+ent.x], toFixed(fjz));
+                addFixed(&a.forceSorted[ent.x], Real<R>::fixed(fjx));
+                addFixed(&a.forceSorted[a.paddedAtoms+ent.x], Real<R>::fixed(fjy));
+                addFixed(&a.forceSorted[2*a.paddedAtoms+ent.x], Real<R>::fixed(fjz));
             }
             Fx += fix; Fy += fiy; Fz += fiz;
             if (ENERGY && NSUB > 0) {
@@ -265,10 +309,15 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
 
 template <int KIND, int PBC, int NSUB>
 static void launch4(const DirectArgs& a, cudaStream_t st, int grid) {
+    if (a.doublePrecision) {
+        // the double-precision mode is a correctness mode: one instantiation (energies always on)
+        k_direct<double, KIND, PBC, NSUB, true><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
+        return;
+    }
     if (a.needEnergy || a.pairDump)
-        k_direct<KIND, PBC, NSUB, true><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
+        k_direct<float, KIND, PBC, NSUB, true><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
     else
-        k_direct<KIND, PBC, NSUB, false><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
+        k_direct<float, KIND, PBC, NSUB, false><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
 }
 
 template <int KIND, int PBC>

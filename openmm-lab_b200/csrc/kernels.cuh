@@ -14,10 +14,12 @@ struct SortArgs {
     BoxD boxd;
     const double* posd;
     const float4* params4;
+    const double* paramsD;
     const int* cellRank;
     double* extent;
     int *cellCount, *cellStart, *atomCell, *atomSlot, *sortedAtom, *sortedPos;
     float4 *posqLocal, *sparams;
+    double4 *posqLocalD, *sparamsD;  // double-precision mode only (else null)
     double* blockCenter;
     float4* blockExt;
 };
@@ -44,10 +46,12 @@ void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 
 struct DirectArgs {
     DirectParams p;
-    int kind, useSwitch, numSubsets, needEnergy;
+    int kind, useSwitch, numSubsets, needEnergy, doublePrecision;
     const int* sortedAtom;
     const float4* posqLocal;
     const float4* sparams;
+    const double4* posqLocalD;     // double-precision mode only
+    const double4* sparamsD;
     const double* blockCenter;
     const double* posd;
     const int2* jList;
@@ -81,22 +85,24 @@ void launchBonded(const BondedArgs& a, cudaStream_t stream);
 
 struct PmeArgs {
     int numAtoms, numSubsets, term;  // term 0 Coulomb, 1 dispersion
-    int nx, ny, nz;
+    int nx, ny, nz, doublePrecision;
     double alpha;
     BoxD boxd;
     const double* posd;
     const int* sortedAtom;
-    const float4* params4;          // q in .x ; sigma/2, 2 sqrt(eps) in .y .z (dispersion "charge" = 8 s^3 e)
-    float* grid;                    // [S][nx][ny][nz] real
-    float2* cgrid;                  // [S][nx][ny][nz/2+1]
-    const float* eterm;             // [nx][ny][nz/2+1]
+    const float4* params4;          // q in .x ; sigma/2, 2 sqrt(eps) in .y .z (dispersion "charge" = 8 s^3 e) ; subset bits in .w
+    const double* paramsD;          // [N][3] sigma/2, 2 sqrt(eps), q
+    void* grid;                     // [S][nx][ny][nz] real (float or double)
+    long long* gridFixed;           // same shape, 2^40 fixed point (deterministic spreading), or null
+    void* cgrid;                    // [S][nx][ny][nz/2+1] complex
+    void* eterm;                    // [nx][ny][nz/2+1]
     const double* moduli[3];
-    float lambda[SNB_MAX_SLICES];   // of this term
+    double lambda[SNB_MAX_SLICES];  // of this term
     long long* forceOrig;
     int paddedAtoms;
     double* energyBuf;
 };
-void launchPmeEterm(const PmeArgs& a, float* eterm, cudaStream_t stream);
+void launchPmeEterm(const PmeArgs& a, cudaStream_t stream);
 void launchPmeSpread(const PmeArgs& a, cudaStream_t stream);
 void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);

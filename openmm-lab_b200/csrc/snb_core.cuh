@@ -43,14 +43,11 @@ struct BoxD {
 
 struct DirectParams {
     int numAtoms, numBlocks, pbcMode, periodic;
-    float cutoff2, bandTol;             // |r2 - cutoff2| < bandTol -> exact double predicate
+    float bandTol;                      // |r2 - cutoff2| < bandTol -> exact double predicate
     double cutoff2d;
-    float alpha, alpha2, twoAlphaOverSqrtPi;
-    float krf, crf;
-    float switchDist, invSwitchWidth;
-    float dalpha2, dispShiftExp, invCut6; // LJPME: alpha_d^2, [1-exp(-d_c^2)(1+d_c^2+d_c^4/2)], rc^-6
-    float lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
-    BoxF box;
+    double alphad, krfd, crfd, switchDistd, invSwitchWidthd;
+    double dalphad, dispShiftExpd, invCut6d;   // LJPME: alpha_d, [1-exp(-d_c^2)(1+d_c^2+d_c^4/2)], rc^-6
+    double lambdaCd[SNB_MAX_SLICES], lambdaVd[SNB_MAX_SLICES];
     BoxD boxd;
 };
 

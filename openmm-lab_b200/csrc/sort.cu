@@ -177,11 +177,19 @@ __global__ void k_blockBounds(SortArgs a) {
         pl = make_float4((float) (p[0]-c[0]), (float) (p[1]-c[1]), (float) (p[2]-c[2]), prm.x*a.sqrtK);
     a.posqLocal[k] = pl;
     float sig = prm.y, eps = prm.z;
-    // the subset travels as raw int bits (-1 = padding lane); stored through an int view so that no
-    // floating-point move can canonicalise the bit pattern
-    int4 sp = make_int4(__float_as_int(sig), __float_as_int(eps), atom >= 0 ? __float_as_int(prm.w) : -1,
-                        __float_as_int(8.0f*sig*sig*sig*eps));
-    reinterpret_cast<int4*>(a.sparams)[k] = sp;
+    // (sigma/2, 2 sqrt(eps), subset as an exact small real with -1 = padding lane, c6 = 8 s^3 e)
+    const float subsetF = atom >= 0 ? (float) __float_as_int(prm.w) : -1.0f;
+    a.sparams[k] = make_float4(sig, eps, subsetF, 8.0f*sig*sig*sig*eps);
+    if (a.posqLocalD) {
+        double4 pd = make_double4(0, 0, 0, 0), sd = make_double4(0, 0, -1, 0);
+        if (atom >= 0) {
+            const double sg = a.paramsD[3*atom], ep = a.paramsD[3*atom+1], qd = a.paramsD[3*atom+2];
+            pd = make_double4(p[0]-c[0], p[1]-c[1], p[2]-c[2], qd*sqrt(SNB_ONE_4PI_EPS0));
+            sd = make_double4(sg, ep, (double) subsetF, 8.0*sg*sg*sg*ep);
+        }
+        a.posqLocalD[k] = pd;
+        a.sparamsD[k] = sd;
+    }
     if (lane == 0) {
         a.blockCenter[3*warp] = c[0]; a.blockCenter[3*warp+1] = c[1]; a.blockCenter[3*warp+2] = c[2];
         // half extents, rounded up so the box is conservative in single precision

@@ -27,11 +27,12 @@ class CalcSlicedNonbondedForceKernel:
     def Name():
         return "CalcSlicedNonbondedForce"
 
-    def __init__(self, lib, prefix, device_index=0):
+    def __init__(self, lib, prefix, device_index=0, flags=0):
         self._lib = lib
         self._prefix = prefix
         self._handle = C.c_void_p()
         self._device_index = device_index
+        self._flags = flags
         self._packed = None
 
     def _fn(self, name):
@@ -47,7 +48,7 @@ class CalcSlicedNonbondedForceKernel:
     def initialize(self, system, force):
         self.destroy()
         box = system.getDefaultPeriodicBoxVectors()
-        self._packed = PackedDesc(force, np.asarray(box, dtype=np.float64), self._device_index)
+        self._packed = PackedDesc(force, np.asarray(box, dtype=np.float64), self._device_index, self._flags)
         create = self._fn("create")
         create.argtypes = [C.POINTER(SnbDesc), C.POINTER(C.c_void_p)]
         self._check(create(C.byref(self._packed.desc), C.byref(self._handle)))
@@ -78,7 +79,7 @@ class CalcSlicedNonbondedForceKernel:
 
     # copyParametersToContext(context, force) -- OpenMMLabKernels.h:68
     def copyParametersToContext(self, context, force):
-        packed = PackedDesc(force, np.asarray(context._system.getDefaultPeriodicBoxVectors(), dtype=np.float64), self._device_index)
+        packed = PackedDesc(force, np.asarray(context._system.getDefaultPeriodicBoxVectors(), dtype=np.float64), self._device_index, self._flags)
         fn = self._fn("update_parameters")
         fn.argtypes = [C.c_void_p, C.POINTER(SnbDesc)]
         self._check(fn(self._handle, C.byref(packed.desc)))
@@ -143,8 +144,10 @@ def load_library():
 class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
     """The sm_100a implementation, registered on platform "B200" (platform.py)."""
 
-    def __init__(self, device_index=0):
-        super().__init__(load_library(), "snb_", device_index)
+    def __init__(self, device_index=0, precision="mixed", deterministic=False):
+        flags = (_abi.FLAG_DOUBLE_PRECISION if precision == "double" else 0) | (_abi.FLAG_DETERMINISTIC if deterministic else 0)
+        super().__init__(load_library(), "snb_", device_index, flags)
+        self.precision = precision
 
     def executeDevice(self, posq_ptr, box, params, flags, forces_ptr):
         fn = self._lib.snb_execute_device

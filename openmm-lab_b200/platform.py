@@ -3,7 +3,9 @@
 Mirrors the reference's plugin entry points
 (platforms/cuda/src/CudaOpenMMLabKernelFactory.cpp:19-57): ``registerKernelFactories``
 registers a factory for the kernel name "CalcSlicedNonbondedForce"; the factory throws for
-any other name (:56).
+any other name (:56).  Platform properties follow the reference's CUDA platform
+(CudaOpenMMLabKernels.cpp:483,496; platforms/cuda/tests/CudaOpenMMLabTests.h:26-31):
+``Precision`` (mixed | double), ``DeterministicForces``, ``DeviceIndex``.
 """
 from .context import Platform
 from .force import OpenMMException
@@ -12,7 +14,12 @@ from .kernel import B200CalcSlicedNonbondedForceKernel, CalcSlicedNonbondedForce
 
 def _createKernelImpl(name, platform, context):
     if name == CalcSlicedNonbondedForceKernel.Name():
-        return B200CalcSlicedNonbondedForceKernel(platform._properties.get("DeviceIndex", 0))
+        props = getattr(context, "_properties", platform._properties)
+        precision = str(props.get("Precision", "mixed")).lower()
+        if precision not in ("mixed", "double"):
+            raise OpenMMException("Illegal value for Precision: %s (this platform offers mixed and double)" % precision)
+        deterministic = str(props.get("DeterministicForces", "false")).lower() in ("true", "1")
+        return B200CalcSlicedNonbondedForceKernel(int(props.get("DeviceIndex", 0)), precision, deterministic)
     raise OpenMMException("Tried to create kernel with illegal kernel name '%s'" % name)
 
 

@@ -8,19 +8,53 @@ import openmmlab_b200 as mm
 from openmmlab_b200 import SlicedNonbondedForce as F
 from openmmlab_b200 import systems
 
-from util import assert_parity, evaluate
+from util import assert_parity, assert_parity_mixed, evaluate
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5   # BASELINE.json north_star: "within 1e-5 relative error in mixed precision"
 
 
-def _check(w, tol=TOL, pairs=True, **kw):
-    ref = evaluate("Reference", w, pairs=pairs and w.force.getNonbondedMethod() != F.NoCutoff, **kw)
-    got = evaluate("B200", w, pairs=pairs and kw.get("direct", True), **kw)
-    if pairs and kw.get("direct", True) and "pairs" in ref:
-        assert ref["pairs"].shape == got["pairs"].shape, "pair count %d vs %d" % (len(ref["pairs"]), len(got["pairs"]))
-        assert np.array_equal(ref["pairs"], got["pairs"]), "interacting pair sets differ"
-    return assert_parity(ref, got, tol, w.name)
+DOUBLE = {"Precision": "double"}
+
+
+def _check_pairs(ref, got):
+    assert ref["pairs"].shape == got["pairs"].shape, "pair count %d vs %d" % (len(ref["pairs"]), len(got["pairs"]))
+    assert np.array_equal(ref["pairs"], got["pairs"]), "interacting pair sets differ"
+
+
+def _check(w, pairs=True, mixed=True, **kw):
+    """Parity of one workload with the CPU oracle in both precision modes of the platform.
+
+    Precision=double: bit-exact pair set; total energy, every slice energy, every derivative and every
+    force component within 1e-5 by the reference's own metric -- direct-only, reciprocal-only and both.
+    Precision=mixed (default, the fast path): bit-exact pair set; util.assert_parity_mixed.
+    """
+    method = w.force.getNonbondedMethod()
+    direct, reciprocal = kw.pop("direct", True), kw.pop("reciprocal", True)
+    ewald_family = method in (F.PME, F.LJPME)
+    want_pairs = pairs and method != F.NoCutoff
+    combos = []
+    if direct:
+        combos.append(("direct", dict(direct=True, reciprocal=False)))
+    if reciprocal and ewald_family:
+        combos.append(("recip", dict(direct=False, reciprocal=True)))
+    if len(combos) == 2:
+        combos.append(("total", dict(direct=True, reciprocal=True)))
+    refs = {}
+    for name, flags in combos:
+        ref = refs[name] = evaluate("Reference", w, pairs=want_pairs and name == "direct", **flags, **kw)
+        got = evaluate("B200", w, pairs=pairs and name == "direct", properties=DOUBLE, **flags, **kw)
+        if "pairs" in ref:
+            _check_pairs(ref, got)
+        assert_parity(ref, got, TOL, "%s %s [double]" % (w.name, name))
+        if mixed:
+            got = evaluate("B200", w, pairs=pairs and name == "direct", **flags, **kw)
+            if "pairs" in ref:
+                _check_pairs(ref, got)
+            if name == "total":
+                assert_parity_mixed(ref, got, refs["direct"], refs["recip"], what="%s total [mixed]" % w.name)
+            else:
+                assert_parity_mixed(ref, got, what="%s %s [mixed]" % (w.name, name))
 
 
 @pytest.mark.parametrize("method", [F.CutoffPeriodic, F.PME])
@@ -95,10 +129,11 @@ def test_lambda_changes_and_offsets():
 
 
 def test_update_parameters():
+    # copyParametersToContext (reference test idea: testChangingParameters, TestSlicedNonbondedForce.h:667-732)
     w = systems.water_box()
     results = {}
-    for platform in ("Reference", "B200"):
-        ctx = mm.Context(w.system, platform)
+    for platform, props in (("Reference", None), ("B200", DOUBLE)):
+        ctx = mm.Context(w.system, platform, props)
         ctx.setPositions(w.positions)
         ctx.getState()
         for i in range(0, w.num_particles, 5):
@@ -118,6 +153,8 @@ def test_deterministic_forces():
     # fixed-point accumulation: two evaluations give bit-identical forces (reference test idea:
     # platforms/cuda/tests/TestCudaSlicedNonbondedForce.cpp:109-141)
     w = systems.water_box()
-    a = evaluate("B200", w)
-    b = evaluate("B200", w)
-    assert np.array_equal(a["forces"], b["forces"])
+    for props in ({"DeterministicForces": "true"}, DOUBLE):
+        a = evaluate("B200", w, properties=props)
+        b = evaluate("B200", w, properties=props)
+        assert np.array_equal(a["forces"], b["forces"])
+        assert a["energy"] == b["energy"] or abs(a["energy"]-b["energy"]) < 1e-9*abs(a["energy"])

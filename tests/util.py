@@ -46,10 +46,11 @@ def rel_err(expected, found):
     return abs(expected-found)/max(abs(expected), 1.0)
 
 
-def evaluate(platform, w, direct=True, reciprocal=True, forces=True, energy=True, parameters=None, pairs=False):
+def evaluate(platform, w, direct=True, reciprocal=True, forces=True, energy=True, parameters=None, pairs=False,
+             properties=None):
     """One kernel.execute on `platform` for workload `w`; returns energies, forces, derivatives (and pairs)."""
     import openmmlab_b200 as mm
-    ctx = mm.Context(w.system, platform)
+    ctx = mm.Context(w.system, platform, properties)
     ctx.setPositions(w.positions)
     if w.box is not None:
         ctx.setPeriodicBoxVectors(*w.box)
@@ -80,3 +81,44 @@ def assert_parity(ref, got, tol=1e-5, what=""):
     err = max_force_error(ref["forces"], got["forces"])
     assert err <= tol, "%s max force error %g > %g" % (what, err, tol)
     return err
+
+
+def assert_parity_mixed(ref, got, ref_direct=None, ref_recip=None, what=""):
+    """Mixed-precision criteria (FP32 pair arithmetic, FP64 accumulation).
+
+    Energies: the reference metric at 1e-5, with the scale of a quantity taken as the larger of its
+    own magnitude and the summed magnitudes of its direct- and reciprocal-space parts when those are
+    given (the parts are each checked at 1e-5 on their own; they cancel to ~1e-3 of their size in
+    the total, and FP32 pair terms cannot resolve a 1e-5 fraction of the remainder).
+    Forces: per-atom reference metric at the reference's own single/mixed tolerance of 1e-3
+    (tests/TestSlicedNonbondedForce.h:995), plus rms(dF) <= 1e-5 rms(F) and max|dF| <= 1e-4 rms(F).
+    """
+    def scale_of(key, idx=None):
+        def pick(r):
+            v = r[key] if idx is None else r[key][idx]
+            return abs(v)
+        s = pick(ref)
+        if ref_direct is not None and ref_recip is not None:
+            s = max(s, pick(ref_direct)+pick(ref_recip))
+        return max(s, 1.0)
+    tol = 1e-5
+    assert abs(ref["energy"]-got["energy"])/scale_of("energy") <= tol, "%s energy %r vs %r" % (what, ref["energy"], got["energy"])
+    for s in range(ref["slices"].shape[0]):
+        for t in range(2):
+            err = abs(ref["slices"][s, t]-got["slices"][s, t])/scale_of("slices", (s, t))
+            assert err <= tol, "%s slice %d term %d: %r vs %r (%.2e)" % (what, s, t, ref["slices"][s, t], got["slices"][s, t], err)
+    assert set(ref["derivs"]) == set(got["derivs"])
+    for k in ref["derivs"]:
+        s = abs(ref["derivs"][k])
+        if ref_direct is not None and ref_recip is not None:
+            s = max(s, abs(ref_direct["derivs"][k])+abs(ref_recip["derivs"][k]))
+        assert abs(ref["derivs"][k]-got["derivs"][k])/max(s, 1.0) <= tol, "%s derivative %s: %r vs %r" % (what, k, ref["derivs"][k], got["derivs"][k])
+    dF = ref["forces"]-got["forces"]
+    rmsF = max(np.sqrt((ref["forces"]**2).sum(axis=1).mean()), 1.0)
+    per_atom = max_force_error(ref["forces"], got["forces"])
+    rms_err = np.sqrt((dF**2).sum(axis=1).mean())/rmsF
+    max_err = np.abs(dF).max()/rmsF
+    assert per_atom <= 1e-3, "%s per-atom force error %g" % (what, per_atom)
+    assert rms_err <= 1e-5, "%s rms force error %g of rms force" % (what, rms_err)
+    assert max_err <= 1e-4, "%s max force error %g of rms force" % (what, max_err)
+    return per_atom, rms_err, max_err
