@@ -22,7 +22,7 @@ def _check_pairs(ref, got):
     assert np.array_equal(ref["pairs"], got["pairs"]), "interacting pair sets differ"
 
 
-def _check(w, pairs=True, mixed=True, **kw):
+def _check(w, pairs=True, mixed=True, energy_tol=1e-4, **kw):
     """Parity of one workload with the CPU oracle in both precision modes of the platform.
 
     Precision=double: bit-exact pair set; total energy, every slice energy, every derivative and every
@@ -52,20 +52,20 @@ def _check(w, pairs=True, mixed=True, **kw):
             if "pairs" in ref:
                 _check_pairs(ref, got)
             if name == "total":
-                assert_parity_mixed(ref, got, refs["direct"], refs["recip"], what="%s total [mixed]" % w.name)
+                assert_parity_mixed(ref, got, refs["direct"], refs["recip"], what="%s total [mixed]" % w.name, energy_tol=energy_tol)
             else:
-                assert_parity_mixed(ref, got, what="%s %s [mixed]" % (w.name, name))
+                assert_parity_mixed(ref, got, what="%s %s [mixed]" % (w.name, name), energy_tol=energy_tol)
 
 
 @pytest.mark.parametrize("method", [F.CutoffPeriodic, F.PME])
 def test_water_box(method):
     # BASELINE.json configs[0]: 648-atom water box, 2 subsets, CutoffPeriodic and PME
-    _check(systems.water_box(method=method))
+    _check(systems.water_box(method=method), energy_tol=1e-5)
 
 
 @pytest.mark.parametrize("direct,reciprocal", [(True, False), (False, True)])
 def test_water_box_direct_reciprocal_split(direct, reciprocal):
-    _check(systems.water_box(), direct=direct, reciprocal=reciprocal)
+    _check(systems.water_box(), direct=direct, reciprocal=reciprocal, energy_tol=1e-5)
 
 
 @pytest.mark.parametrize("method", [F.CutoffPeriodic, F.PME, F.LJPME])
@@ -91,7 +91,10 @@ def test_switching_function():
 def test_nonperiodic_methods():
     for method in (F.NoCutoff, F.CutoffNonPeriodic):
         w = systems.small_mixed(method=method, scaling=[("lam", 0.5, 0, 1, True, True)], derivatives=["lam"])
-        _check(w)
+        # NoCutoff sums 217k unscreened 1/r terms that cancel to 1e-5 of their gross size: in mixed
+        # precision that configuration is held to the reference's own mixed tolerance (1e-3,
+        # TestSlicedNonbondedForce.h:995); Precision=double is held to 1e-5 as everywhere else.
+        _check(w, energy_tol=1e-3 if method == F.NoCutoff else 1e-4)
 
 
 def test_triclinic():
@@ -111,12 +114,12 @@ def test_periodic_exceptions_and_many_subsets():
 
 def test_fep_ljpme():
     # BASELINE.json configs[3]
-    _check(systems.fep_ligand())
+    _check(systems.fep_ligand(), energy_tol=1e-5)
 
 
 def test_dhfr_size():
     # BASELINE.json configs[1]
-    _check(systems.dhfr_like())
+    _check(systems.dhfr_like(), energy_tol=1e-5)
 
 
 def test_lambda_changes_and_offsets():
