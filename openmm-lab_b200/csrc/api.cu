@@ -182,14 +182,18 @@ struct snb_handle {
     int cellDim[3] = {0, 0, 0}, numCells = 0;
     int pbcModeOverride = -1;
     // ---- device state ----
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, pmeStream = nullptr;
+    cudaEvent_t evSorted = nullptr, evPmeDone = nullptr;
     int numSMs = 148;
     DevBuf<double> posd, paramsD, exception14, blockCenter, extent, energyBuf, forcesOutD;
     DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn;
     DevBuf<double4> posqLocalD, sparamsD;
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
-                exclStart, exclList, is14D, counters;
+                exclStart, exclList, is14D, counters, cellScratch;
     DevBuf<int2> exceptionAtomsD, jList;
+    DevBuf<unsigned> tileFlags;
+    DevBuf<ExactParams> exactD;
+    PinnedBuf<ExactParams> exactH;
     DevBuf<int4> workItems;
     DevBuf<long long> forceSorted, forceOrig;
     PinnedBuf<double> hPos, hForces, hEnergy;
@@ -348,6 +352,9 @@ snb_handle* createHandle(const snb_desc& d) {
         CUDA_CHECK(cudaGetDeviceProperties(&prop, h.device));
         h.numSMs = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h.pmeStream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h.evSorted, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h.evPmeDone, cudaEventDisableTiming));
         h.N = d.num_particles;
         h.NB = (h.N+31)/32;
         h.NP = h.NB*32;
@@ -422,7 +429,7 @@ snb_handle* createHandle(const snb_desc& d) {
         h.params4.alloc(h.N);
         h.subsetD.alloc(h.N);
         h.exception14.alloc(3*(size_t) h.X);
-        h.atomCell.alloc(h.N); h.atomSlot.alloc(h.N);
+        h.atomCell.alloc(h.N); h.atomSlot.alloc(h.N); h.cellScratch.alloc(h.N);
         h.sortedAtom.alloc(h.NP); h.sortedPos.alloc(h.N);
         h.posqLocal.alloc(h.NP); h.sparams.alloc(h.NP);
         if (h.doublePrecision) { h.posqLocalD.alloc(h.NP); h.sparamsD.alloc(h.NP); }
@@ -580,7 +587,10 @@ void ensureListCapacity(snb_handle& h, const double* box, bool periodic) {
         perBlock = std::min<size_t>((size_t) (atoms/32)+2, (size_t) h.NB+1);
     }
     h.maxChunks = std::max<size_t>(64, perBlock*h.NB);
-    h.maxItems = h.maxChunks/2+h.NB+16;
+    // work items of 1..8 chunks: small systems need every chunk as its own item to fill 148 SMs
+    size_t expectedChunks = h.maxChunks*2/3;
+    h.itemChunks = (int) std::max<size_t>(1, std::min<size_t>(SNB_ITEM_CHUNKS, expectedChunks/((size_t) h.numSMs*24*8)));
+    h.maxItems = h.maxChunks/h.itemChunks+2*(size_t) h.NB+16;
     h.jList.alloc(h.maxChunks*32);
     h.workItems.alloc(h.maxItems);
 }
@@ -618,8 +628,8 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         bool triclinic = bd.bx != 0 || bd.cx != 0 || bd.cy != 0;
         double room = std::min(bd.ax, std::min(bd.by, bd.cz))*0.5-h.cutoff;
         if (triclinic) pbcMode = PBC_PAIR_TRICLINIC;
-        else if (h.pbcModeOverride >= 0) pbcMode = h.pbcModeOverride;
-        else pbcMode = room > 0.75 ? PBC_SHIFT : PBC_PAIR_ORTHO;
+        else pbcMode = PBC_SHIFT;      // per work item: one image per j atom, or per-pair wrapping for wide i blocks
+        (void) room;
     }
 
     CUDA_CHECK(cudaMemsetAsync(h.forceSorted.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
@@ -635,18 +645,19 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         memset(&sa, 0, sizeof(sa));
         sa.numAtoms = h.N; sa.paddedAtoms = h.NP; sa.numBlocks = h.NB; sa.numCells = h.numCells; sa.periodic = periodic;
         for (int k = 0; k < 3; k++) sa.cellDim[k] = h.cellDim[k];
-        sa.checkShift = pbcMode == PBC_SHIFT;
+        sa.checkShift = 0;
         sa.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); sa.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); sa.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
         sa.counters = h.counters.p;
         sa.sqrtK = (float) sqrt(SNB_ONE_4PI_EPS0);
         sa.boxd = bd;
         sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.paramsD = h.paramsD.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
         sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
-        sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p;
+        sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p;
         launchSort(sa, st);
         tm.mark(1);
+        if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
 
         ListArgs la;
         memset(&la, 0, sizeof(la));
@@ -658,7 +669,13 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p;
         la.exclStart = h.exclStart.p; la.exclList = h.exclList.p;
         la.jList = h.jList.p; la.workItems = h.workItems.p; la.counters = h.counters.p;
-        la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems;
+        la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems; la.itemChunks = h.itemChunks;
+        la.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); la.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); la.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
+        if (h.NB <= SNB_FLAGS_MAX_BLOCKS) {
+            la.flagStride = (h.NB+31)&~31;
+            h.tileFlags.alloc((size_t) h.NB*la.flagStride);
+            la.tileFlags = h.tileFlags.p;
+        }
         launchBuildList(la, st, h.numSMs);
         tm.mark(2);
 
@@ -677,6 +694,10 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         p.invCut6d = pow(h.cutoff, -6.0);
         for (int s = 0; s < h.L; s++) { p.lambdaCd[s] = h.lambdaC[s]; p.lambdaVd[s] = h.lambdaV[s]; }
         p.boxd = bd;
+        h.exactD.alloc(1); h.exactH.alloc(1);
+        h.exactH.p->boxd = bd; h.exactH.p->cutoff2d = p.cutoff2d; h.exactH.p->periodic = periodic;
+        CUDA_CHECK(cudaMemcpyAsync(h.exactD.p, h.exactH.p, sizeof(ExactParams), cudaMemcpyHostToDevice, st));
+        da.exact = h.exactD.p;
         da.kind = h.method == SNB_NO_CUTOFF ? KIND_PLAIN : h.method <= SNB_CUTOFF_PERIODIC ? KIND_RF : h.method == SNB_LJPME ? KIND_LJPME : KIND_EWALD;
         da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
         da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
@@ -702,9 +723,16 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         // the sorted order is still needed by the reciprocal kernels and the final gather:
         // identity order is enough there
         tm.mark(1); tm.mark(2); tm.mark(3); tm.mark(4);
+        if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
     }
 
     if (includeRecip && pmeFamily) {
+        // Reciprocal space runs on its own stream, concurrently with the tile list / direct-space /
+        // bonded kernels (it only needs the sorted order).  With per-phase timing on, everything is
+        // serialised on the main stream so that the phase times mean what they say.
+        cudaStream_t ps = h.timing ? st : h.pmeStream;
+        if (!h.timing)
+            CUDA_CHECK(cudaStreamWaitEvent(ps, h.evSorted, 0));
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
             PmeGrid& g = term == 0 ? h.pme : h.dpme;
             PmeArgs pa;
@@ -720,21 +748,27 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
             pa.forceOrig = h.forceOrig.p; pa.paddedAtoms = h.NP; pa.energyBuf = h.energyBuf.p;
             double key[6] = {bd.ax, bd.bx, bd.by, bd.cx, bd.cy, bd.cz};
             if (!g.etermValid || memcmp(key, g.etermBox, sizeof(key)) != 0) {
-                launchPmeEterm(pa, st);
+                launchPmeEterm(pa, ps);
                 memcpy(g.etermBox, key, sizeof(key));
                 g.etermValid = true;
             }
-            launchPmeSpread(pa, st);
+            CUFFT_CHECK(cufftSetStream(g.fwd, ps));
+            CUFFT_CHECK(cufftSetStream(g.inv, ps));
+            launchPmeSpread(pa, ps);
             if (term == 0) tm.mark(5);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecD2Z(g.fwd, (double*) g.real.p, (cufftDoubleComplex*) g.cplx.p));
             else CUFFT_CHECK(cufftExecR2C(g.fwd, (float*) g.real.p, (cufftComplex*) g.cplx.p));
             if (term == 0) tm.mark(6);
-            launchPmeConvolution(pa, st);
+            launchPmeConvolution(pa, ps);
             if (term == 0) tm.mark(7);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecZ2D(g.inv, (cufftDoubleComplex*) g.cplx.p, (double*) g.real.p));
             else CUFFT_CHECK(cufftExecC2R(g.inv, (cufftComplex*) g.cplx.p, (float*) g.real.p));
-            launchPmeInterpolate(pa, st);
+            launchPmeInterpolate(pa, ps);
             if (term == 0) tm.mark(8);
+        }
+        if (!h.timing) {
+            CUDA_CHECK(cudaEventRecord(h.evPmeDone, ps));
+            CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
         }
     }
     else {
@@ -769,10 +803,6 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
             h.workItems.alloc(h.maxItems);
             return false;
         }
-        if (h.hCounters.p[4]) {
-            h.pbcModeOverride = PBC_PAIR_ORTHO;
-            return false;
-        }
     }
     if (h.timing) {
         for (int k = 0; k < 9; k++)
@@ -783,7 +813,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
     h.countersOut[3] = h.hCounters.p[1];
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
-    if (includeDirect) launches += (periodic ? 5 : 6)+1+1+(h.X > 0 ? 1 : 0);
+    if (includeDirect) launches += (periodic ? 5 : 6)+(h.NB <= SNB_FLAGS_MAX_BLOCKS ? 2 : 1)+1+(h.X > 0 ? 1 : 0);
     if (includeRecip && pmeFamily) launches += (h.deterministic ? 4 : 3)*(h.method == SNB_LJPME ? 2 : 1);
     if (includeForces) launches += 1;
     if (!hostPositions) launches += 1;
@@ -873,9 +903,12 @@ void snb_destroy(snb_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->evCreated)
         for (auto& e : h->ev) cudaEventDestroy(e);
-    cudaStream_t s = h->stream;
+    cudaStream_t s = h->stream, s2 = h->pmeStream;
+    if (h->evSorted) cudaEventDestroy(h->evSorted);
+    if (h->evPmeDone) cudaEventDestroy(h->evPmeDone);
     delete h;
     if (s) cudaStreamDestroy(s);
+    if (s2) cudaStreamDestroy(s2);
 }
 
 int snb_update_parameters(snb_handle* h, const snb_desc* desc) {

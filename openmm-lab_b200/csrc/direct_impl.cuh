@@ -56,6 +56,15 @@ template <> struct Real<double> {
     static __device__ __forceinline__ long long fixed(double f) { return toFixedD(f); }
 };
 
+// Borderline pairs (|r^2 - rc^2| within the single-precision uncertainty) are decided exactly as the
+// CPU oracle decides them: in double, from the untouched input coordinates, lower index first.  Kept
+// out of line: it runs for ~1e-5 of the pairs and would otherwise bloat the hot loop.
+static __device__ __noinline__ bool exactInRange(const double* posd, int origI, int origJ, const ExactParams* p) {
+    double d[3];
+    deltaExact(posd+3*(size_t) min(origI, origJ), posd+3*(size_t) max(origI, origJ), p->boxd, p->periodic != 0, d);
+    return !(dot3Exact(d) > p->cutoff2d);
+}
+
 template <typename R, int NSUB> struct SubsetTable {
     // lambda and energy tables indexed by the j atom's subset (the i subset is fixed per lane)
     R lamC[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS], lamV[NSUB > 0 ? NSUB : SNB_MAX_SUBSETS];
@@ -64,7 +73,7 @@ template <typename R, int NSUB> struct SubsetTable {
 };
 
 template <typename R, int KIND, int PBC, int NSUB, bool ENERGY>
-__global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
+__global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_direct(DirectArgs a) {
     constexpr int NS = NSUB > 0 ? NSUB : SNB_MAX_SUBSETS;
     typedef typename Real<R>::vec4 vec4;
     __shared__ vec4 sPos[DIRECT_WARPS][32];
@@ -77,7 +86,7 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
     const int numSub = NSUB > 0 ? NSUB : a.numSubsets;
     const bool SWITCH = a.useSwitch != 0, DUMP = a.pairDump != nullptr;
     const int numItems = a.counters[1];
-    const R cutoff2 = (R) p.cutoff2d, bandTol = (R) p.bandTol;
+    const R cutoffHi = (R) (p.cutoff2d+p.bandTol), cutoffLo = (R) (p.cutoff2d-p.bandTol);
     const R alpha = (R) p.alphad, alpha2 = alpha*alpha, twoAlphaOverSqrtPi = (R) (2.0*p.alphad/1.772453850905516);
     const R krf = (R) p.krfd, crf = (R) p.crfd;
     const R switchDist = (R) p.switchDistd, invSwitchWidth = (R) p.invSwitchWidthd;
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
             break;
         const int4 wi = a.workItems[item];
         const int I = wi.x;
+        const bool perPair = PBC == PBC_SHIFT && wi.w != 0;    // i block too wide for one image per j atom
         const int ki = I*32+lane;
         const vec4 pi = Real<R>::pos(a)[ki];
         const vec4 si4 = Real<R>::prm(a)[ki];
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
                 const int J = ent.x>>5;
                 R ox = (R) (a.blockCenter[3*J]-cIx), oy = (R) (a.blockCenter[3*J+1]-cIy), oz = (R) (a.blockCenter[3*J+2]-cIz);
                 pj.x += ox; pj.y += oy; pj.z += oz;
-                if (PBC == PBC_SHIFT) {
+                if (PBC == PBC_SHIFT && !perPair) {
                     // one image per j atom, chosen relative to the i block's centre (valid while
                     // halfBox - cutoff exceeds the block's half extent; validated in k_blockBounds' caller)
                     pj.x -= bAx*Real<R>::rint(pj.x*iAx);
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
                 const vec4 q = sPos[w][slot];
                 const unsigned mj = (unsigned) sEnt[w][slot].y;
                 R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
-                if (PBC == PBC_PAIR_ORTHO) {
+                if (PBC == PBC_SHIFT && perPair) {
                     dx -= bAx*Real<R>::rint(dx*iAx);
                     dy -= bBy*Real<R>::rint(dy*iBy);
                     dz -= bCz*Real<R>::rint(dz*iCz);
@@ -164,17 +174,13 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32) k_direct(DirectArgs a) {
                     dx -= k*bAx;
                 }
                 const R r2 = dx*dx+dy*dy+dz*dz;
+                // one compare on the hot path: r2 below cutoff2 + band; pairs inside the band (about 1e-5 of
+                // them) are then decided exactly, as the CPU oracle decides them
                 bool in = iValid && !((mj>>lane)&1u);
                 if (KIND != KIND_PLAIN) {
-                    in = in && r2 < cutoff2;
-                    // Borderline pairs are decided exactly as the CPU oracle decides them: in double,
-                    // from the untouched input coordinates (bit-exact pair set).
-                    if (iValid && !((mj>>lane)&1u) && fabs(r2-cutoff2) < bandTol) {
-                        const int origJ = a.sortedAtom[sEnt[w][slot].x];
-                        double d[3];
-                        deltaExact(a.posd+3*(size_t) min(origI, origJ), a.posd+3*(size_t) max(origI, origJ), p.boxd, p.periodic != 0, d);
-                        in = !(dot3Exact(d) > p.cutoff2d);
-                    }
+                    in = in && r2 < cutoffHi;
+                    if (in && r2 > cutoffLo)
+                        in = exactInRange(a.posd, origI, a.sortedAtom[sEnt[w][slot].x], a.exact);
                 }
                 if (in) {
                     const vec4 prm = sPrm[w][slot];
@@ -338,10 +344,10 @@ void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid) {
             if (KIND == KIND_PLAIN || KIND == KIND_RF) launch3<KIND, PBC_NONE>(a, st, grid);
             break;
         case PBC_SHIFT:
-            if (KIND != KIND_PLAIN) launch3<KIND, PBC_SHIFT>(a, st, grid);
-            break;
         case PBC_PAIR_ORTHO:
-            if (KIND != KIND_PLAIN) launch3<KIND, PBC_PAIR_ORTHO>(a, st, grid);
+            // orthorhombic box: one image per j atom, or per-pair wrapping for the (few) i blocks whose
+            // bounding box is too wide for that -- decided per work item
+            if (KIND != KIND_PLAIN) launch3<KIND, PBC_SHIFT>(a, st, grid);
             break;
         default:
             if (KIND != KIND_PLAIN) launch3<KIND, PBC_PAIR_TRICLINIC>(a, st, grid);

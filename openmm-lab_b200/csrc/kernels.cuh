@@ -17,7 +17,7 @@ struct SortArgs {
     const double* paramsD;
     const int* cellRank;
     double* extent;
-    int *cellCount, *cellStart, *atomCell, *atomSlot, *sortedAtom, *sortedPos;
+    int *cellCount, *cellStart, *atomCell, *atomSlot, *cellScratch, *sortedAtom, *sortedPos;
     float4 *posqLocal, *sparams;
     double4 *posqLocalD, *sparamsD;  // double-precision mode only (else null)
     double* blockCenter;
@@ -40,7 +40,10 @@ struct ListArgs {
     int2* jList;
     int4* workItems;
     int* counters;          // [0] chunks allocated, [1] work items, [2] overflow flag, [3] next work item
-    int maxChunks, maxItems;
+    int maxChunks, maxItems, itemChunks;
+    unsigned* tileFlags;    // [numBlocks][flagStride] per-atom interaction flags (parallel build), or null
+    int flagStride;
+    float shiftLimit[3];    // halfBox - cutoff: i blocks wider than this cannot use one image per j atom
 };
 void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 
@@ -54,6 +57,7 @@ struct DirectArgs {
     const double4* sparamsD;
     const double* blockCenter;
     const double* posd;
+    const ExactParams* exact;
     const int2* jList;
     const int4* workItems;
     int* counters;

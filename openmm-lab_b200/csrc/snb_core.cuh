@@ -27,7 +27,8 @@
 #define SNB_BLOCK 32
 #define SNB_FORCE_SCALE 4294967296.0f       /* 2^32, as the reference's fixed-point forces (realToFixedPoint.cu:1-2) */
 #define SNB_FORCE_SCALE_D 4294967296.0
-#define SNB_ITEM_CHUNKS 8                   /* chunks of 32 j atoms per work item */
+#define SNB_ITEM_CHUNKS 8                   /* most chunks of 32 j atoms per work item */
+#define SNB_FLAGS_MAX_BLOCKS 4096           /* parallel tile-flag build up to this many blocks (131k atoms) */
 
 enum { PBC_NONE = 0, PBC_SHIFT = 1, PBC_PAIR_ORTHO = 2, PBC_PAIR_TRICLINIC = 3 };
 enum { KIND_PLAIN = 0, KIND_RF = 1, KIND_EWALD = 2, KIND_LJPME = 3 };
@@ -49,6 +50,14 @@ struct DirectParams {
     double dalphad, dispShiftExpd, invCut6d;   // LJPME: alpha_d, [1-exp(-d_c^2)(1+d_c^2+d_c^4/2)], rc^-6
     double lambdaCd[SNB_MAX_SLICES], lambdaVd[SNB_MAX_SLICES];
     BoxD boxd;
+};
+
+// what the exact (double) cutoff predicate reads; lives in device memory so that the rare out-of-line
+// call takes a pointer instead of forcing the kernel's parameter block onto the stack
+struct ExactParams {
+    BoxD boxd;
+    double cutoff2d;
+    int periodic;
 };
 
 // ---- small device helpers ---------------------------------------------------------

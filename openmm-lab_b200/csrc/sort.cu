@@ -109,29 +109,28 @@ __global__ void k_scanCells(const int* __restrict__ count, int* __restrict__ sta
 }
 
 // ---- 3. scatter + deterministic order inside each cell --------------------------------
+// k_scatterAtoms drops every atom into its cell's segment at the slot the atomic counter gave it
+// (run-to-run order varies); k_rankInCell then gives every atom its final place = the number of
+// atoms of the same cell with a smaller index, so the sorted order is a function of the positions only.
 __global__ void k_scatterAtoms(SortArgs a) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
     if (i < a.numAtoms)
-        a.sortedAtom[a.cellStart[a.atomCell[i]]+a.atomSlot[i]] = i;
+        a.cellScratch[a.cellStart[a.atomCell[i]]+a.atomSlot[i]] = i;
     // padding slots of the last block
     int pad = a.numAtoms+i;
     if (i < a.paddedAtoms-a.numAtoms)
         a.sortedAtom[pad] = -1;
 }
 
-__global__ void k_sortCells(SortArgs a) {
-    int c = blockIdx.x*blockDim.x+threadIdx.x;
-    if (c >= a.numCells)
+__global__ void k_rankInCell(SortArgs a) {
+    int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (i >= a.numAtoms)
         return;
-    int s = a.cellStart[c], e = a.cellStart[c+1];
-    for (int i = s+1; i < e; i++) {
-        int v = a.sortedAtom[i], j = i-1;
-        while (j >= s && a.sortedAtom[j] > v) {
-            a.sortedAtom[j+1] = a.sortedAtom[j];
-            j--;
-        }
-        a.sortedAtom[j+1] = v;
-    }
+    const int c = a.atomCell[i], s = a.cellStart[c], e = a.cellStart[c+1];
+    int rank = 0;
+    for (int k = s; k < e; k++)
+        rank += a.cellScratch[k] < i;
+    a.sortedAtom[s+rank] = i;
 }
 
 // ---- 4. blocks of 32: bounding box, centre, local coordinates -------------------------
@@ -209,6 +208,6 @@ void launchSort(const SortArgs& a, cudaStream_t stream) {
     k_assignCells<<<atomBlocks, threads, 0, stream>>>(a);
     k_scanCells<<<1, 1024, 0, stream>>>(a.cellCount, a.cellStart, a.numCells);
     k_scatterAtoms<<<atomBlocks, threads, 0, stream>>>(a);
-    k_sortCells<<<(a.numCells+threads-1)/threads, threads, 0, stream>>>(a);
+    k_rankInCell<<<atomBlocks, threads, 0, stream>>>(a);
     k_blockBounds<<<(a.numBlocks*32+threads-1)/threads, threads, 0, stream>>>(a);
 }
