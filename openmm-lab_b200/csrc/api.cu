@@ -186,7 +186,7 @@ struct snb_handle {
     cudaEvent_t evSorted = nullptr, evPmeDone = nullptr;
     int numSMs = 148;
     DevBuf<double> posd, paramsD, exception14, blockCenter, extent, energyBuf, forcesOutD;
-    DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn;
+    DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt;
     DevBuf<double4> posqLocalD, sparamsD;
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
                 exclStart, exclList, is14D, counters, cellScratch;
@@ -434,13 +434,14 @@ snb_handle* createHandle(const snb_desc& d) {
         h.posqLocal.alloc(h.NP); h.sparams.alloc(h.NP);
         if (h.doublePrecision) { h.posqLocalD.alloc(h.NP); h.sparamsD.alloc(h.NP); }
         h.blockCenter.alloc(3*(size_t) h.NB); h.blockExt.alloc(h.NB);
+        h.octetCenter.alloc(4*(size_t) h.NB); h.octetExt.alloc(4*(size_t) h.NB);
         h.extent.alloc(6);
-        h.energyBuf.alloc(2*SNB_MAX_SLICES);
+        h.energyBuf.alloc(32*2*SNB_MAX_SLICES);    // 32 replicas of the slice-energy table (direct.cu), summed on the host
         h.counters.alloc(8);
         h.forceSorted.alloc(3*(size_t) h.NP); h.forceOrig.alloc(3*(size_t) h.NP);
         h.forcesOutD.alloc(3*(size_t) h.N);
         h.hPos.alloc(3*(size_t) h.N); h.hForces.alloc(3*(size_t) h.N);
-        h.hEnergy.alloc(2*SNB_MAX_SLICES);
+        h.hEnergy.alloc(32*2*SNB_MAX_SLICES);
         h.hCounters.alloc(8);
         h.sliceEnergies.assign(2*h.L, 0.0);
         if (h.method == SNB_PME || h.method == SNB_LJPME)
@@ -577,20 +578,21 @@ void setupCells(snb_handle& h, const double* box, bool periodic) {
 void ensureListCapacity(snb_handle& h, const double* box, bool periodic) {
     if (h.maxChunks > 0)
         return;
-    size_t perBlock;
+    // chunks of 32 j atoms per octet (the i side of the list works on octets of 8 atoms)
+    size_t perOctet;
     if (h.method == SNB_NO_CUTOFF)
-        perBlock = h.NB+1;
+        perOctet = h.NB+2;
     else {
         double density = periodic ? h.N/(box[0]*box[4]*box[8]) : 100.0;
-        double reach = h.cutoff+0.45;
-        double atoms = 0.5*density*(4.0/3.0*M_PI*reach*reach*reach)*1.3+96;
-        perBlock = std::min<size_t>((size_t) (atoms/32)+2, (size_t) h.NB+1);
+        double reach = h.cutoff+0.3;
+        double atoms = 0.5*density*(4.0/3.0*M_PI*reach*reach*reach)*1.3+72;
+        perOctet = std::min<size_t>((size_t) (atoms/32)+2, (size_t) h.NB+2);
     }
-    h.maxChunks = std::max<size_t>(64, perBlock*h.NB);
-    // work items of 1..8 chunks: small systems need every chunk as its own item to fill 148 SMs
+    h.maxChunks = std::max<size_t>(64, perOctet*4*h.NB);
+    // work items of 1..8 chunks: small systems need short items to fill 148 SMs many times over
     size_t expectedChunks = h.maxChunks*2/3;
-    h.itemChunks = (int) std::max<size_t>(1, std::min<size_t>(SNB_ITEM_CHUNKS, expectedChunks/((size_t) h.numSMs*24*8)));
-    h.maxItems = h.maxChunks/h.itemChunks+2*(size_t) h.NB+16;
+    h.itemChunks = (int) std::max<size_t>(2, std::min<size_t>(SNB_ITEM_CHUNKS, expectedChunks/((size_t) h.numSMs*24*6)));
+    h.maxItems = h.maxChunks/h.itemChunks+8*(size_t) h.NB+16;
     h.jList.alloc(h.maxChunks*32);
     h.workItems.alloc(h.maxItems);
 }
@@ -634,7 +636,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
 
     CUDA_CHECK(cudaMemsetAsync(h.forceSorted.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
     CUDA_CHECK(cudaMemsetAsync(h.forceOrig.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
-    CUDA_CHECK(cudaMemsetAsync(h.energyBuf.p, 0, sizeof(double)*2*SNB_MAX_SLICES, st));
+    CUDA_CHECK(cudaMemsetAsync(h.energyBuf.p, 0, sizeof(double)*32*2*SNB_MAX_SLICES, st));
     CUDA_CHECK(cudaMemsetAsync(h.counters.p, 0, sizeof(int)*8, st));
     tm.mark(0);
 
@@ -654,7 +656,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
         sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
-        sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p;
+        sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
         launchSort(sa, st);
         tm.mark(1);
         if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
@@ -666,16 +668,16 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         la.cutoff = (float) (h.cutoff*(1.0+1e-5)+1e-5);
         la.box = bf; la.boxd = bd;
         la.sortedAtom = h.sortedAtom.p; la.sortedPos = h.sortedPos.p; la.posqLocal = h.posqLocal.p;
-        la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p;
+        la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p; la.octetCenter = h.octetCenter.p; la.octetExt = h.octetExt.p;
         la.exclStart = h.exclStart.p; la.exclList = h.exclList.p;
         la.jList = h.jList.p; la.workItems = h.workItems.p; la.counters = h.counters.p;
         la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems; la.itemChunks = h.itemChunks;
         la.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); la.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); la.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
-        if (h.NB <= SNB_FLAGS_MAX_BLOCKS) {
-            la.flagStride = (h.NB+31)&~31;
-            h.tileFlags.alloc((size_t) h.NB*la.flagStride);
-            la.tileFlags = h.tileFlags.p;
-        }
+        if (h.NB > SNB_FLAGS_MAX_BLOCKS)
+            throw SnbException(SNB_ERR_UNSUPPORTED, "systems above 131072 atoms need the grid-based candidate search (not in this build)");
+        la.flagStride = (h.NB+31)&~31;
+        h.tileFlags.alloc(4*(size_t) h.NB*la.flagStride);
+        la.tileFlags = h.tileFlags.p;
         launchBuildList(la, st, h.numSMs);
         tm.mark(2);
 
@@ -702,7 +704,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
         da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
         da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
-        da.blockCenter = h.blockCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.workItems = h.workItems.p;
+        da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.workItems = h.workItems.p;
         da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
         launchDirect(da, st, h.numSMs);
         tm.mark(3);
@@ -788,7 +790,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
             CUDA_CHECK(cudaMemcpyAsync(h.hForces.p, h.forcesOutD.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyDeviceToHost, st));
     }
     tm.mark(9);
-    CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, h.energyBuf.p, sizeof(double)*2*SNB_MAX_SLICES, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, h.energyBuf.p, sizeof(double)*32*2*SNB_MAX_SLICES, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     CUDA_CHECK(cudaGetLastError());
@@ -813,7 +815,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
     h.countersOut[3] = h.hCounters.p[1];
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
-    if (includeDirect) launches += (periodic ? 5 : 6)+(h.NB <= SNB_FLAGS_MAX_BLOCKS ? 2 : 1)+1+(h.X > 0 ? 1 : 0);
+    if (includeDirect) launches += (periodic ? 5 : 6)+2+1+(h.X > 0 ? 1 : 0);
     if (includeRecip && pmeFamily) launches += (h.deterministic ? 4 : 3)*(h.method == SNB_LJPME ? 2 : 1);
     if (includeForces) launches += 1;
     if (!hostPositions) launches += 1;
@@ -823,8 +825,12 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
 
 void finishEnergies(snb_handle& h, const double* box, int flags) {
     const bool includeDirect = flags&SNB_INCLUDE_DIRECT, includeRecip = flags&SNB_INCLUDE_RECIPROCAL;
-    for (int k = 0; k < 2*h.L; k++)
-        h.sliceEnergies[k] = h.hEnergy.p[k];
+    for (int k = 0; k < 2*h.L; k++) {
+        double sum = 0;
+        for (int r = 0; r < 32; r++)
+            sum += h.hEnergy.p[(size_t) r*2*SNB_MAX_SLICES+k];
+        h.sliceEnergies[k] = sum;
+    }
     if (includeRecip && (h.method == SNB_PME || h.method == SNB_LJPME))
         for (int s = 0; s < h.S; s++) {
             h.sliceEnergies[2*(s*(s+3)/2)] += h.selfC[s];

@@ -1,14 +1,16 @@
 // Direct-space tile kernel (north-star subsystem 2).
 //
-// One warp per work item = one i block (32 sorted atoms, one per lane, kept in registers) against
-// up to SNB_ITEM_CHUNKS chunks of 32 compacted j atoms.  A chunk's j atoms are gathered with
-// coalesced float4 loads, shifted into the i block's frame and staged in shared memory; in step s
-// lane l works on slot (l+s)&31, so every step touches 32 different j atoms, the j-force
-// accumulators travel between lanes by warp shuffle and come home after 32 steps, and no
-// reduction tree is needed.  Per-pair arithmetic is FP32 (rsqrt, ex2, polynomial erfc); the
-// i forces are carried in FP64 across chunks, all forces leave as 2^32 fixed-point 64-bit atomics
-// (order independent => bit-reproducible), slice energies are accumulated per j subset in FP32
-// per chunk and FP64 beyond.
+// One warp per work item = one octet of i atoms against up to SNB_ITEM_CHUNKS chunks of 32 compacted
+// j atoms.  The octet is held four times over in the warp (lane = 8*copy + k, atom k of the octet);
+// copy c owns j slots 8c..8c+7 of the chunk, so a chunk is 8 steps of 32 pairs.  A chunk's j atoms are
+// gathered with coalesced float4 loads, shifted into the octet's frame (one periodic image per j atom
+// where the box allows it) and staged in shared memory.  In step s lane (c,k) works on slot
+// 8c + (k+s)%8: every step touches 32 different pairs, the j-force accumulators travel between the 8
+// lanes of a copy by warp shuffle and are home after 8 steps, so no reduction tree is needed; the four
+// copies' i forces are summed by shuffle once per work item.
+// Pair arithmetic is FP32 (MUFU rsqrt + Newton step, MUFU ex2, polynomial erfc); i forces are carried
+// in FP64 across chunks; all forces leave as 2^32 fixed-point 64-bit atomics (order independent =>
+// bit-reproducible); slice energies are accumulated per j subset in FP32 per chunk and FP64 beyond.
 //
 // Pair arithmetic follows the reference's Reference platform:
 //   Ewald/PME/LJPME direct:  platforms/reference/src/ReferenceSlicedLJCoulombIxn.cpp:351-429
@@ -16,13 +18,14 @@
 // (behavioural cross-reference on the GPU side: platforms/common/src/kernels/coulombLennardJones.cc:1-124).
 #include "kernels.cuh"
 
-#define DIRECT_WARPS 8
+#define DIRECT_CTAS_PER_SM 24
+#define ENERGY_REPLICAS 32      /* copies of the slice-energy table, to spread the final atomics */
 
 template <int KIND> void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid);
 
-// Precision traits: R = float is the mixed-precision path (FP32 pair arithmetic, MUFU rsqrt/ex2,
-// polynomial erfc); R = double is the double-precision mode (the analogue of the reference CUDA
-// platform's Precision=double), used to prove parity to 1e-5 on every quantity.
+// Precision traits: R = float is the mixed-precision path; R = double is the double-precision mode
+// (the analogue of the reference CUDA platform's Precision=double), used to prove parity to 1e-5 on
+// every quantity.
 template <typename R> struct Real;
 template <> struct Real<float> {
     typedef float4 vec4;
@@ -73,14 +76,16 @@ template <typename R, int NSUB> struct SubsetTable {
 };
 
 template <typename R, int KIND, int PBC, int NSUB, bool ENERGY>
-__global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_direct(DirectArgs a) {
+__global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? DIRECT_CTAS_PER_SM/2 : DIRECT_CTAS_PER_SM) : 8) k_direct(DirectArgs a) {
     constexpr int NS = NSUB > 0 ? NSUB : SNB_MAX_SUBSETS;
     typedef typename Real<R>::vec4 vec4;
-    __shared__ vec4 sPos[DIRECT_WARPS][32];
-    __shared__ vec4 sPrm[DIRECT_WARPS][32];
-    __shared__ int2 sEnt[DIRECT_WARPS][32];
-    __shared__ double sEnergy[2*SNB_MAX_SLICES];
-    const int lane = threadIdx.x&31, w = threadIdx.x>>5;
+    // one warp per CTA: the staging area is addressed by the slot alone
+    __shared__ vec4 sPos[32];
+    __shared__ vec4 sPrm[32];
+    __shared__ unsigned sMask[32];
+    __shared__ int sJ[32];
+    const int lane = threadIdx.x;
+    const int copy = lane>>3, k = lane&7;
     const unsigned full = 0xffffffffu;
     const DirectParams& p = a.p;
     const int numSub = NSUB > 0 ? NSUB : a.numSubsets;
@@ -93,12 +98,18 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_dir
     const R dalpha2 = (R) (p.dalphad*p.dalphad), dispShiftExp = (R) p.dispShiftExpd, invCut6 = (R) p.invCut6d;
     const R bAx = (R) p.boxd.ax, bBy = (R) p.boxd.by, bCz = (R) p.boxd.cz;
     const R iAx = (R) (1.0/p.boxd.ax), iBy = (R) (1.0/p.boxd.by), iCz = (R) (1.0/p.boxd.cz);
-    if (ENERGY) {
-        for (int k = threadIdx.x; k < 2*SNB_MAX_SLICES; k += blockDim.x)
-            sEnergy[k] = 0.0;
-        __syncthreads();
+    const unsigned kBit = 1u<<k;
+    const int srcLane = (copy<<3)|((k+1)&7);       // the j accumulators move one lane down inside the copy
+    // slice energies of this thread over all its work items, keyed by (own subset, j subset); reduced
+    // over the warp once, at the end of the kernel
+    double accC[NS > 4 ? 1 : NS][NS > 4 ? 1 : NS], accV[NS > 4 ? 1 : NS][NS > 4 ? 1 : NS];
+    if (ENERGY && NSUB > 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+            for (int u = 0; u < NS; u++)
+                accC[s][u] = accV[s][u] = 0.0;
     }
-    // per-lane energy totals keyed by (own subset at the time, j subset) are flushed per item
     for (;;) {
         int item = 0;
         if (lane == 0)
@@ -107,15 +118,18 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_dir
         if (item >= numItems)
             break;
         const int4 wi = a.workItems[item];
-        const int I = wi.x;
-        const bool perPair = PBC == PBC_SHIFT && wi.w != 0;    // i block too wide for one image per j atom
-        const int ki = I*32+lane;
+        const int O = wi.x, I = O>>2;
+        const bool perPair = PBC == PBC_SHIFT && wi.w != 0;    // octet too wide for one image per j atom
+        const int ki = O*8+k;
         const vec4 pi = Real<R>::pos(a)[ki];
         const vec4 si4 = Real<R>::prm(a)[ki];
         const int subI = (int) si4.z;           // subsets travel as exact small reals, -1 = padding lane
         const bool iValid = subI >= 0;
         const int origI = a.sortedAtom[ki];
         const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
+        const float4 oc = a.octetCenter[O];
+        // a padding lane can never be "in range": its upper bound is negative
+        const R myCutHi = iValid ? cutoffHi : (R) -1;
         SubsetTable<R, NSUB> t;
 #pragma unroll
         for (int s = 0; s < NS; s++) {
@@ -137,28 +151,29 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_dir
                 R ox = (R) (a.blockCenter[3*J]-cIx), oy = (R) (a.blockCenter[3*J+1]-cIy), oz = (R) (a.blockCenter[3*J+2]-cIz);
                 pj.x += ox; pj.y += oy; pj.z += oz;
                 if (PBC == PBC_SHIFT && !perPair) {
-                    // one image per j atom, chosen relative to the i block's centre (valid while
-                    // halfBox - cutoff exceeds the block's half extent; validated in k_blockBounds' caller)
-                    pj.x -= bAx*Real<R>::rint(pj.x*iAx);
-                    pj.y -= bBy*Real<R>::rint(pj.y*iBy);
-                    pj.z -= bCz*Real<R>::rint(pj.z*iCz);
+                    // one image per j atom, chosen relative to the octet's centre (valid while
+                    // halfBox - cutoff exceeds the octet's half extent; k_compactList flags the rest)
+                    pj.x -= bAx*Real<R>::rint((pj.x-(R) oc.x)*iAx);
+                    pj.y -= bBy*Real<R>::rint((pj.y-(R) oc.y)*iBy);
+                    pj.z -= bCz*Real<R>::rint((pj.z-(R) oc.z)*iCz);
                 }
             }
             __syncwarp();
-            sPos[w][lane] = pj;
-            sPrm[w][lane] = sj4;
-            sEnt[w][lane] = ent;
+            sPos[lane] = pj;
+            sPrm[lane] = sj4;
+            sMask[lane] = (unsigned) ent.y;
+            sJ[lane] = ent.x;
             __syncwarp();
             R fix = 0, fiy = 0, fiz = 0, fjx = 0, fjy = 0, fjz = 0;
 #pragma unroll
             for (int s = 0; s < NS; s++)
                 t.eC[s] = t.eV[s] = 0;
-            // ---- 32 x 32 pair steps ------------------------------------------------------
-#pragma unroll 4
-            for (int s = 0; s < 32; s++) {
-                const int slot = (lane+s)&31;
-                const vec4 q = sPos[w][slot];
-                const unsigned mj = (unsigned) sEnt[w][slot].y;
+            // ---- 8 steps of 32 pairs --------------------------------------------------------
+#pragma unroll 2
+            for (int s = 0; s < 8; s++) {
+                const int slot = (copy<<3)|((k+s)&7);
+                const vec4 q = sPos[slot];
+                const unsigned mj = sMask[slot];
                 R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
                 if (PBC == PBC_SHIFT && perPair) {
                     dx -= bAx*Real<R>::rint(dx*iAx);
@@ -166,25 +181,26 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_dir
                     dz -= bCz*Real<R>::rint(dz*iCz);
                 }
                 else if (PBC == PBC_PAIR_TRICLINIC) {
-                    R k = Real<R>::rint(dz*iCz);
-                    dx -= k*(R) p.boxd.cx; dy -= k*(R) p.boxd.cy; dz -= k*bCz;
-                    k = Real<R>::rint(dy*iBy);
-                    dx -= k*(R) p.boxd.bx; dy -= k*bBy;
-                    k = Real<R>::rint(dx*iAx);
-                    dx -= k*bAx;
+                    R m = Real<R>::rint(dz*iCz);
+                    dx -= m*(R) p.boxd.cx; dy -= m*(R) p.boxd.cy; dz -= m*bCz;
+                    m = Real<R>::rint(dy*iBy);
+                    dx -= m*(R) p.boxd.bx; dy -= m*bBy;
+                    m = Real<R>::rint(dx*iAx);
+                    dx -= m*bAx;
                 }
                 const R r2 = dx*dx+dy*dy+dz*dz;
-                // one compare on the hot path: r2 below cutoff2 + band; pairs inside the band (about 1e-5 of
-                // them) are then decided exactly, as the CPU oracle decides them
-                bool in = iValid && !((mj>>lane)&1u);
+                // one compare on the hot path: r2 below cutoff2 + band; pairs inside the band (about 1e-5
+                // of them) are then decided exactly, as the CPU oracle decides them
+                bool in = !(mj&kBit);
                 if (KIND != KIND_PLAIN) {
-                    in = in && r2 < cutoffHi;
+                    in = in && r2 < myCutHi;
                     if (in && r2 > cutoffLo)
-                        in = exactInRange(a.posd, origI, a.sortedAtom[sEnt[w][slot].x], a.exact);
+                        in = exactInRange(a.posd, origI, a.sortedAtom[sJ[slot]], a.exact);
                 }
+                else
+                    in = in && iValid;
                 if (in) {
-                    const vec4 prm = sPrm[w][slot];
-                    const int subJ = (int) prm.z;
+                    const vec4 prm = sPrm[slot];
                     const R invR = Real<R>::rsqrt(r2);
                     const R invR2 = invR*invR;
                     const R r = r2*invR;
@@ -240,12 +256,12 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_dir
                         lc = t.lamC[0]; lv = t.lamV[0];
 #pragma unroll
                         for (int u = 1; u < NS; u++) {
-                            lc = subJ == u ? t.lamC[u] : lc;
-                            lv = subJ == u ? t.lamV[u] : lv;
+                            lc = prm.z == (R) u ? t.lamC[u] : lc;
+                            lv = prm.z == (R) u ? t.lamV[u] : lv;
                         }
                     }
                     else {
-                        const int sl = sliceOf(subI, subJ);
+                        const int sl = sliceOf(subI, (int) prm.z);
                         lc = (R) p.lambdaCd[sl]; lv = (R) p.lambdaVd[sl];
                     }
                     const R f = lv*fv+lc*fc;
@@ -255,27 +271,27 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_dir
                         if (NSUB > 0) {
 #pragma unroll
                             for (int u = 0; u < NS; u++) {
-                                t.eC[u] += subJ == u ? ec : (R) 0;
-                                t.eV[u] += subJ == u ? ev : (R) 0;
+                                t.eC[u] += prm.z == (R) u ? ec : (R) 0;
+                                t.eV[u] += prm.z == (R) u ? ev : (R) 0;
                             }
                         }
                         else {
-                            // many subsets: straight to the block's shared table (rare configuration)
-                            atomicAdd(&sEnergy[2*sliceOf(subI, subJ)], (double) ec);
-                            atomicAdd(&sEnergy[2*sliceOf(subI, subJ)+1], (double) ev);
+                            // many subsets: straight to the global table (rare configuration)
+                            double* table = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
+                            atomicAdd(&table[2*sliceOf(subI, (int) prm.z)], (double) ec);
+                            atomicAdd(&table[2*sliceOf(subI, (int) prm.z)+1], (double) ev);
                         }
                     }
                     if (DUMP) {
-                        const int origJ = a.sortedAtom[sEnt[w][slot].x];
+                        const int origJ = a.sortedAtom[sJ[slot]];
                         unsigned long long idx = atomicAdd(a.pairDumpCount, 1ull);
                         if ((long long) idx < a.pairDumpCapacity)
                             a.pairDump[idx] = make_int2(min(origI, origJ), max(origI, origJ));
                     }
                 }
-                // the j accumulators move one lane down; after 32 steps they are home
-                fjx = __shfl_sync(full, fjx, (lane+1)&31);
-                fjy = __shfl_sync(full, fjy, (lane+1)&31);
-                fjz = __shfl_sync(full, fjz, (lane+1)&31);
+                fjx = __shfl_sync(full, fjx, srcLane);
+                fjy = __shfl_sync(full, fjy, srcLane);
+                fjz = __shfl_sync(full, fjz, srcLane);
             }
             if (ent.x >= 0) {
                 addFixed(&a.forceSorted[ent.x], Real<R>::fixed(fjx));
@@ -291,25 +307,43 @@ __global__ void __launch_bounds__(DIRECT_WARPS*32, sizeof(R) == 4 ? 3 : 1) k_dir
                 }
             }
         }
-        if (iValid) {
+        // the four copies of the octet: sum their i forces (and energies) onto copy 0
+        for (int o = 8; o < 32; o <<= 1) {
+            Fx += __shfl_xor_sync(full, Fx, o);
+            Fy += __shfl_xor_sync(full, Fy, o);
+            Fz += __shfl_xor_sync(full, Fz, o);
+        }
+        if (iValid && copy == 0) {
             addFixed(&a.forceSorted[ki], toFixedD(Fx));
             addFixed(&a.forceSorted[a.paddedAtoms+ki], toFixedD(Fy));
             addFixed(&a.forceSorted[2*a.paddedAtoms+ki], toFixedD(Fz));
         }
-        if (ENERGY && NSUB > 0 && iValid) {
+        if (ENERGY && NSUB > 0) {
 #pragma unroll
-            for (int u = 0; u < NS; u++) {
-                if (t.EC[u] != 0.0) atomicAdd(&sEnergy[2*sliceOf(subI, u)], t.EC[u]);
-                if (t.EV[u] != 0.0) atomicAdd(&sEnergy[2*sliceOf(subI, u)+1], t.EV[u]);
-            }
+            for (int s = 0; s < NS; s++)
+#pragma unroll
+                for (int u = 0; u < NS; u++) {
+                    accC[s][u] += subI == s ? t.EC[u] : 0.0;
+                    accV[s][u] += subI == s ? t.EV[u] : 0.0;
+                }
         }
     }
-    if (ENERGY) {
-        __syncthreads();
-        const int L = numSub*(numSub+1)/2;
-        for (int k = threadIdx.x; k < 2*L; k += blockDim.x)
-            if (sEnergy[k] != 0.0)
-                atomicAdd(&a.energyBuf[k], sEnergy[k]);
+    if (ENERGY && NSUB > 0) {
+        double* table = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+            for (int u = 0; u < NS; u++) {
+                double ecs = accC[s][u], evs = accV[s][u];
+                for (int o = 16; o > 0; o >>= 1) {
+                    ecs += __shfl_xor_sync(full, ecs, o);
+                    evs += __shfl_xor_sync(full, evs, o);
+                }
+                if (lane == 0 && s < numSub && u < numSub) {
+                    if (ecs != 0.0) atomicAdd(&table[2*sliceOf(s, u)], ecs);
+                    if (evs != 0.0) atomicAdd(&table[2*sliceOf(s, u)+1], evs);
+                }
+            }
     }
 }
 
@@ -317,13 +351,13 @@ template <int KIND, int PBC, int NSUB>
 static void launch4(const DirectArgs& a, cudaStream_t st, int grid) {
     if (a.doublePrecision) {
         // the double-precision mode is a correctness mode: one instantiation (energies always on)
-        k_direct<double, KIND, PBC, NSUB, true><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
+        k_direct<double, KIND, PBC, NSUB, true><<<grid/3, 32, 0, st>>>(a);
         return;
     }
     if (a.needEnergy || a.pairDump)
-        k_direct<float, KIND, PBC, NSUB, true><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
+        k_direct<float, KIND, PBC, NSUB, true><<<grid, 32, 0, st>>>(a);
     else
-        k_direct<float, KIND, PBC, NSUB, false><<<grid, DIRECT_WARPS*32, 0, st>>>(a);
+        k_direct<float, KIND, PBC, NSUB, false><<<grid, 32, 0, st>>>(a);
 }
 
 template <int KIND, int PBC>
@@ -345,7 +379,7 @@ void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid) {
             break;
         case PBC_SHIFT:
         case PBC_PAIR_ORTHO:
-            // orthorhombic box: one image per j atom, or per-pair wrapping for the (few) i blocks whose
+            // orthorhombic box: one image per j atom, or per-pair wrapping for the (few) octets whose
             // bounding box is too wide for that -- decided per work item
             if (KIND != KIND_PLAIN) launch3<KIND, PBC_SHIFT>(a, st, grid);
             break;

@@ -22,6 +22,7 @@ struct SortArgs {
     double4 *posqLocalD, *sparamsD;  // double-precision mode only (else null)
     double* blockCenter;
     float4* blockExt;
+    float4 *octetCenter, *octetExt;  // [4*numBlocks] block-local centre / half extents of every octet
 };
 void launchSort(const SortArgs& a, cudaStream_t stream);
 
@@ -35,6 +36,7 @@ struct ListArgs {
     const float4* posqLocal;
     const double* blockCenter;
     const float4* blockExt;
+    const float4 *octetCenter, *octetExt;
     const int* exclStart;   // CSR over ORIGINAL atom indices: partners of each atom (both directions)
     const int* exclList;
     int2* jList;
@@ -56,6 +58,7 @@ struct DirectArgs {
     const double4* posqLocalD;     // double-precision mode only
     const double4* sparamsD;
     const double* blockCenter;
+    const float4* octetCenter;
     const double* posd;
     const ExactParams* exact;
     const int2* jList;

@@ -194,8 +194,30 @@ __global__ void k_blockBounds(SortArgs a) {
         // half extents, rounded up so the box is conservative in single precision
         a.blockExt[warp] = make_float4(__double2float_ru(0.5*(hi[0]-lo[0])), __double2float_ru(0.5*(hi[1]-lo[1])),
                                        __double2float_ru(0.5*(hi[2]-lo[2])), 0.f);
-        if (a.checkShift && (0.5*(hi[0]-lo[0]) >= a.shiftLimit[0] || 0.5*(hi[1]-lo[1]) >= a.shiftLimit[1] || 0.5*(hi[2]-lo[2]) >= a.shiftLimit[2]))
-            a.counters[4] = 1;
+    }
+    // bounding boxes of the four octets (8 consecutive atoms) of the block, in block-local coordinates:
+    // the i side of the tile list works on octets (a tighter box => fewer out-of-range pairs per tile)
+    float ol[3] = {pl.x, pl.y, pl.z}, oh[3] = {pl.x, pl.y, pl.z};
+    if (atom < 0)
+        for (int d = 0; d < 3; d++) { ol[d] = 3.0e38f; oh[d] = -3.0e38f; }
+    for (int d = 0; d < 3; d++)
+        for (int o = 4; o > 0; o >>= 1) {
+            ol[d] = fminf(ol[d], __shfl_xor_sync(0xffffffffu, ol[d], o));
+            oh[d] = fmaxf(oh[d], __shfl_xor_sync(0xffffffffu, oh[d], o));
+        }
+    if ((lane&7) == 0) {
+        const int oct = warp*4+(lane>>3);
+        if (ol[0] > oh[0]) {                      // empty octet (padding)
+            a.octetCenter[oct] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a.octetExt[oct] = make_float4(-1.f, -1.f, -1.f, 0.f);
+        }
+        else {
+            const float cx = 0.5f*(ol[0]+oh[0]), cy = 0.5f*(ol[1]+oh[1]), cz = 0.5f*(ol[2]+oh[2]);
+            a.octetCenter[oct] = make_float4(cx, cy, cz, 0.f);
+            // max distance from the rounded centre to either face, plus an ulp of slack
+            a.octetExt[oct] = make_float4(fmaxf(oh[0]-cx, cx-ol[0])*1.000001f+1e-7f, fmaxf(oh[1]-cy, cy-ol[1])*1.000001f+1e-7f,
+                                          fmaxf(oh[2]-cz, cz-ol[2])*1.000001f+1e-7f, 0.f);
+        }
     }
 }
 
