@@ -190,8 +190,7 @@ struct snb_handle {
     DevBuf<double4> posqLocalD, sparamsD;
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
                 exclStart, exclList, is14D, counters, cellScratch;
-    DevBuf<int2> exceptionAtomsD, jList;
-    DevBuf<unsigned> tileFlags;
+    DevBuf<int2> exceptionAtomsD, jList, cellRange;
     DevBuf<ExactParams> exactD;
     PinnedBuf<ExactParams> exactH;
     DevBuf<int4> workItems;
@@ -573,6 +572,7 @@ void setupCells(snb_handle& h, const double* box, bool periodic) {
     CUDA_CHECK(cudaStreamSynchronize(h.stream));
     h.cellCount.alloc(h.numCells);
     h.cellStart.alloc(h.numCells+1);
+    h.cellRange.alloc(h.numCells);
 }
 
 void ensureListCapacity(snb_handle& h, const double* box, bool periodic) {
@@ -654,7 +654,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         sa.boxd = bd;
         sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.paramsD = h.paramsD.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
         sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
-        sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
+        sa.cellRange = h.cellRange.p; sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
         launchSort(sa, st);
@@ -673,11 +673,10 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         la.jList = h.jList.p; la.workItems = h.workItems.p; la.counters = h.counters.p;
         la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems; la.itemChunks = h.itemChunks;
         la.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); la.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); la.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
-        if (h.NB > SNB_FLAGS_MAX_BLOCKS)
-            throw SnbException(SNB_ERR_UNSUPPORTED, "systems above 131072 atoms need the grid-based candidate search (not in this build)");
-        la.flagStride = (h.NB+31)&~31;
-        h.tileFlags.alloc(4*(size_t) h.NB*la.flagStride);
-        la.tileFlags = h.tileFlags.p;
+        la.cellRange = h.cellRange.p; la.extent = h.extent.p;
+        for (int k = 0; k < 3; k++) la.cellDim[k] = h.cellDim[k];
+        la.octLo = 0; la.octHi = 4*h.NB;
+        la.bitmapWords = (h.NB+31)/32;
         launchBuildList(la, st, h.numSMs);
         tm.mark(2);
 

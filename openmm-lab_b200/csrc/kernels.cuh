@@ -18,6 +18,7 @@ struct SortArgs {
     const int* cellRank;
     double* extent;
     int *cellCount, *cellStart, *atomCell, *atomSlot, *cellScratch, *sortedAtom, *sortedPos;
+    int2* cellRange;        // [numCells] sorted range (first, end) of every cell, by LINEAR cell index
     float4 *posqLocal, *sparams;
     double4 *posqLocalD, *sparamsD;  // double-precision mode only (else null)
     double* blockCenter;
@@ -43,8 +44,11 @@ struct ListArgs {
     int4* workItems;
     int* counters;          // [0] chunks allocated, [1] work items, [2] overflow flag, [3] next work item
     int maxChunks, maxItems, itemChunks;
-    unsigned* tileFlags;    // [numBlocks][flagStride] per-atom interaction flags (parallel build), or null
-    int flagStride;
+    const int2* cellRange;  // [numCells] sorted range of every cell, by linear cell index ((x*dimY+y)*dimZ+z)
+    int cellDim[3];
+    const double* extent;   // non-periodic methods: bounding box of all atoms (min[3], max[3])
+    int octLo, octHi;       // this rank's octets
+    int bitmapWords;        // ceil(numBlocks/32)
     float shiftLimit[3];    // halfBox - cutoff: i blocks wider than this cannot use one image per j atom
 };
 void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);

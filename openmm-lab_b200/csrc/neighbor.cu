@@ -1,4 +1,4 @@
-// Tile-list build (north-star subsystem 1b).
+// Tile-list build (north-star subsystem 1b): one fused kernel, one warp per octet.
 //
 // The sorted atoms are cut into blocks of 32 (j side) and octets of 8 (i side; 4 per block).  For
 // every octet the list holds the later atoms that come within the cutoff of the octet's bounding
@@ -6,20 +6,26 @@
 // exclusion mask over the octet's atoms.  An octet's box is much tighter than a 32-atom block's, so
 // ~40% of the pairs a tile visits are in range instead of ~27%.
 //
-//  k_tileFlags   one warp per (i block, group of 32 candidate j blocks): block-box test per lane, then
-//                for every hit block four 32-bit words of per-atom flags, one per octet of the i block.
-//  k_compactList one warp per octet: prefix sums of the popcounts place every flagged j atom in the
-//                octet's contiguous chunk range; exclusion masks are OR-ed in from the octet's own
-//                (short) exclusion lists.
+// Candidate search is O(N): the atoms were binned into small cells (sort.cu) whose sorted ranges
+// are known, so a warp
+//   1. marks, in a per-warp bitmap over the j blocks, the blocks owning atoms of the cells that
+//      overlap the octet's box dilated by the cutoff (periodic wrap in fractional coordinates,
+//      so triclinic boxes need nothing special);
+//   2. walks the set bits in ascending order and tests the 32 atoms of each candidate block against
+//      the octet's box (one ballot -> one 32-bit word of interaction flags per block);
+//   3. prefix-sums the popcounts, takes a contiguous range of chunks from the global list with one
+//      atomicAdd, writes the entries (ascending j: the tile kernel's gathers stay coalesced) and ORs
+//      the exclusion masks in from the octet's own (short) exclusion lists.
 // No order-dependent atomics: chunk CONTENTS are deterministic, only their location in the list varies.
+// A rank of a multi-GPU run builds the lists of its own octet range [octLo, octHi) only.
 //
 // No counterpart source exists in the reference tree (OpenMM's CudaNonbondedUtilities does this job
 // there, un-vendored); exclusion semantics: every exception excludes its pair
 // (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:104-112).
 #include "kernels.cuh"
 
-#define FLAG_WARPS 8
-#define COMPACT_WARPS 4
+#define LIST_WARPS 4
+#define HIT_CAP 128            /* hit blocks buffered per batch; a fuller octet emits several batches */
 
 __device__ __forceinline__ float wrapOrtho(float d, float L, float invL) { return d-L*rintf(d*invL); }
 
@@ -57,165 +63,242 @@ __device__ __forceinline__ float imageDist2(float dx, float dy, float dz, float3
     return best;
 }
 
-// candidate c of i block I: the block itself and all later blocks
-__device__ __forceinline__ int candidateBlock(const ListArgs& a, int I, int c) {
-    const int J = I+c;
-    return J < a.numBlocks ? J : -1;
-}
-__device__ __forceinline__ int candidateIndex(const ListArgs& a, int I, int J) { return J-I; }
-
-__global__ void __launch_bounds__(FLAG_WARPS*32) k_tileFlags(ListArgs a) {
-    const int lane = threadIdx.x&31;
-    const int groups = a.flagStride>>5;
-    const long long warpId = ((long long) blockIdx.x*blockDim.x+threadIdx.x)>>5;
-    if (warpId >= (long long) a.numBlocks*groups)
-        return;
-    const int I = (int) (warpId/groups), g = (int) (warpId-(long long) I*groups);
-    if (candidateBlock(a, I, g<<5) < 0)
-        return;
-    const unsigned full = 0xffffffffu;
-    const float cut2 = a.cutoff*a.cutoff;
-    const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
-    const float4 e4 = a.blockExt[I];
-    const float3 hI = make_float3(e4.x, e4.y, e4.z);
-    float4 oc[4], oe[4];
-#pragma unroll
-    for (int o = 0; o < 4; o++) {
-        oc[o] = a.octetCenter[4*I+o];
-        oe[o] = a.octetExt[4*I+o];
-    }
-    const int c = (g<<5)+lane;
-    const int J = candidateBlock(a, I, c);
-    bool hit = J >= 0;
-    if (hit && a.useCutoff && J != I) {
-        const float4 eJ = a.blockExt[J];
-        const float dx = (float) (a.blockCenter[3*J]-cIx), dy = (float) (a.blockCenter[3*J+1]-cIy), dz = (float) (a.blockCenter[3*J+2]-cIz);
-        hit = imageDist2(dx, dy, dz, make_float3(hI.x+eJ.x, hI.y+eJ.y, hI.z+eJ.z), a) < cut2;
-    }
-    unsigned bits = __ballot_sync(full, hit);
-    unsigned myWord[4] = {0u, 0u, 0u, 0u};
-    while (bits) {
-        const int b = __ffs(bits)-1;
-        bits &= bits-1;
-        const int Jb = __shfl_sync(full, J, b), j = Jb*32+lane;
-        const bool valid = a.sortedAtom[j] >= 0;
-        const float4 pj = a.posqLocal[j];
-        const float px = pj.x+(float) (a.blockCenter[3*Jb]-cIx), py = pj.y+(float) (a.blockCenter[3*Jb+1]-cIy), pz = pj.z+(float) (a.blockCenter[3*Jb+2]-cIz);
-#pragma unroll
-        for (int o = 0; o < 4; o++) {
-            // only atoms after the octet's own (every pair is visited once); the octet's own atoms are
-            // the first entries of its list (k_compactList)
-            bool acc = valid && oe[o].x >= 0.f && j > (4*I+o)*8+7;
-            if (acc && a.useCutoff)
-                acc = imageDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, make_float3(oe[o].x, oe[o].y, oe[o].z), a) < cut2;
-            const unsigned word = __ballot_sync(full, acc);
-            if (lane == b)
-                myWord[o] = word;
+// Range of cells [lo, lo+n) (periodic: modulo dim) along every axis that the box centre +- half can touch.
+__device__ __forceinline__ void cellSpan(const ListArgs& a, const double c[3], const double half[3], int lo[3], int n[3]) {
+    if (a.periodic) {
+        const double (*r)[3] = a.boxd.recip;
+        double f[3], h[3];
+        f[0] = c[0]*r[0][0]+c[1]*r[1][0]+c[2]*r[2][0];
+        f[1] = c[1]*r[1][1]+c[2]*r[2][1];
+        f[2] = c[2]*r[2][2];
+        h[0] = half[0]*fabs(r[0][0])+half[1]*fabs(r[1][0])+half[2]*fabs(r[2][0]);
+        h[1] = half[1]*fabs(r[1][1])+half[2]*fabs(r[2][1]);
+        h[2] = half[2]*fabs(r[2][2]);
+        for (int d = 0; d < 3; d++) {
+            const int dim = a.cellDim[d];
+            const int l = (int) floor((f[d]-h[d])*dim), u = (int) floor((f[d]+h[d])*dim);
+            n[d] = min(u-l+1, dim);
+            int m = l%dim;
+            lo[d] = n[d] == dim ? 0 : (m < 0 ? m+dim : m);
         }
     }
-    if (c < a.flagStride)
-#pragma unroll
-        for (int o = 0; o < 4; o++)
-            a.tileFlags[(size_t) (4*I+o)*a.flagStride+c] = myWord[o];
+    else {
+        for (int d = 0; d < 3; d++) {
+            const int dim = a.cellDim[d];
+            const double e0 = a.extent[d], span = a.extent[3+d]-e0;
+            int l = 0, u = 0;
+            if (span > 0) {
+                l = max(0, min(dim-1, (int) floor((c[d]-half[d]-e0)/span*dim)));
+                u = max(0, min(dim-1, (int) floor((c[d]+half[d]-e0)/span*dim)));
+            }
+            lo[d] = l;
+            n[d] = u-l+1;
+        }
+    }
 }
 
-__global__ void __launch_bounds__(COMPACT_WARPS*32) k_compactList(ListArgs a) {
-    extern __shared__ int sBase[];                  // [COMPACT_WARPS][flagStride] list-relative start of every candidate
+__global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
+    extern __shared__ unsigned sMem[];
     const int lane = threadIdx.x&31, w = threadIdx.x>>5;
-    const int O = blockIdx.x*COMPACT_WARPS+w;       // octet
-    if (O >= 4*a.numBlocks)
+    const int O = a.octLo+blockIdx.x*LIST_WARPS+w;      // octet
+    if (O >= a.octHi)
         return;
     const float4 ext = a.octetExt[O];
     if (ext.x < 0.f)
-        return;                                     // padding octet
-    const int I = O>>2;
-    int* base = sBase+(size_t) w*a.flagStride;
+        return;                                         // padding octet
+    unsigned* bm = sMem+(size_t) w*(a.bitmapWords+3*HIT_CAP);
+    int* hitJ = (int*) (bm+a.bitmapWords);
+    unsigned* hitWord = (unsigned*) (hitJ+HIT_CAP);
+    int* hitBase = (int*) (hitWord+HIT_CAP);
     const unsigned full = 0xffffffffu;
-    const unsigned* row = a.tileFlags+(size_t) O*a.flagStride;
-    const int numCand = a.numBlocks-I;
-    // pass 1: positions (the octet's own atoms occupy entries 0..7)
-    int running = 8;
-    for (int c0 = 0; c0 < numCand; c0 += 32) {
-        const int c = c0+lane;
-        const unsigned word = c < numCand ? row[c] : 0u;
-        const int cnt = __popc(word);
-        int incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(full, incl, o);
-            if (lane >= o) incl += t;
+    const int I = O>>2, lastI = O*8+7, wFirst = I>>5;
+    const float4 oc = a.octetCenter[O];
+    const float3 oe = make_float3(ext.x, ext.y, ext.z);
+    const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
+    const float cut2 = a.cutoff*a.cutoff;
+
+    // ---- 1. candidate blocks ------------------------------------------------------------------
+    for (int k = wFirst+lane; k < a.bitmapWords; k += 32)
+        bm[k] = 0u;
+    __syncwarp();
+    if (!a.useCutoff) {
+        // no cutoff: every later atom interacts
+        for (int k = wFirst+lane; k < a.bitmapWords; k += 32) {
+            unsigned word = full;
+            if (k == wFirst) word &= full<<(I&31);
+            const int rem = a.numBlocks-k*32;
+            if (rem < 32) word &= rem <= 0 ? 0u : (full>>(32-rem));
+            bm[k] = word;
         }
-        if (c < numCand)
-            base[c] = running+incl-cnt;
-        running += __shfl_sync(full, incl, 31);
     }
-    const int total = running, n = (total+31)>>5;
-    const int numItemsHere = (n+a.itemChunks-1)/a.itemChunks;
-    int c0g = 0, item0 = 0;
-    if (lane == 0) {
-        c0g = atomicAdd(&a.counters[0], n);
-        item0 = atomicAdd(&a.counters[1], numItemsHere);
-        if (c0g+n > a.maxChunks || item0+numItemsHere > a.maxItems)
-            a.counters[2] = 1;                      // overflow: the host grows the buffers and repeats
-    }
-    c0g = __shfl_sync(full, c0g, 0);
-    item0 = __shfl_sync(full, item0, 0);
-    if (c0g+n > a.maxChunks || item0+numItemsHere > a.maxItems)
-        return;
-    int2* out = a.jList+(size_t) c0g*32;
-    // octets too wide for the one-image-per-j-atom shortcut wrap every pair instead
-    const int wide = (a.pbcMode == PBC_SHIFT && (ext.x >= a.shiftLimit[0] || ext.y >= a.shiftLimit[1] || ext.z >= a.shiftLimit[2])) ? 1 : 0;
-    for (int k = lane; k < numItemsHere; k += 32)
-        a.workItems[item0+k] = make_int4(O, c0g+k*a.itemChunks, min(a.itemChunks, n-k*a.itemChunks), wide);
-    // pass 2: entries.  Own atoms first (lower triangle masked: every pair once), then the tail padding
-    const int ki = O*8+(lane&7);
-    const int atomI = lane < 8 ? a.sortedAtom[ki] : -1;
-    if (lane < 8)
-        out[lane] = atomI >= 0 ? make_int2(ki, (int) ((0xffu<<lane)&0xffu)) : make_int2(-1, 0xff);
-    for (int k = total+lane; k < n*32; k += 32)
-        out[k] = make_int2(-1, 0xff);
-    for (int c0 = 0; c0 < numCand; c0 += 32) {
-        const int c = c0+lane;
-        const unsigned word = c < numCand ? row[c] : 0u;
-        unsigned hits = __ballot_sync(full, word != 0u);
-        while (hits) {
-            const int b = __ffs(hits)-1;
-            hits &= hits-1;
-            const unsigned wb = __shfl_sync(full, word, b);
-            const int J = candidateBlock(a, I, c0+b);
-            if ((wb>>lane)&1u)
-                out[base[c0+b]+__popc(wb&((1u<<lane)-1))] = make_int2(J*32+lane, 0);
+    else {
+        const double margin = 1e-5;     // block-local float coordinates vs the double coordinates the cells were cut from
+        const double c[3] = {cIx+(double) oc.x, cIy+(double) oc.y, cIz+(double) oc.z};
+        const double half[3] = {(double) oe.x+a.cutoff+margin, (double) oe.y+a.cutoff+margin, (double) oe.z+a.cutoff+margin};
+        int lo[3], n[3];
+        cellSpan(a, c, half, lo, n);
+        const int nyz = n[1]*n[2], total = n[0]*nyz;
+        const int dy = a.cellDim[1], dz = a.cellDim[2], dx = a.cellDim[0];
+        for (int base = 0; base < total; base += 128) {
+            int2 range[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base+u*32+lane;
+                range[u] = make_int2(0, 0);
+                if (idx < total) {
+                    const int ix = idx/nyz, s = idx-ix*nyz;
+                    const int iy = s/n[2], iz = s-iy*n[2];
+                    int cx = lo[0]+ix, cy = lo[1]+iy, cz = lo[2]+iz;
+                    cx -= cx >= dx ? dx : 0;
+                    cy -= cy >= dy ? dy : 0;
+                    cz -= cz >= dz ? dz : 0;
+                    range[u] = a.cellRange[(cx*dy+cy)*dz+cz];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int s0 = max(range[u].x, lastI+1), e0 = range[u].y;
+                if (e0 > s0)
+                    for (int b = s0>>5; b <= (e0-1)>>5; b++)
+                        atomicOr(&bm[b>>5], 1u<<(b&31));
+            }
         }
     }
     __syncwarp();
-    // pass 3: exclusion masks from the i side; partners before the octet are that octet's business
-    if (atomI >= 0) {
-        const int e0 = a.exclStart[atomI], e1 = a.exclStart[atomI+1];
-        for (int e = e0; e < e1; e++) {
-            const int sp = a.sortedPos[a.exclList[e]];
-            if ((sp>>3) == O) {
-                if ((sp&7) > lane)
-                    atomicOr(&out[sp&7].y, (int) (1u<<lane));
+
+    // ---- 2. + 3. walk the candidates, buffer the hit blocks, emit batches ------------------------
+    int nh = 0;
+    bool first = true, dead = false;
+    // octets too wide for the one-image-per-j-atom shortcut wrap every pair instead
+    const int wide = (a.pbcMode == PBC_SHIFT && (ext.x >= a.shiftLimit[0] || ext.y >= a.shiftLimit[1] || ext.z >= a.shiftLimit[2])) ? 1 : 0;
+    const int ki = O*8+(lane&7);
+    const int atomI = lane < 8 ? a.sortedAtom[ki] : -1;
+
+    auto flush = [&]() {
+        // positions of the batch's entries (the octet's own atoms occupy entries 0..7 of its first batch)
+        int running = first ? 8 : 0;
+        for (int k0 = 0; k0 < nh; k0 += 32) {
+            const int k = k0+lane;
+            const int cnt = k < nh ? __popc(hitWord[k]) : 0;
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(full, incl, o);
+                if (lane >= o) incl += t;
             }
-            else if (sp > O*8+7) {
-                const int c = candidateIndex(a, I, sp>>5), b = sp&31;
-                const unsigned word = row[c];
-                if ((word>>b)&1u)
-                    atomicOr(&out[base[c]+__popc(word&((1u<<b)-1))].y, (int) (1u<<lane));
+            if (k < nh)
+                hitBase[k] = running+incl-cnt;
+            running += __shfl_sync(full, incl, 31);
+        }
+        const int total = running, n = (total+31)>>5;
+        if (n == 0)
+            return;
+        const int numItemsHere = (n+a.itemChunks-1)/a.itemChunks;
+        int c0g = 0, item0 = 0;
+        if (lane == 0) {
+            c0g = atomicAdd(&a.counters[0], n);
+            item0 = atomicAdd(&a.counters[1], numItemsHere);
+            if (c0g+n > a.maxChunks || item0+numItemsHere > a.maxItems)
+                a.counters[2] = 1;                      // overflow: the host grows the buffers and repeats
+        }
+        c0g = __shfl_sync(full, c0g, 0);
+        item0 = __shfl_sync(full, item0, 0);
+        if (c0g+n > a.maxChunks || item0+numItemsHere > a.maxItems) {
+            dead = true;
+            return;
+        }
+        int2* out = a.jList+(size_t) c0g*32;
+        for (int k = lane; k < numItemsHere; k += 32)
+            a.workItems[item0+k] = make_int4(O, c0g+k*a.itemChunks, min(a.itemChunks, n-k*a.itemChunks), wide);
+        // own atoms first (lower triangle masked: every pair once), then the tail padding
+        if (first && lane < 8)
+            out[lane] = atomI >= 0 ? make_int2(ki, (int) ((0xffu<<lane)&0xffu)) : make_int2(-1, 0xff);
+        for (int k = total+lane; k < n*32; k += 32)
+            out[k] = make_int2(-1, 0xff);
+        __syncwarp();
+        for (int k = 0; k < nh; k++) {
+            const unsigned wb = hitWord[k];
+            if ((wb>>lane)&1u)
+                out[hitBase[k]+__popc(wb&((1u<<lane)-1))] = make_int2(hitJ[k]*32+lane, 0);
+        }
+        __syncwarp();
+        // exclusion masks from the i side; partners before the octet are that octet's business
+        if (atomI >= 0) {
+            const int e0 = a.exclStart[atomI], e1 = a.exclStart[atomI+1];
+            for (int e = e0; e < e1; e++) {
+                const int sp = a.sortedPos[a.exclList[e]];
+                if ((sp>>3) == O) {
+                    if (first && (sp&7) > lane)
+                        atomicOr(&out[sp&7].y, (int) (1u<<lane));
+                }
+                else if (sp > lastI) {
+                    // hit blocks are in ascending order: binary search for the partner's block
+                    const int J = sp>>5, b = sp&31;
+                    int l = 0, r = nh-1, found = -1;
+                    while (l <= r) {
+                        const int m = (l+r)>>1, v = hitJ[m];
+                        if (v == J) { found = m; break; }
+                        if (v < J) l = m+1; else r = m-1;
+                    }
+                    if (found >= 0) {
+                        const unsigned word = hitWord[found];
+                        if ((word>>b)&1u)
+                            atomicOr(&out[hitBase[found]+__popc(word&((1u<<b)-1))].y, (int) (1u<<lane));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        first = false;
+        nh = 0;
+    };
+
+    for (int w0 = wFirst; w0 < a.bitmapWords && !dead; w0 += 32) {
+        const unsigned myWord = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
+        unsigned nz = __ballot_sync(full, myWord != 0u);
+        while (nz && !dead) {
+            const int src = __ffs(nz)-1;
+            nz &= nz-1;
+            unsigned wd = __shfl_sync(full, myWord, src);
+            const int Jbase = (w0+src)*32;
+            while (wd && !dead) {
+                const int J = Jbase+__ffs(wd)-1;
+                wd &= wd-1;
+                const int j = J*32+lane;
+                bool acc = j < a.numAtoms && j > lastI;
+                if (a.useCutoff) {
+                    const float4 pj = a.posqLocal[j];
+                    const float px = pj.x+(float) (a.blockCenter[3*J]-cIx)-oc.x, py = pj.y+(float) (a.blockCenter[3*J+1]-cIy)-oc.y,
+                                pz = pj.z+(float) (a.blockCenter[3*J+2]-cIz)-oc.z;
+                    acc = acc && imageDist2(px, py, pz, oe, a) < cut2;
+                }
+                const unsigned word = __ballot_sync(full, acc);
+                if (word) {
+                    if (lane == 0) {
+                        hitJ[nh] = J;
+                        hitWord[nh] = word;
+                    }
+                    nh++;
+                    __syncwarp();
+                    if (nh == HIT_CAP)
+                        flush();
+                }
             }
         }
     }
+    if (!dead && (first || nh > 0))
+        flush();
 }
 
 void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs) {
     (void) numSMs;
-    const int groups = a.flagStride>>5;
-    const long long warps = (long long) a.numBlocks*groups;
-    k_tileFlags<<<(unsigned) ((warps+FLAG_WARPS-1)/FLAG_WARPS), FLAG_WARPS*32, 0, stream>>>(a);
-    const size_t smem = sizeof(int)*(size_t) COMPACT_WARPS*a.flagStride;
-    static bool attrSet = false;
-    if (!attrSet) {
-        cudaFuncSetAttribute(k_compactList, cudaFuncAttributeMaxDynamicSharedMemorySize, 4*COMPACT_WARPS*SNB_FLAGS_MAX_BLOCKS);
-        attrSet = true;
+    const int numOctets = a.octHi-a.octLo;
+    if (numOctets <= 0)
+        return;
+    const size_t smem = sizeof(unsigned)*(size_t) LIST_WARPS*(a.bitmapWords+3*HIT_CAP);
+    static size_t attrSet = 0;
+    if (smem > 48*1024 && smem > attrSet) {
+        cudaFuncSetAttribute(k_buildList, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        attrSet = smem;
     }
-    k_compactList<<<(4*a.numBlocks+COMPACT_WARPS-1)/COMPACT_WARPS, COMPACT_WARPS*32, smem, stream>>>(a);
+    k_buildList<<<(numOctets+LIST_WARPS-1)/LIST_WARPS, LIST_WARPS*32, smem, stream>>>(a);
 }

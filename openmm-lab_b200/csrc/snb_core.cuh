@@ -28,7 +28,6 @@
 #define SNB_FORCE_SCALE 4294967296.0f       /* 2^32, as the reference's fixed-point forces (realToFixedPoint.cu:1-2) */
 #define SNB_FORCE_SCALE_D 4294967296.0
 #define SNB_ITEM_CHUNKS 8                   /* most chunks of 32 j atoms per work item */
-#define SNB_FLAGS_MAX_BLOCKS 4096           /* parallel tile-flag build up to this many blocks (131k atoms) */
 
 enum { PBC_NONE = 0, PBC_SHIFT = 1, PBC_PAIR_ORTHO = 2, PBC_PAIR_TRICLINIC = 3 };
 enum { KIND_PLAIN = 0, KIND_RF = 1, KIND_EWALD = 2, KIND_LJPME = 3 };

@@ -116,6 +116,11 @@ __global__ void k_scatterAtoms(SortArgs a) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
     if (i < a.numAtoms)
         a.cellScratch[a.cellStart[a.atomCell[i]]+a.atomSlot[i]] = i;
+    // sorted range of every cell, addressed by its linear index (the tile-list build walks cells)
+    if (i < a.numCells) {
+        const int r = a.cellRank[i];
+        a.cellRange[i] = make_int2(a.cellStart[r], a.cellStart[r+1]);
+    }
     // padding slots of the last block
     int pad = a.numAtoms+i;
     if (i < a.paddedAtoms-a.numAtoms)
@@ -229,7 +234,7 @@ void launchSort(const SortArgs& a, cudaStream_t stream) {
         k_extent<<<1, 256, 0, stream>>>(a.posd, a.numAtoms, a.extent);
     k_assignCells<<<atomBlocks, threads, 0, stream>>>(a);
     k_scanCells<<<1, 1024, 0, stream>>>(a.cellCount, a.cellStart, a.numCells);
-    k_scatterAtoms<<<atomBlocks, threads, 0, stream>>>(a);
+    k_scatterAtoms<<<(max(a.paddedAtoms, a.numCells)+threads-1)/threads, threads, 0, stream>>>(a);
     k_rankInCell<<<atomBlocks, threads, 0, stream>>>(a);
     k_blockBounds<<<(a.numBlocks*32+threads-1)/threads, threads, 0, stream>>>(a);
 }
