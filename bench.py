@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Benchmark of the SlicedNonbondedForce hot path (BASELINE.json metric: sliced-PME force
-evaluations per second).
+evaluations per second, and ns/day).
 
     python bench.py --gpus N --steps K --warmup W [--workload dhfr|stmv|apoa1|fep|water] [--impl reference]
 
@@ -8,16 +8,22 @@ One "step" = one evaluation (forces + energy + derivatives, direct + reciprocal 
 workload, including the full neighbour/tile-list rebuild -- exactly what one `execute` of the
 reference kernel does (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:193-261).
 
-  value     evaluations/s with the positions already resident in HBM (snb_execute_device)
+  value     evaluations/s with the positions already resident in HBM (snb_execute_device),
+            host wall-clock around each synchronised step (>= the CUDA-event time, which is
+            reported next to it as device_ms_per_step), max over ranks
   e2e       the same through the reference-facing call with HOST buffers (snb_execute):
             positions host->device, forces + energies device->host inside the timed region
   roofline  direct-space tile kernel: algorithmic flop (67 per interacting pair)
-            / its CUDA-event duration, against the FP32 FMA peak (non-tensor path)
+            / its CUDA-event duration, against the FP32 FMA peak (non-tensor path); the
+            memory-bound PME kernels are listed against the measured HBM peak in "kernels"
+  N > 1     ONE evaluation is shared by all ranks: tile list and exceptions partitioned,
+            reciprocal space on rank 0, positions broadcast and fixed-point forces reduced by
+            NCCL ("scaling": "strong")
+  stmv      the same measurement on the STMV-size workload (BASELINE.json configs[4]), a few steps
   cpu_baseline / --impl reference: the reference's own Reference-platform sources (oracle/_ref,
             compiled unchanged) timed on the host cores -- the one place bench.py executes oracle/.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -78,7 +84,7 @@ def make_workload(name):
 def cpu_reference(w, seconds_budget=20.0, max_evals=3):
     """Time the reference's Reference-platform arithmetic (serial, as the reference is) on one host core."""
     import openmmlab_b200 as mm
-    from oracle import oracle_kernel
+    from oracle import oracle_kernel  # noqa: F401
     ctx = mm.Context(w.system, "Reference")
     ctx.setPositions(w.positions)
     for k, v in w.parameters.items():
@@ -98,7 +104,7 @@ def cpu_reference(w, seconds_budget=20.0, max_evals=3):
     med = times[len(times)//2]
     return {"value": 1.0/med, "unit": "evals/s", "cores": 1, "kind": "reference" if kernel.backend() == "reference" else "port",
             "sample": "%d full evaluation(s) of %s (neighbour list + direct + PME + exceptions), median; serial as the reference's Reference platform is"
-                      % (len(times), w.name), "seconds_per_eval": med}
+                      % (len(times), w.name), "seconds_per_eval": med, "host_cores_available": os.cpu_count()}
 
 
 def run_reference(args):
@@ -110,28 +116,148 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "sliced-PME force evaluations/s", "value": base["value"], "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*base["seconds_per_eval"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_of(w, args), "cpu_baseline": base,
+            "config": config_of(w), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ns_per_day_2fs": base["value"]*0.1728}
     print(json.dumps(line))
 
 
-def config_of(w, args):
+def config_of(w, world=1):
     f = w.force
     alpha, nx, ny, nz = f.getPMEParameters()
     return {"workload": w.name, "atoms": w.num_particles, "subsets": f.getNumSubsets(), "slices": f.getNumSlices(),
             "method": f.getNonbondedMethodName(), "cutoff_nm": f.getCutoffDistance(), "pme_grid": [nx, ny, nz],
             "scaling_parameters": f.getNumScalingParameters(), "derivatives": f.getNumScalingParameterDerivatives(),
             "evaluation": "forces+energy+derivatives, direct+reciprocal, tile list rebuilt every step",
-            "l2": "every step rewrites the force/grid/list buffers; inputs are re-read from HBM after a 256 MiB L2 flush write",
+            "parallelism": "1 GPU" if world == 1 else
+                           "%d ranks share each evaluation: tile list + exceptions partitioned, reciprocal space on rank 0, "
+                           "ncclBroadcast(positions) + ncclReduce(fixed-point forces) + ncclAllReduce(slice energies)" % world,
+            "l2": "256 MiB flush write between timed steps; every step rewrites the force/grid/list buffers",
+            "timing": "host wall-clock around each synchronised step, max over ranks (CUDA-event time reported as device_ms_per_step)",
             "precision": "mixed (FP32 pair arithmetic, FP64 / 2^32 fixed-point accumulation)"}
+
+
+class Runner:
+    """One workload on this rank's GPU (and, for world > 1, its share of every evaluation)."""
+
+    def __init__(self, name, local, rank, world, dist):
+        import torch
+        import openmmlab_b200 as mm
+        from openmmlab_b200 import _abi
+        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        w = self.w = make_workload(name)
+        n = self.n = w.num_particles
+        platform = mm.Platform.getPlatformByName("B200")
+        platform._properties["DeviceIndex"] = local
+        self.ctx = ctx = mm.Context(w.system, platform)
+        ctx.setPositions(w.positions)
+        for k, v in w.parameters.items():
+            ctx.setParameter(k, v)
+        self.kernel = kernel = ctx._kernels[0][1]
+        if world > 1:
+            ident = [kernel.ncclUniqueId() if rank == 0 else None]
+            dist.broadcast_object_list(ident, src=0)
+            kernel.commInit(ident[0], rank, world)
+        self.params = np.array([ctx.getParameter(name) for name in kernel.globalNames], dtype=np.float64)
+        self.box = np.ascontiguousarray(w.box, dtype=np.float64).reshape(9)
+        self.flags = _abi.EXECUTE_ALL
+        # device-resident inputs / outputs for `value`
+        self.posq = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+        self.posq[:, :3] = torch.from_numpy(w.positions.astype(np.float32)).cuda()
+        self.forces_fixed = torch.zeros((3, n), dtype=torch.int64, device="cuda")
+        # host buffers for `e2e`: pinned positions in, forces + energies out
+        self.pos_host = torch.from_numpy(w.positions.copy()).pin_memory()
+        ctx._positions = self.pos_host.numpy()
+
+    def step_device(self):
+        self.kernel.executeDevice(self.posq.data_ptr(), self.box, self.params, self.flags, self.forces_fixed.data_ptr())
+        return self.kernel.readEnergies(self.flags)
+
+    def step_host(self):
+        self.ctx._forces = np.zeros((self.n, 3))
+        self.ctx._energyParameterDerivatives = {}
+        return self.kernel.execute(self.ctx, True, True, True, True)
+
+    def timed(self, fn, steps, warmup, flush):
+        torch, dist = self.torch, self.dist
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        total, dev = 0.0, 0.0
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()     # the ranks enter every shared evaluation together
+            t0 = time.perf_counter()
+            fn()                      # returns after the stream synchronised (energies are read back)
+            total += time.perf_counter()-t0
+            dev += self.kernel.getLastDeviceMs()*1e-3
+        t = torch.tensor([total, dev], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item())
+
+    def phases(self, reps, flush):
+        """Per-phase CUDA-event times (this mode serialises the two streams), averaged."""
+        k = self.kernel
+        k.setTiming(True)
+        self.step_device()
+        acc = {name: 0.0 for name in k.getPhaseTimes()}
+        for _ in range(reps):
+            flush.zero_()
+            self.step_device()
+            for name, v in k.getPhaseTimes().items():
+                acc[name] += v/reps
+        k.setTiming(False)
+        return acc
+
+    def measure(self, steps, warmup, flush, peaks, e2e=True):
+        torch, dist = self.torch, self.dist
+        t_dev, t_evt = self.timed(self.step_device, steps, warmup, flush)
+        acc = self.phases(min(steps, 10), flush)
+        out = {"value": steps/t_dev, "ms_per_step": 1e3*t_dev/steps, "device_ms_per_step": 1e3*t_evt/steps}
+        if e2e:
+            t_e2e, _ = self.timed(self.step_host, steps, max(3, warmup), flush)
+            n = self.n
+            out["e2e"] = {"value": steps/t_e2e, "unit": "evals/s", "h2d_bytes_per_step": int(n*24), "d2h_bytes_per_step": int(n*24+8*72+32),
+                          "ms_per_step": 1e3*t_e2e/steps}
+        # roofline of the dominant kernel on the slowest rank: its own pairs / its own kernel time
+        pairs = self.kernel.countPairs()
+        mine = torch.tensor([acc["direct"], float(pairs)], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            gathered = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine)
+            rows = [g.cpu().numpy() for g in gathered]
+        else:
+            rows = [mine.cpu().numpy()]
+        slow = max(range(len(rows)), key=lambda r: rows[r][0])
+        kernel_ms, kernel_pairs = float(rows[slow][0]), int(rows[slow][1])
+        achieved = kernel_pairs*FLOP_PER_PAIR/(kernel_ms*1e-3)/1e12 if kernel_ms > 0 else 0.0
+        out["roofline"] = {"bound": "fp32", "kernel": "k_direct (direct-space tile kernel)", "achieved": achieved,
+                           "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved/FP32_PEAK_TFLOPS,
+                           "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz (FP32 FMA, non-tensor; MEASURED_PEAKS.json carries no FP32 entry)",
+                           "interacting_pairs": kernel_pairs, "interacting_pairs_all_ranks": int(sum(r[1] for r in rows)),
+                           "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": kernel_ms, "rank": slow, "traffic": None}
+        # the memory-bound kernels against the measured HBM peak (algorithmic bytes, SURVEY.md 8d)
+        f = self.w.force
+        _, nx, ny, nz = f.getPMEParameters()
+        S, G, n = f.getNumSubsets(), nx*ny*nz, self.n
+        hbm = peaks.get("hbm_gbs")
+        bytes_of = {"spread": n*28+S*G*4, "conv": 2*S*nx*ny*(nz//2+1)*8, "interp": n*40+S*G*4}
+        out["kernels"] = {k: {"ms": acc[k], "algorithmic_bytes": b, "gbs": b/(acc[k]*1e-3)/1e9 if acc[k] > 0 else None,
+                              "frac_of_hbm_peak": (b/(acc[k]*1e-3)/1e9/hbm) if (hbm and acc[k] > 0) else None}
+                          for k, b in bytes_of.items()}
+        out["phases_ms"] = acc
+        out["gpu_launches"] = int(self.kernel.getCounters()[2])*steps
+        return out
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    import openmmlab_b200 as mm
-    from openmmlab_b200 import _abi
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -139,101 +265,42 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w = make_workload(args.workload)
-    n = w.num_particles
-    platform = mm.Platform.getPlatformByName("B200")
-    platform._properties["DeviceIndex"] = local
-    ctx = mm.Context(w.system, platform)
-    ctx.setPositions(w.positions)
-    for k, v in w.parameters.items():
-        ctx.setParameter(k, v)
-    kernel = ctx._kernels[0][1]
-    params = np.array([ctx.getParameter(name) for name in kernel.globalNames], dtype=np.float64)
-    box = np.ascontiguousarray(w.box, dtype=np.float64).reshape(9)
-    flags = _abi.EXECUTE_ALL
-
-    # device-resident inputs / outputs for `value`
-    posq = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
-    posq[:, :3] = torch.from_numpy(w.positions.astype(np.float32)).cuda()
-    forces_fixed = torch.zeros((3, n), dtype=torch.int64, device="cuda")
+    peaks = load_peaks()
     flush = torch.empty(256*1024*1024//4, dtype=torch.float32, device="cuda")
-
-    def step_device():
-        kernel.executeDevice(posq.data_ptr(), box, params, flags, forces_fixed.data_ptr())
-        return kernel.readEnergies(flags)
-
-    # host buffers for `e2e`: pinned positions in, forces + energies out
-    pos_host = torch.from_numpy(w.positions.copy()).pin_memory()
-    ctx._positions = pos_host.numpy()
-
-    def step_host():
-        ctx._forces = np.zeros((n, 3))
-        ctx._energyParameterDerivatives = {}
-        return kernel.execute(ctx, True, True, True, True)
-
-    def timed(fn, steps, warmup, flush_l2):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        total = 0.0
-        for _ in range(steps):
-            if flush_l2:
-                flush.zero_()
-                torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            fn()                      # returns after the stream synchronised (energies are read back)
-            total += time.perf_counter()-t0
-        t = torch.tensor([total], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     sampler = ClockSampler(local)
     sampler.start()
-    t_dev = timed(step_device, args.steps, args.warmup, True)
-    # per-phase CUDA-event times (this mode serialises the two streams), averaged over a few more steps
-    kernel.setTiming(True)
-    step_device()
-    acc = {k: 0.0 for k in kernel.getPhaseTimes()}
-    reps = min(args.steps, 10)
-    for _ in range(reps):
-        flush.zero_()
-        step_device()
-        for k, v in kernel.getPhaseTimes().items():
-            acc[k] += v/reps
-    kernel.setTiming(False)
-    t_e2e = timed(step_host, args.steps, max(3, args.warmup), True)
+    main = Runner(args.workload, local, rank, world, dist)
+    res = main.measure(args.steps, args.warmup, flush, peaks)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-
-    if rank != 0:
-        return
-    evals = args.steps*world if args.scaling == "weak" else args.steps
-    value = evals/t_dev
-    e2e = evals/t_e2e
-    pairs = len(kernel.dumpPairs())
-    direct_s = acc["direct"]*1e-3
-    achieved = pairs*FLOP_PER_PAIR/direct_s/1e12 if direct_s > 0 else 0.0
-    peaks = load_peaks()
-    line = {"metric": "sliced-PME force evaluations/s", "value": value, "unit": "evals/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*t_dev/args.steps, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(w, args),
-            "ns_per_day_2fs": value*0.1728, "ns_per_day_4fs": value*0.3456,
-            "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": int(n*24), "d2h_bytes_per_step": int(n*24+8*72+32),
-                    "ms_per_step": 1e3*t_e2e/args.steps},
-            "gpu_launches": int(kernel.getCounters()[2])*args.steps,
-            "roofline": {"bound": "fp32", "kernel": "k_direct (direct-space tile kernel)", "achieved": achieved,
-                         "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved/FP32_PEAK_TFLOPS,
-                         "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz (FP32 FMA, non-tensor; MEASURED_PEAKS.json carries no FP32 entry)",
-                         "interacting_pairs": pairs, "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": acc["direct"], "traffic": None,
-                         "hbm_peak_gbs": peaks.get("hbm_gbs")},
-            "phases_ms": acc, "clocks": sampler.summary()}
-    if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_reference(w)
-    print(json.dumps(line))
+    extra = None
+    if not args.no_stmv and args.workload != "stmv":
+        w = main.w
+        del main
+        stmv = Runner("stmv", local, rank, world, dist)
+        extra = stmv.measure(min(args.steps, 10), 3, flush, peaks)
+        extra["config"] = config_of(stmv.w, world)
+        del stmv
+        main_w = w
+    else:
+        main_w = main.w
+    if rank == 0:
+        value = res["value"]
+        line = {"metric": "sliced-PME force evaluations/s", "value": value, "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "device_ms_per_step": res["device_ms_per_step"], "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_of(main_w, world), "ns_per_day_2fs": value*0.1728, "ns_per_day_4fs": value*0.3456,
+                "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "kernels": res["kernels"],
+                "phases_ms": res["phases_ms"], "clocks": sampler.summary()}
+        if extra is not None:
+            extra["ns_per_day_2fs"] = extra["value"]*0.1728
+            line["stmv"] = extra
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_reference(main_w)
+        print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -242,13 +309,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default=None)
+    ap.add_argument("--workload", default="dhfr")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--scaling", default="weak")
+    ap.add_argument("--no-stmv", action="store_true")
     args = ap.parse_args()
-    if args.workload is None:
-        args.workload = "dhfr"
     if args.impl == "reference":
         run_reference(args)
     else:

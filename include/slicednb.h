@@ -166,9 +166,23 @@ int snb_read_energies(snb_handle* h, int flags, double* energy, double* slice_en
 int snb_get_pme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz);
 int snb_get_ljpme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz);
 
-/* ---- multi-GPU (tile list partitioned across ranks; reciprocal on rank 0) -- */
-int snb_nccl_unique_id(void* id128);             /* fills a 128-byte ncclUniqueId       */
+/* ---- multi-GPU ----------------------------------------------------------
+ * One process (one handle) per GPU of one box.  The tile list and the exceptions are
+ * partitioned across the ranks, reciprocal space / self energy / dispersion correction stay
+ * on rank 0 -- the split of the reference's multi-device kernel
+ * (platforms/cuda/src/CudaParallelOpenMMLabKernels.cpp:19-53;
+ * CudaOpenMMLabKernels.cpp:379,405,466,680-683,762-765).  Every rank calls snb_execute* with
+ * the same box, global parameters and flags; rank 0's positions are broadcast (ncclBroadcast),
+ * the 2^32 fixed-point forces are summed onto rank 0 (ncclReduce, exact: the result is
+ * bit-identical to the single-GPU one) and the slice energies / derivatives are all-reduced,
+ * so forces are returned on rank 0 only and energies on every rank. */
+int snb_nccl_unique_id(void* id128);             /* rank 0: fills a 128-byte ncclUniqueId; ship it to the other ranks */
 int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size);
+/* rank 0's share of the tile list relative to 1.0 for every other rank (it also runs reciprocal
+ * space); negative = built-in cost model */
+int snb_set_rank0_share(snb_handle* h, double share);
+/* the partition rule itself (host only, no GPU): contiguous range [lo, hi) of n units for `rank` */
+int snb_partition(int64_t n, int world_size, int rank, double rank0_share, int64_t* lo, int64_t* hi);
 
 /* ---- introspection for tests and benches --------------------------------- */
 
@@ -176,6 +190,8 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size);
  * neighbour search of the LAST execute; *pairs is malloc'ed, caller frees
  * with snb_free. */
 int snb_dump_pairs(snb_handle* h, int32_t** pairs, int64_t* num_pairs);
+/* number of interacting pairs of the last execute on this handle (this rank's share), without the list */
+int snb_count_pairs(snb_handle* h, int64_t* num_pairs);
 void snb_free(void* p);
 
 /* per-phase device times (ms) of the last execute, when timing is enabled */
@@ -184,6 +200,9 @@ enum { SNB_PHASE_SORT = 0, SNB_PHASE_LIST, SNB_PHASE_DIRECT, SNB_PHASE_BONDED,
        SNB_PHASE_REDUCE, SNB_PHASE_TOTAL, SNB_NUM_PHASES };
 int snb_set_timing(snb_handle* h, int enabled);
 int snb_get_phase_times(snb_handle* h, float* ms /*[SNB_NUM_PHASES]*/);
+/* CUDA-event time (ms) of the last execute on the handle's stream: first memset .. last read-back copy
+ * (excludes the host->device copy of the positions, which precedes it) */
+int snb_get_last_device_ms(snb_handle* h, float* ms);
 /* counters of the last execute: [0]=interacting pairs, [1]=tile entries, [2]=kernel launches */
 int snb_get_counters(snb_handle* h, int64_t* out /*[8]*/);
 

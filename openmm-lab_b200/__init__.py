@@ -8,7 +8,7 @@ from . import _abi
 from ._abi import SnbError
 from .context import Context, Platform, State, System
 from .force import OpenMMException, SlicedNonbondedForce
-from .kernel import B200CalcSlicedNonbondedForceKernel, CalcSlicedNonbondedForceKernel, load_library
+from .kernel import B200CalcSlicedNonbondedForceKernel, CalcSlicedNonbondedForceKernel, load_library, partition
 from .platform import registerKernelFactories, registerPlatforms
 from . import systems
 

@@ -8,9 +8,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libslicednb_b200.so")
-SOURCES = ["api.cu", "sort.cu", "neighbor.cu", "direct.cu", "direct_plain.cu", "direct_rf.cu", "direct_ewald.cu",
+SOURCES = ["api.cu", "comm.cu", "sort.cu", "neighbor.cu", "direct.cu", "direct_plain.cu", "direct_rf.cu", "direct_ewald.cu",
            "direct_ljpme.cu", "bonded.cu", "pme.cu", "finish.cu"]
-HEADERS = ["snb_core.cuh", "kernels.cuh", "direct_impl.cuh", "../../include/slicednb.h", "../../include/snb_constants.h"]
+HEADERS = ["snb_core.cuh", "kernels.cuh", "comm.cuh", "direct_impl.cuh", "../../include/slicednb.h", "../../include/snb_constants.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true"]
 
@@ -45,7 +45,7 @@ def build(verbose=False, force=False):
         list(pool.map(run, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB]+objs+["-lcufft", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"])
+        run([nvcc, "-shared", "-o", LIB]+objs+["-lcufft", "-ldl", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"])
     return LIB
 
 

@@ -8,6 +8,7 @@
 // Scheduling differs from the reference's CUDA platform (CudaOpenMMLabKernels.cpp:888-1112) by
 // design: one stream-ordered sequence with no host synchronisation until the final read-back.
 #include "kernels.cuh"
+#include "comm.cuh"
 
 #include <cufft.h>
 
@@ -37,6 +38,8 @@ struct SnbException : public std::exception {
 
 #define CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     throw SnbException(SNB_ERR_CUDA, std::string(#call)+": "+cudaGetErrorString(e_)); } while (0)
+#define NCCL_CHECK(api, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) \
+    throw SnbException(SNB_ERR_CUDA, std::string(#call)+": "+(api)->GetErrorString(r_)); } while (0)
 #define CUFFT_CHECK(call) do { cufftResult r_ = (call); if (r_ != CUFFT_SUCCESS) \
     throw SnbException(SNB_ERR_CUDA, std::string(#call)+": cuFFT error "+std::to_string((int) r_)); } while (0)
 
@@ -153,6 +156,8 @@ struct PmeGrid {
 
 }  // namespace
 
+#define SNB_ENERGY_DOUBLES (32*2*SNB_MAX_SLICES+8)   /* 32 replicas of [slice][term] + flags ([0] = list overflow) */
+
 struct snb_handle {
     // ---- snapshot of the force (ReferenceOpenMMLabKernels.cpp:65-191) ----
     int N = 0, NP = 0, NB = 0, S = 1, L = 1, G = 0, method = 0, device = 0;
@@ -183,7 +188,8 @@ struct snb_handle {
     int pbcModeOverride = -1;
     // ---- device state ----
     cudaStream_t stream = nullptr, pmeStream = nullptr;
-    cudaEvent_t evSorted = nullptr, evPmeDone = nullptr;
+    cudaEvent_t evSorted = nullptr, evPmeDone = nullptr, evBegin = nullptr, evEnd = nullptr;
+    float lastDeviceMs = 0;
     int numSMs = 148;
     DevBuf<double> posd, paramsD, exception14, blockCenter, extent, energyBuf, forcesOutD;
     DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt;
@@ -199,6 +205,12 @@ struct snb_handle {
     PinnedBuf<int> hCounters;
     size_t maxChunks = 0, maxItems = 0;
     PmeGrid pme, dpme;
+    // ---- multi-GPU (comm.cuh): tile list and exceptions partitioned, reciprocal space on rank 0 ----
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    double rank0Share = -1;             // < 0: cost-model default
+    DevBuf<long long> reduceSend, reduceRecv;
+    DevBuf<double> energyRecv;
     // ---- results of the last execute ----
     std::vector<double> sliceEnergies;
     double lastEnergy = 0;
@@ -354,6 +366,8 @@ snb_handle* createHandle(const snb_desc& d) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&h.pmeStream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evSorted, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evPmeDone, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreate(&h.evBegin));
+        CUDA_CHECK(cudaEventCreate(&h.evEnd));
         h.N = d.num_particles;
         h.NB = (h.N+31)/32;
         h.NP = h.NB*32;
@@ -435,12 +449,12 @@ snb_handle* createHandle(const snb_desc& d) {
         h.blockCenter.alloc(3*(size_t) h.NB); h.blockExt.alloc(h.NB);
         h.octetCenter.alloc(4*(size_t) h.NB); h.octetExt.alloc(4*(size_t) h.NB);
         h.extent.alloc(6);
-        h.energyBuf.alloc(32*2*SNB_MAX_SLICES);    // 32 replicas of the slice-energy table (direct.cu), summed on the host
+        h.energyBuf.alloc(SNB_ENERGY_DOUBLES);    // 32 replicas of the slice-energy table (direct.cu), summed on the host, + flags
         h.counters.alloc(8);
         h.forceSorted.alloc(3*(size_t) h.NP); h.forceOrig.alloc(3*(size_t) h.NP);
         h.forcesOutD.alloc(3*(size_t) h.N);
         h.hPos.alloc(3*(size_t) h.N); h.hForces.alloc(3*(size_t) h.N);
-        h.hEnergy.alloc(32*2*SNB_MAX_SLICES);
+        h.hEnergy.alloc(SNB_ENERGY_DOUBLES);
         h.hCounters.alloc(8);
         h.sliceEnergies.assign(2*h.L, 0.0);
         if (h.method == SNB_PME || h.method == SNB_LJPME)
@@ -608,6 +622,19 @@ struct Timer {
     void mark(int k) { if (h.timing) CUDA_CHECK(cudaEventRecord(h.ev[k], h.stream)); }
 };
 
+// Rank 0's share of the tile list relative to 1.0 for every other rank.  Cost model: reciprocal space
+// (rank 0 only) costs about rho = 0.7 of the whole direct-space phase of the same system on one GPU, so
+// balancing  P + f0 D = (1 - f0) D / (W - 1)  gives f0 = (1 - (W-1) rho) / W of the octets to rank 0.
+double rank0Share(const snb_handle& h) {
+    if (h.world <= 1) return 1.0;
+    if (h.rank0Share >= 0) return h.rank0Share;
+    if (const char* env = getenv("SNB_RANK0_SHARE")) return std::max(0.0, atof(env));
+    if (h.method != SNB_PME && h.method != SNB_LJPME) return 1.0;
+    const double rho = h.method == SNB_LJPME ? 1.2 : 0.7;
+    const double f0 = std::max(0.0, (1.0-(h.world-1)*rho)/h.world);
+    return f0*(h.world-1)/(1.0-f0);
+}
+
 // One stream-ordered evaluation.  Returns false when a device-side capacity or mode check asks
 // for a repeat (buffers were grown / the PBC mode was changed).
 bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, void* forcesFixedOut) {
@@ -634,9 +661,10 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         (void) room;
     }
 
+    CUDA_CHECK(cudaEventRecord(h.evBegin, st));
     CUDA_CHECK(cudaMemsetAsync(h.forceSorted.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
     CUDA_CHECK(cudaMemsetAsync(h.forceOrig.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
-    CUDA_CHECK(cudaMemsetAsync(h.energyBuf.p, 0, sizeof(double)*32*2*SNB_MAX_SLICES, st));
+    CUDA_CHECK(cudaMemsetAsync(h.energyBuf.p, 0, sizeof(double)*SNB_ENERGY_DOUBLES, st));
     CUDA_CHECK(cudaMemsetAsync(h.counters.p, 0, sizeof(int)*8, st));
     tm.mark(0);
 
@@ -675,7 +703,9 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         la.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); la.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); la.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
         la.cellRange = h.cellRange.p; la.extent = h.extent.p;
         for (int k = 0; k < 3; k++) la.cellDim[k] = h.cellDim[k];
-        la.octLo = 0; la.octHi = 4*h.NB;
+        int64_t lo = 0, hi = 4*(int64_t) h.NB;
+        partitionRange(4*(int64_t) h.NB, h.world, h.rank, rank0Share(h), &lo, &hi);
+        la.octLo = (int) lo; la.octHi = (int) hi;
         la.bitmapWords = (h.NB+31)/32;
         launchBuildList(la, st, h.numSMs);
         tm.mark(2);
@@ -710,7 +740,10 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
 
         BondedArgs ba;
         memset(&ba, 0, sizeof(ba));
-        ba.numExceptions = h.X; ba.periodicExceptions = h.exceptionsPeriodic; ba.ewald = pmeFamily; ba.ljpme = h.method == SNB_LJPME;
+        int64_t xlo = 0, xhi = h.X;
+        partitionRange(h.X, h.world, h.rank, 1.0, &xlo, &xhi);
+        ba.firstException = (int) xlo;
+        ba.numExceptions = (int) (xhi-xlo); ba.periodicExceptions = h.exceptionsPeriodic; ba.ewald = pmeFamily; ba.ljpme = h.method == SNB_LJPME;
         ba.includeForces = 1;
         ba.alpha = h.alpha; ba.dalpha = h.dalpha; ba.boxd = bd;
         ba.posd = h.posd.p; ba.paramsD = h.paramsD.p; ba.subset = h.subsetD.p; ba.exceptionAtoms = h.exceptionAtomsD.p;
@@ -727,7 +760,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
     }
 
-    if (includeRecip && pmeFamily) {
+    if (includeRecip && pmeFamily && h.rank == 0) {
         // Reciprocal space runs on its own stream, concurrently with the tile list / direct-space /
         // bonded kernels (it only needs the sorted order).  With per-phase timing on, everything is
         // serialised on the main stream so that the phase times mean what they say.
@@ -776,34 +809,62 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         tm.mark(5); tm.mark(6); tm.mark(7); tm.mark(8);
     }
 
-    if (includeForces) {
+    const NcclApi* nccl = h.comm ? ncclApi(nullptr) : nullptr;
+    if (includeForces || nccl) {
         FinishArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.numAtoms = h.N; fa.paddedAtoms = h.NP;
         fa.sortedPos = includeDirect ? h.sortedPos.p : nullptr;
         fa.forceSorted = h.forceSorted.p; fa.forceOrig = h.forceOrig.p;
-        fa.forcesOut = hostPositions ? h.forcesOutD.p : nullptr;
-        fa.forcesFixedOut = (long long*) forcesFixedOut;
-        launchFinish(fa, st);
-        if (hostPositions)
+        fa.counters = h.counters.p; fa.flagsOut = h.energyBuf.p+32*2*SNB_MAX_SLICES;
+        if (nccl) {
+            // every rank contributes [3][N] fixed-point forces; the sum is exact, so the result is bit-identical
+            // to the single-GPU evaluation whatever the partition
+            h.reduceSend.alloc(3*(size_t) h.N);
+            h.reduceRecv.alloc(3*(size_t) h.N);
+            fa.reduceOut = h.reduceSend.p;
+            launchFinish(fa, st);
+            if (includeForces) {
+                NCCL_CHECK(nccl, nccl->Reduce(h.reduceSend.p, h.reduceRecv.p, 3*(size_t) h.N, ncclInt64, ncclSum, 0, h.comm, st));
+                if (h.rank == 0)
+                    launchEmitReduced(h.reduceRecv.p, h.N, hostPositions ? h.forcesOutD.p : nullptr, (long long*) forcesFixedOut, st);
+            }
+        }
+        else {
+            fa.forcesOut = hostPositions ? h.forcesOutD.p : nullptr;
+            fa.forcesFixedOut = (long long*) forcesFixedOut;
+            launchFinish(fa, st);
+        }
+        if (includeForces && hostPositions && h.rank == 0)
             CUDA_CHECK(cudaMemcpyAsync(h.hForces.p, h.forcesOutD.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyDeviceToHost, st));
     }
     tm.mark(9);
-    CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, h.energyBuf.p, sizeof(double)*32*2*SNB_MAX_SLICES, cudaMemcpyDeviceToHost, st));
+    const double* energySrc = h.energyBuf.p;
+    if (nccl) {
+        // slice energies of all ranks (and the list-overflow flags: every rank must take the same retry decision)
+        h.energyRecv.alloc(SNB_ENERGY_DOUBLES);
+        NCCL_CHECK(nccl, nccl->AllReduce(h.energyBuf.p, h.energyRecv.p, SNB_ENERGY_DOUBLES, ncclFloat64, ncclSum, h.comm, st));
+        energySrc = h.energyRecv.p;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, energySrc, sizeof(double)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaEventRecord(h.evEnd, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(cudaEventElapsedTime(&h.lastDeviceMs, h.evBegin, h.evEnd));
     CUDA_CHECK(cudaGetLastError());
     h.lastDirect = da;
     h.listValid = includeDirect;
     if (includeDirect) {
+        const bool anyOverflow = nccl ? h.hEnergy.p[32*2*SNB_MAX_SLICES] != 0.0 : h.hCounters.p[2] != 0;
         if (h.hCounters.p[2]) {
             // list buffers too small: grow to what the device asked for and repeat
             h.maxChunks = (size_t) (h.hCounters.p[0]*1.25)+64;
             h.maxItems = std::max<size_t>(h.maxItems, (size_t) (h.hCounters.p[1]*1.25)+64);
             h.jList.alloc(h.maxChunks*32);
             h.workItems.alloc(h.maxItems);
-            return false;
         }
+        if (anyOverflow)
+            return false;       // all ranks repeat together (the flag travelled with the all-reduce)
     }
     if (h.timing) {
         for (int k = 0; k < 9; k++)
@@ -814,9 +875,9 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
     h.countersOut[3] = h.hCounters.p[1];
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
-    if (includeDirect) launches += (periodic ? 5 : 6)+2+1+(h.X > 0 ? 1 : 0);
-    if (includeRecip && pmeFamily) launches += (h.deterministic ? 4 : 3)*(h.method == SNB_LJPME ? 2 : 1);
-    if (includeForces) launches += 1;
+    if (includeDirect) launches += (periodic ? 5 : 6)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
+    if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 4 : 3)*(h.method == SNB_LJPME ? 2 : 1);
+    if (includeForces || h.comm) launches += 1+(h.comm && h.rank == 0 ? 1 : 0);
     if (!hostPositions) launches += 1;
     h.countersOut[2] = launches;
     return true;
@@ -830,6 +891,8 @@ void finishEnergies(snb_handle& h, const double* box, int flags) {
             sum += h.hEnergy.p[(size_t) r*2*SNB_MAX_SLICES+k];
         h.sliceEnergies[k] = sum;
     }
+    // (multi-GPU: the all-reduce gave every rank the summed slice energies; the host-side terms below are
+    // added identically everywhere, so every rank returns the same energies.  Forces land on rank 0.)
     if (includeRecip && (h.method == SNB_PME || h.method == SNB_LJPME))
         for (int s = 0; s < h.S; s++) {
             h.sliceEnergies[2*(s*(s+3)/2)] += h.selfC[s];
@@ -870,6 +933,11 @@ void evaluate(snb_handle& h, const double* positions, const void* posqDev, const
     }
     else
         launchConvertPositions((const float4*) posqDev, h.posd.p, h.N, h.stream);
+    if (h.comm) {
+        // rank 0's positions are authoritative: every rank then builds the identical sorted order
+        const NcclApi* nccl = ncclApi(nullptr);
+        NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, h.stream));
+    }
     double unitBox[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const double* b = periodic ? box : unitBox;
     for (int attempt = 0; attempt < 4; attempt++)
@@ -906,11 +974,17 @@ void snb_destroy(snb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) {
+        if (const NcclApi* nccl = ncclApi(nullptr)) nccl->CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
     if (h->evCreated)
         for (auto& e : h->ev) cudaEventDestroy(e);
     cudaStream_t s = h->stream, s2 = h->pmeStream;
     if (h->evSorted) cudaEventDestroy(h->evSorted);
     if (h->evPmeDone) cudaEventDestroy(h->evPmeDone);
+    if (h->evBegin) cudaEventDestroy(h->evBegin);
+    if (h->evEnd) cudaEventDestroy(h->evEnd);
     delete h;
     if (s) cudaStreamDestroy(s);
     if (s2) cudaStreamDestroy(s2);
@@ -928,7 +1002,7 @@ int snb_execute(snb_handle* h, const double* positions, const double* box, const
     SNB_TRY
     if (!positions) throw SnbException(SNB_ERR_INVALID, "positions are null");
     evaluate(*h, positions, nullptr, box, globals, flags, nullptr);
-    if ((flags&SNB_INCLUDE_FORCES) && forces)
+    if ((flags&SNB_INCLUDE_FORCES) && forces && h->rank == 0)
         for (size_t k = 0; k < 3*(size_t) h->N; k++)
             forces[k] += h->hForces.p[k];
     return snb_read_energies(h, flags, energy, slice_energies, derivatives);
@@ -1009,6 +1083,27 @@ int snb_dump_pairs(snb_handle* h, int32_t** pairs, int64_t* num_pairs) {
     SNB_CATCH
 }
 
+int snb_count_pairs(snb_handle* h, int64_t* num_pairs) {
+    SNB_TRY
+    if (!h->listValid) throw SnbException(SNB_ERR_INVALID, "no tile list has been built (run an execute with direct space first)");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    DevBuf<unsigned long long> count;
+    DevBuf<int2> buf;
+    count.alloc(1);
+    buf.alloc(1);
+    unsigned long long found = 0;
+    CUDA_CHECK(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long), h->stream));
+    CUDA_CHECK(cudaMemsetAsync(h->counters.p+3, 0, sizeof(int), h->stream));
+    DirectArgs da = h->lastDirect;
+    da.pairDump = buf.p; da.pairDumpCount = count.p; da.pairDumpCapacity = 0;
+    launchDirect(da, h->stream, h->numSMs);
+    CUDA_CHECK(cudaMemcpyAsync(&found, count.p, sizeof(found), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    *num_pairs = (int64_t) found;
+    return SNB_OK;
+    SNB_CATCH
+}
+
 void snb_free(void* p) { free(p); }
 
 /* debugging aid: print the sorted order and the tile list of the last execute (small systems) */
@@ -1042,13 +1137,52 @@ int snb_get_phase_times(snb_handle* h, float* ms) {
     return SNB_OK;
 }
 
+int snb_get_last_device_ms(snb_handle* h, float* ms) { *ms = h->lastDeviceMs; return SNB_OK; }
+
 int snb_get_counters(snb_handle* h, int64_t* out) {
     for (int k = 0; k < 8; k++) out[k] = h->countersOut[k];
     return SNB_OK;
 }
 
-int snb_nccl_unique_id(void*) { g_lastError = "multi-GPU support is not built into this library yet"; return SNB_ERR_UNSUPPORTED; }
-int snb_comm_init(snb_handle*, const void*, int, int) { g_lastError = "multi-GPU support is not built into this library yet"; return SNB_ERR_UNSUPPORTED; }
+int snb_nccl_unique_id(void* id128) {
+    SNB_TRY
+    const char* why = nullptr;
+    const NcclApi* nccl = ncclApi(&why);
+    if (!nccl) throw SnbException(SNB_ERR_UNSUPPORTED, std::string("NCCL is not available: ")+why);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    NCCL_CHECK(nccl, nccl->GetUniqueId((ncclUniqueId*) id128));
+    return SNB_OK;
+    SNB_CATCH
+}
+
+int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size) {
+    SNB_TRY
+    if (!h || !id128 || world_size < 1 || rank < 0 || rank >= world_size)
+        throw SnbException(SNB_ERR_INVALID, "bad communicator arguments");
+    const char* why = nullptr;
+    const NcclApi* nccl = ncclApi(&why);
+    if (!nccl) throw SnbException(SNB_ERR_UNSUPPORTED, std::string("NCCL is not available: ")+why);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    if (h->comm) { nccl->CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCCL_CHECK(nccl, nccl->CommInitRank(&h->comm, world_size, id, rank));
+    h->rank = rank;
+    h->world = world_size;
+    return SNB_OK;
+    SNB_CATCH
+}
+
+int snb_set_rank0_share(snb_handle* h, double share) { h->rank0Share = share; return SNB_OK; }
+
+int snb_partition(int64_t n, int world_size, int rank, double rank0_share, int64_t* lo, int64_t* hi) {
+    if (!lo || !hi || world_size < 1 || rank < 0 || rank >= world_size || n < 0) {
+        g_lastError = "bad partition arguments";
+        return SNB_ERR_INVALID;
+    }
+    partitionRange(n, world_size, rank, rank0_share, lo, hi);
+    return SNB_OK;
+}
 
 const char* snb_last_error(void) { return g_lastError.c_str(); }
 const char* snb_version(void) { return "slicednb-b200 0.1 (sm_100a)"; }

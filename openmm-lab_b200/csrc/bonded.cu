@@ -16,8 +16,9 @@ __global__ void __launch_bounds__(128) k_bonded(BondedArgs a) {
     for (int k = threadIdx.x; k < 2*SNB_MAX_SLICES; k += blockDim.x)
         sE[k] = 0.0;
     __syncthreads();
-    int e = blockIdx.x*blockDim.x+threadIdx.x;
-    if (e < a.numExceptions) {
+    const int idx = blockIdx.x*blockDim.x+threadIdx.x;
+    if (idx < a.numExceptions) {
+        const int e = a.firstException+idx;
         const int2 atoms = a.exceptionAtoms[e];
         const int i = atoms.x, j = atoms.y;
         const int slice = sliceOf(a.subset[i], a.subset[j]);

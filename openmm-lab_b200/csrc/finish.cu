@@ -14,6 +14,23 @@ __global__ void k_finish(FinishArgs a) {
             a.forcesOut[3*i+c] = (double) f*(1.0/SNB_FORCE_SCALE_D);
         if (a.forcesFixedOut)
             a.forcesFixedOut[(size_t) c*a.numAtoms+i] += f;
+        if (a.reduceOut)
+            a.reduceOut[(size_t) c*a.numAtoms+i] = f;
+    }
+    if (i == 0 && a.flagsOut)
+        a.flagsOut[0] = (double) a.counters[2];
+}
+
+__global__ void k_emitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut) {
+    int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (i >= numAtoms)
+        return;
+    for (int c = 0; c < 3; c++) {
+        const long long f = reduced[(size_t) c*numAtoms+i];
+        if (forcesOut)
+            forcesOut[3*i+c] = (double) f*(1.0/SNB_FORCE_SCALE_D);
+        if (forcesFixedOut)
+            forcesFixedOut[(size_t) c*numAtoms+i] += f;
     }
 }
 
@@ -28,6 +45,11 @@ __global__ void k_convertPositions(const float4* posq, double* posd, int numAtom
 void launchFinish(const FinishArgs& a, cudaStream_t stream) {
     if (a.numAtoms > 0)
         k_finish<<<(a.numAtoms+255)/256, 256, 0, stream>>>(a);
+}
+
+void launchEmitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut, cudaStream_t stream) {
+    if (numAtoms > 0)
+        k_emitReduced<<<(numAtoms+255)/256, 256, 0, stream>>>(reduced, numAtoms, forcesOut, forcesFixedOut);
 }
 
 void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream) {

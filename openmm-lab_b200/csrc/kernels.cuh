@@ -79,6 +79,7 @@ void launchDirect(const DirectArgs& a, cudaStream_t stream, int numSMs);
 
 struct BondedArgs {
     int numExceptions, periodicExceptions, ewald, ljpme, includeForces;
+    int firstException;             // this rank's contiguous range is [firstException, firstException+numExceptions)
     double alpha, dalpha;
     BoxD boxd;
     const double* posd;
@@ -125,7 +126,12 @@ struct FinishArgs {
     const long long* forceOrig;
     double* forcesOut;              // [N][3] host-visible staging (device), or null
     long long* forcesFixedOut;      // [3][N] added to, or null
+    long long* reduceOut;           // [3][N] overwritten: this rank's contribution to the NCCL force reduction, or null
+    const int* counters;            // list-build counters; [2] = overflow flag
+    double* flagsOut;               // [1] overflow flag as a double, travels with the energy all-reduce (or null)
 };
+// after the force reduction (root only): reduced [3][N] fixed-point forces -> the caller's layout
+void launchEmitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut, cudaStream_t stream);
 void launchFinish(const FinishArgs& a, cudaStream_t stream);
 void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream);
 

@@ -172,12 +172,50 @@ class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
         self._check(self._lib.snb_get_phase_times(self._handle, ms))
         return dict(zip(_abi.PHASES, list(ms)))
 
+    def countPairs(self):
+        n = C.c_int64()
+        fn = self._lib.snb_count_pairs
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        self._check(fn(self._handle, C.byref(n)))
+        return n.value
+
+    def getLastDeviceMs(self):
+        ms = C.c_float()
+        self._check(self._lib.snb_get_last_device_ms(self._handle, C.byref(ms)))
+        return ms.value
+
     def getCounters(self):
         out = (C.c_int64*8)()
         self._check(self._lib.snb_get_counters(self._handle, out))
         return list(out)
 
+    # ---- multi-GPU: one process / one kernel per GPU (include/slicednb.h, "multi-GPU") ----
+    def ncclUniqueId(self):
+        """128-byte NCCL id made on rank 0; ship it to the other ranks (e.g. torch.distributed broadcast)."""
+        buf = C.create_string_buffer(128)
+        fn = self._lib.snb_nccl_unique_id
+        fn.argtypes = [C.c_char_p]
+        self._check(fn(buf))
+        return buf.raw
+
     def commInit(self, unique_id, rank, world_size):
         fn = self._lib.snb_comm_init
         fn.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         self._check(fn(self._handle, unique_id, rank, world_size))
+        self.rank, self.worldSize = rank, world_size
+
+    def setRank0Share(self, share):
+        fn = self._lib.snb_set_rank0_share
+        fn.argtypes = [C.c_void_p, C.c_double]
+        self._check(fn(self._handle, float(share)))
+
+
+def partition(n, world_size, rank, rank0_share=1.0):
+    """The library's partition rule (host only, no GPU needed): range [lo, hi) of n units for `rank`."""
+    lib = load_library()
+    lo, hi = C.c_int64(), C.c_int64()
+    fn = lib.snb_partition
+    fn.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    if fn(n, world_size, rank, float(rank0_share), C.byref(lo), C.byref(hi)) != _abi.OK:
+        raise SnbError(_abi.ERR_INVALID, "bad partition arguments")
+    return lo.value, hi.value
