@@ -156,6 +156,15 @@ struct PmeGrid {
 
 }  // namespace
 
+// Everything that shapes the launches of one evaluation.  Two evaluations with equal keys enqueue the
+// same nodes with the same arguments (the box and the lambdas travel through StepParams in device
+// memory), so the second one onwards replays a captured CUDA graph.
+struct GraphKey {
+    int flags, hostPositions, pbcMode, cellDim[3], numCells, itemChunks, needEnergy;
+    size_t maxChunks, maxItems;
+    const void *posqDev, *forcesFixedOut, *jList, *workItems;
+};
+
 #define SNB_ENERGY_DOUBLES (32*2*SNB_MAX_SLICES+8)   /* 32 replicas of [slice][term] + flags ([0] = list overflow) */
 
 struct snb_handle {
@@ -187,7 +196,13 @@ struct snb_handle {
     int cellDim[3] = {0, 0, 0}, numCells = 0;
     int pbcModeOverride = -1;
     // ---- device state ----
-    cudaStream_t stream = nullptr, pmeStream = nullptr;
+    cudaStream_t stream = nullptr, pmeStream = nullptr, bondedStream = nullptr;
+    cudaEvent_t evInputs = nullptr, evBondedDone = nullptr;
+    DevBuf<StepParams> stepD;
+    PinnedBuf<StepParams> stepH;
+    bool useGraph = true, graphKeyValid = false;
+    GraphKey graphKey;
+    cudaGraphExec_t graphExec = nullptr;
     cudaEvent_t evSorted = nullptr, evPmeDone = nullptr, evBegin = nullptr, evEnd = nullptr;
     float lastDeviceMs = 0;
     int numSMs = 148;
@@ -197,8 +212,6 @@ struct snb_handle {
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
                 exclStart, exclList, is14D, counters, cellScratch;
     DevBuf<int2> exceptionAtomsD, jList, cellRange;
-    DevBuf<ExactParams> exactD;
-    PinnedBuf<ExactParams> exactH;
     DevBuf<int4> workItems;
     DevBuf<long long> forceSorted, forceOrig;
     PinnedBuf<double> hPos, hForces, hEnergy;
@@ -364,6 +377,13 @@ snb_handle* createHandle(const snb_desc& d) {
         h.numSMs = prop.multiProcessorCount;
         CUDA_CHECK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h.pmeStream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h.bondedStream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h.evInputs, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h.evBondedDone, cudaEventDisableTiming));
+        h.useGraph = getenv("SNB_NO_GRAPH") == nullptr;
+        h.stepD.alloc(1);
+        h.stepH.alloc(1);
+        memset(h.stepH.p, 0, sizeof(StepParams));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evSorted, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evPmeDone, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreate(&h.evBegin));
@@ -635,38 +655,104 @@ double rank0Share(const snb_handle& h) {
     return f0*(h.world-1)/(1.0-f0);
 }
 
-// One stream-ordered evaluation.  Returns false when a device-side capacity or mode check asks
-// for a repeat (buffers were grown / the PBC mode was changed).
-bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, void* forcesFixedOut) {
+struct StepInputs {
+    const void* posqDev;        // device float4 positions, or null when the positions come from hPos
+    void* forcesFixedOut;
+    int flags;
+    bool hostPositions;
+    int pbcMode;
+};
+
+// Host-side preparation of one evaluation: cells, capacities, StepParams mirror, reciprocal-space table.
+int prepareStep(snb_handle& h, const double* box, bool periodic) {
+    BoxD bd;
+    BoxF bf;
+    makeBox(box, bd, bf);
+    setupCells(h, box, periodic);
+    ensureListCapacity(h, box, periodic);
+    int pbcMode = PBC_NONE;
+    if (periodic) {
+        const bool triclinic = bd.bx != 0 || bd.cx != 0 || bd.cy != 0;
+        pbcMode = triclinic ? PBC_PAIR_TRICLINIC : PBC_SHIFT;   // PBC_SHIFT: per work item, one image per j atom or per-pair wrapping
+    }
+    StepParams& sp = *h.stepH.p;
+    sp.exact.boxd = bd;
+    sp.exact.cutoff2d = h.cutoff*h.cutoff;
+    sp.exact.periodic = periodic;
+    sp.box = bf;
+    sp.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); sp.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); sp.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
+    for (int s = 0; s < SNB_MAX_SLICES; s++) {
+        sp.lambdaC[s] = s < h.L ? h.lambdaC[s] : 0.0;
+        sp.lambdaV[s] = s < h.L ? h.lambdaV[s] : 0.0;
+    }
+    return pbcMode;
+}
+
+PmeArgs pmeArgs(snb_handle& h, int term, bool sorted) {
+    PmeGrid& g = term == 0 ? h.pme : h.dpme;
+    PmeArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.numAtoms = h.N; pa.numSubsets = h.S; pa.term = term;
+    pa.nx = g.n[0]; pa.ny = g.n[1]; pa.nz = g.n[2];
+    pa.alpha = g.alpha; pa.sp = h.stepD.p; pa.posd = h.posd.p; pa.doublePrecision = h.doublePrecision;
+    pa.sortedAtom = sorted ? h.sortedAtom.p : nullptr;
+    pa.params4 = h.params4.p; pa.paramsD = h.paramsD.p; pa.grid = g.real.p; pa.cgrid = g.cplx.p; pa.eterm = g.eterm.p;
+    pa.gridFixed = h.deterministic ? g.fixed.p : nullptr;
+    for (int k = 0; k < 3; k++) pa.moduli[k] = g.moduli[k].p;
+    pa.forceOrig = h.forceOrig.p; pa.paddedAtoms = h.NP; pa.energyBuf = h.energyBuf.p;
+    return pa;
+}
+
+// Enqueue one whole evaluation on the handle's streams (no host synchronisation, no allocation: the
+// sequence is capturable as a CUDA graph).
+void enqueueStep(snb_handle& h, const StepInputs& in) {
+    const int flags = in.flags;
     const bool includeForces = flags&SNB_INCLUDE_FORCES, includeDirect = flags&SNB_INCLUDE_DIRECT,
                includeRecip = flags&SNB_INCLUDE_RECIPROCAL;
     const bool periodic = h.method >= SNB_CUTOFF_PERIODIC;
     const bool pmeFamily = h.method == SNB_PME || h.method == SNB_LJPME;
-    bool needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
+    const bool needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     cudaStream_t st = h.stream;
+    const NcclApi* nccl = h.comm ? ncclApi(nullptr) : nullptr;
     Timer tm(h);
-    BoxD bd;
-    BoxF bf;
-    double unitBox[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    makeBox(periodic ? box : unitBox, bd, bf);
-    setupCells(h, box, periodic);
-    ensureListCapacity(h, box, periodic);
 
-    int pbcMode = PBC_NONE;
-    if (periodic) {
-        bool triclinic = bd.bx != 0 || bd.cx != 0 || bd.cy != 0;
-        double room = std::min(bd.ax, std::min(bd.by, bd.cz))*0.5-h.cutoff;
-        if (triclinic) pbcMode = PBC_PAIR_TRICLINIC;
-        else pbcMode = PBC_SHIFT;      // per work item: one image per j atom, or per-pair wrapping for wide i blocks
-        (void) room;
-    }
-
-    CUDA_CHECK(cudaEventRecord(h.evBegin, st));
+    // ---- inputs ----
+    if (in.hostPositions)
+        CUDA_CHECK(cudaMemcpyAsync(h.posd.p, h.hPos.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
+    else
+        launchConvertPositions((const float4*) in.posqDev, h.posd.p, h.N, st);
+    if (nccl)   // rank 0's positions are authoritative: every rank then builds the identical sorted order
+        NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, st));
+    CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemsetAsync(h.forceSorted.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
     CUDA_CHECK(cudaMemsetAsync(h.forceOrig.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
     CUDA_CHECK(cudaMemsetAsync(h.energyBuf.p, 0, sizeof(double)*SNB_ENERGY_DOUBLES, st));
     CUDA_CHECK(cudaMemsetAsync(h.counters.p, 0, sizeof(int)*8, st));
     tm.mark(0);
+
+    // ---- exceptions / exclusion corrections: need the inputs only, so they run beside the sort ----
+    bool bondedForked = false;
+    auto bonded = [&](cudaStream_t bs) {
+        BondedArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        int64_t xlo = 0, xhi = h.X;
+        partitionRange(h.X, h.world, h.rank, 1.0, &xlo, &xhi);
+        ba.firstException = (int) xlo;
+        ba.numExceptions = (int) (xhi-xlo); ba.periodicExceptions = h.exceptionsPeriodic; ba.ewald = pmeFamily; ba.ljpme = h.method == SNB_LJPME;
+        ba.includeForces = 1;
+        ba.alpha = h.alpha; ba.dalpha = h.dalpha; ba.sp = h.stepD.p;
+        ba.posd = h.posd.p; ba.paramsD = h.paramsD.p; ba.subset = h.subsetD.p; ba.exceptionAtoms = h.exceptionAtomsD.p;
+        ba.exception14 = h.exception14.p; ba.exceptionIs14 = h.is14D.p;
+        ba.forceOrig = h.forceOrig.p; ba.paddedAtoms = h.NP; ba.energyBuf = h.energyBuf.p;
+        launchBonded(ba, bs);
+    };
+    if (includeDirect && h.X > 0 && !h.timing) {
+        CUDA_CHECK(cudaEventRecord(h.evInputs, st));
+        CUDA_CHECK(cudaStreamWaitEvent(h.bondedStream, h.evInputs, 0));
+        bonded(h.bondedStream);
+        CUDA_CHECK(cudaEventRecord(h.evBondedDone, h.bondedStream));
+        bondedForked = true;
+    }
 
     DirectArgs da;
     memset(&da, 0, sizeof(da));
@@ -675,117 +761,24 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         memset(&sa, 0, sizeof(sa));
         sa.numAtoms = h.N; sa.paddedAtoms = h.NP; sa.numBlocks = h.NB; sa.numCells = h.numCells; sa.periodic = periodic;
         for (int k = 0; k < 3; k++) sa.cellDim[k] = h.cellDim[k];
-        sa.checkShift = 0;
-        sa.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); sa.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); sa.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
         sa.counters = h.counters.p;
         sa.sqrtK = (float) sqrt(SNB_ONE_4PI_EPS0);
-        sa.boxd = bd;
+        sa.sp = h.stepD.p;
         sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.paramsD = h.paramsD.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
         sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
         sa.cellRange = h.cellRange.p; sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
         launchSort(sa, st);
-        tm.mark(1);
-        if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
-
-        ListArgs la;
-        memset(&la, 0, sizeof(la));
-        la.numAtoms = h.N; la.numBlocks = h.NB; la.pbcMode = pbcMode; la.periodic = periodic;
-        la.useCutoff = h.method != SNB_NO_CUTOFF;
-        la.cutoff = (float) (h.cutoff*(1.0+1e-5)+1e-5);
-        la.box = bf; la.boxd = bd;
-        la.sortedAtom = h.sortedAtom.p; la.sortedPos = h.sortedPos.p; la.posqLocal = h.posqLocal.p;
-        la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p; la.octetCenter = h.octetCenter.p; la.octetExt = h.octetExt.p;
-        la.exclStart = h.exclStart.p; la.exclList = h.exclList.p;
-        la.jList = h.jList.p; la.workItems = h.workItems.p; la.counters = h.counters.p;
-        la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems; la.itemChunks = h.itemChunks;
-        la.shiftLimit[0] = (float) (0.5*bd.ax-h.cutoff); la.shiftLimit[1] = (float) (0.5*bd.by-h.cutoff); la.shiftLimit[2] = (float) (0.5*bd.cz-h.cutoff);
-        la.cellRange = h.cellRange.p; la.extent = h.extent.p;
-        for (int k = 0; k < 3; k++) la.cellDim[k] = h.cellDim[k];
-        int64_t lo = 0, hi = 4*(int64_t) h.NB;
-        partitionRange(4*(int64_t) h.NB, h.world, h.rank, rank0Share(h), &lo, &hi);
-        la.octLo = (int) lo; la.octHi = (int) hi;
-        la.bitmapWords = (h.NB+31)/32;
-        launchBuildList(la, st, h.numSMs);
-        tm.mark(2);
-
-        DirectParams& p = da.p;
-        p.numAtoms = h.N; p.numBlocks = h.NB; p.pbcMode = pbcMode; p.periodic = periodic;
-        p.cutoff2d = h.cutoff*h.cutoff;
-        p.bandTol = (float) (4e-5*h.cutoff*h.cutoff);
-        p.alphad = h.alpha;
-        p.krfd = pow(h.cutoff, -3.0)*(h.rfDielectric-1.0)/(2.0*h.rfDielectric+1.0);
-        p.crfd = (1.0/h.cutoff)*(3.0*h.rfDielectric)/(2.0*h.rfDielectric+1.0);
-        p.switchDistd = h.switchDist;
-        p.invSwitchWidthd = h.useSwitch ? 1.0/(h.cutoff-h.switchDist) : 0.0;
-        double dc2 = h.dalpha*h.cutoff*h.dalpha*h.cutoff;
-        p.dalphad = h.dalpha;
-        p.dispShiftExpd = 1.0-exp(-dc2)*(1.0+dc2+0.5*dc2*dc2);
-        p.invCut6d = pow(h.cutoff, -6.0);
-        for (int s = 0; s < h.L; s++) { p.lambdaCd[s] = h.lambdaC[s]; p.lambdaVd[s] = h.lambdaV[s]; }
-        p.boxd = bd;
-        h.exactD.alloc(1); h.exactH.alloc(1);
-        h.exactH.p->boxd = bd; h.exactH.p->cutoff2d = p.cutoff2d; h.exactH.p->periodic = periodic;
-        CUDA_CHECK(cudaMemcpyAsync(h.exactD.p, h.exactH.p, sizeof(ExactParams), cudaMemcpyHostToDevice, st));
-        da.exact = h.exactD.p;
-        da.kind = h.method == SNB_NO_CUTOFF ? KIND_PLAIN : h.method <= SNB_CUTOFF_PERIODIC ? KIND_RF : h.method == SNB_LJPME ? KIND_LJPME : KIND_EWALD;
-        da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
-        da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
-        da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
-        da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.workItems = h.workItems.p;
-        da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
-        launchDirect(da, st, h.numSMs);
-        tm.mark(3);
-
-        BondedArgs ba;
-        memset(&ba, 0, sizeof(ba));
-        int64_t xlo = 0, xhi = h.X;
-        partitionRange(h.X, h.world, h.rank, 1.0, &xlo, &xhi);
-        ba.firstException = (int) xlo;
-        ba.numExceptions = (int) (xhi-xlo); ba.periodicExceptions = h.exceptionsPeriodic; ba.ewald = pmeFamily; ba.ljpme = h.method == SNB_LJPME;
-        ba.includeForces = 1;
-        ba.alpha = h.alpha; ba.dalpha = h.dalpha; ba.boxd = bd;
-        ba.posd = h.posd.p; ba.paramsD = h.paramsD.p; ba.subset = h.subsetD.p; ba.exceptionAtoms = h.exceptionAtomsD.p;
-        ba.exception14 = h.exception14.p; ba.exceptionIs14 = h.is14D.p;
-        for (int s = 0; s < h.L; s++) { ba.lambdaC[s] = h.lambdaC[s]; ba.lambdaV[s] = h.lambdaV[s]; }
-        ba.forceOrig = h.forceOrig.p; ba.paddedAtoms = h.NP; ba.energyBuf = h.energyBuf.p;
-        launchBonded(ba, st);
-        tm.mark(4);
     }
-    else {
-        // the sorted order is still needed by the reciprocal kernels and the final gather:
-        // identity order is enough there
-        tm.mark(1); tm.mark(2); tm.mark(3); tm.mark(4);
-        if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
-    }
+    tm.mark(1);
+    if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
 
-    if (includeRecip && pmeFamily && h.rank == 0) {
-        // Reciprocal space runs on its own stream, concurrently with the tile list / direct-space /
-        // bonded kernels (it only needs the sorted order).  With per-phase timing on, everything is
-        // serialised on the main stream so that the phase times mean what they say.
-        cudaStream_t ps = h.timing ? st : h.pmeStream;
-        if (!h.timing)
-            CUDA_CHECK(cudaStreamWaitEvent(ps, h.evSorted, 0));
+    // ---- reciprocal space (rank 0): its own stream, beside the tile list / direct-space kernels ----
+    auto reciprocal = [&](cudaStream_t ps) {
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
             PmeGrid& g = term == 0 ? h.pme : h.dpme;
-            PmeArgs pa;
-            memset(&pa, 0, sizeof(pa));
-            pa.numAtoms = h.N; pa.numSubsets = h.S; pa.term = term;
-            pa.nx = g.n[0]; pa.ny = g.n[1]; pa.nz = g.n[2];
-            pa.alpha = g.alpha; pa.boxd = bd; pa.posd = h.posd.p; pa.doublePrecision = h.doublePrecision;
-            pa.sortedAtom = includeDirect ? h.sortedAtom.p : nullptr;
-            pa.params4 = h.params4.p; pa.paramsD = h.paramsD.p; pa.grid = g.real.p; pa.cgrid = g.cplx.p; pa.eterm = g.eterm.p;
-            pa.gridFixed = h.deterministic ? g.fixed.p : nullptr;
-            for (int k = 0; k < 3; k++) pa.moduli[k] = g.moduli[k].p;
-            for (int s = 0; s < h.L; s++) pa.lambda[s] = term == 0 ? h.lambdaC[s] : h.lambdaV[s];
-            pa.forceOrig = h.forceOrig.p; pa.paddedAtoms = h.NP; pa.energyBuf = h.energyBuf.p;
-            double key[6] = {bd.ax, bd.bx, bd.by, bd.cx, bd.cy, bd.cz};
-            if (!g.etermValid || memcmp(key, g.etermBox, sizeof(key)) != 0) {
-                launchPmeEterm(pa, ps);
-                memcpy(g.etermBox, key, sizeof(key));
-                g.etermValid = true;
-            }
+            PmeArgs pa = pmeArgs(h, term, includeDirect);
             CUFFT_CHECK(cufftSetStream(g.fwd, ps));
             CUFFT_CHECK(cufftSetStream(g.inv, ps));
             launchPmeSpread(pa, ps);
@@ -800,16 +793,75 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
             launchPmeInterpolate(pa, ps);
             if (term == 0) tm.mark(8);
         }
-        if (!h.timing) {
-            CUDA_CHECK(cudaEventRecord(h.evPmeDone, ps));
-            CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
-        }
-    }
-    else {
-        tm.mark(5); tm.mark(6); tm.mark(7); tm.mark(8);
+    };
+    const bool doRecip = includeRecip && pmeFamily && h.rank == 0;
+    if (doRecip && !h.timing) {
+        CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.evSorted, 0));
+        reciprocal(h.pmeStream);
+        CUDA_CHECK(cudaEventRecord(h.evPmeDone, h.pmeStream));
     }
 
-    const NcclApi* nccl = h.comm ? ncclApi(nullptr) : nullptr;
+    if (includeDirect) {
+        ListArgs la;
+        memset(&la, 0, sizeof(la));
+        la.numAtoms = h.N; la.numBlocks = h.NB; la.pbcMode = in.pbcMode; la.periodic = periodic;
+        la.useCutoff = h.method != SNB_NO_CUTOFF;
+        la.cutoff = (float) (h.cutoff*(1.0+1e-5)+1e-5);
+        la.sp = h.stepD.p;
+        la.sortedAtom = h.sortedAtom.p; la.sortedPos = h.sortedPos.p; la.posqLocal = h.posqLocal.p;
+        la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p; la.octetCenter = h.octetCenter.p; la.octetExt = h.octetExt.p;
+        la.exclStart = h.exclStart.p; la.exclList = h.exclList.p;
+        la.jList = h.jList.p; la.workItems = h.workItems.p; la.counters = h.counters.p;
+        la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems; la.itemChunks = h.itemChunks;
+        la.cellRange = h.cellRange.p; la.extent = h.extent.p;
+        for (int k = 0; k < 3; k++) la.cellDim[k] = h.cellDim[k];
+        int64_t lo = 0, hi = 4*(int64_t) h.NB;
+        partitionRange(4*(int64_t) h.NB, h.world, h.rank, rank0Share(h), &lo, &hi);
+        la.octLo = (int) lo; la.octHi = (int) hi;
+        la.bitmapWords = (h.NB+31)/32;
+        launchBuildList(la, st, h.numSMs);
+        tm.mark(2);
+
+        DirectParams& p = da.p;
+        p.numAtoms = h.N; p.numBlocks = h.NB; p.pbcMode = in.pbcMode; p.periodic = periodic;
+        p.cutoff2d = h.cutoff*h.cutoff;
+        p.bandTol = (float) (4e-5*h.cutoff*h.cutoff);
+        p.alphad = h.alpha;
+        p.krfd = pow(h.cutoff, -3.0)*(h.rfDielectric-1.0)/(2.0*h.rfDielectric+1.0);
+        p.crfd = (1.0/h.cutoff)*(3.0*h.rfDielectric)/(2.0*h.rfDielectric+1.0);
+        p.switchDistd = h.switchDist;
+        p.invSwitchWidthd = h.useSwitch ? 1.0/(h.cutoff-h.switchDist) : 0.0;
+        double dc2 = h.dalpha*h.cutoff*h.dalpha*h.cutoff;
+        p.dalphad = h.dalpha;
+        p.dispShiftExpd = 1.0-exp(-dc2)*(1.0+dc2+0.5*dc2*dc2);
+        p.invCut6d = pow(h.cutoff, -6.0);
+        da.sp = h.stepD.p;
+        da.kind = h.method == SNB_NO_CUTOFF ? KIND_PLAIN : h.method <= SNB_CUTOFF_PERIODIC ? KIND_RF : h.method == SNB_LJPME ? KIND_LJPME : KIND_EWALD;
+        da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
+        da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
+        da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
+        da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.workItems = h.workItems.p;
+        da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
+        launchDirect(da, st, h.numSMs);
+        tm.mark(3);
+        if (h.X > 0 && !bondedForked)
+            bonded(st);
+        tm.mark(4);
+    }
+    else {
+        tm.mark(2); tm.mark(3); tm.mark(4);
+    }
+    if (doRecip && h.timing)
+        reciprocal(st);
+    else if (h.timing) {
+        tm.mark(5); tm.mark(6); tm.mark(7); tm.mark(8);
+    }
+    if (bondedForked)
+        CUDA_CHECK(cudaStreamWaitEvent(st, h.evBondedDone, 0));
+    if (doRecip && !h.timing)
+        CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
+
+    // ---- outputs ----
     if (includeForces || nccl) {
         FinishArgs fa;
         memset(&fa, 0, sizeof(fa));
@@ -820,42 +872,114 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
         if (nccl) {
             // every rank contributes [3][N] fixed-point forces; the sum is exact, so the result is bit-identical
             // to the single-GPU evaluation whatever the partition
-            h.reduceSend.alloc(3*(size_t) h.N);
-            h.reduceRecv.alloc(3*(size_t) h.N);
             fa.reduceOut = h.reduceSend.p;
             launchFinish(fa, st);
             if (includeForces) {
                 NCCL_CHECK(nccl, nccl->Reduce(h.reduceSend.p, h.reduceRecv.p, 3*(size_t) h.N, ncclInt64, ncclSum, 0, h.comm, st));
                 if (h.rank == 0)
-                    launchEmitReduced(h.reduceRecv.p, h.N, hostPositions ? h.forcesOutD.p : nullptr, (long long*) forcesFixedOut, st);
+                    launchEmitReduced(h.reduceRecv.p, h.N, in.hostPositions ? h.forcesOutD.p : nullptr, (long long*) in.forcesFixedOut, st);
             }
         }
         else {
-            fa.forcesOut = hostPositions ? h.forcesOutD.p : nullptr;
-            fa.forcesFixedOut = (long long*) forcesFixedOut;
+            fa.forcesOut = in.hostPositions ? h.forcesOutD.p : nullptr;
+            fa.forcesFixedOut = (long long*) in.forcesFixedOut;
             launchFinish(fa, st);
         }
-        if (includeForces && hostPositions && h.rank == 0)
+        if (includeForces && in.hostPositions && h.rank == 0)
             CUDA_CHECK(cudaMemcpyAsync(h.hForces.p, h.forcesOutD.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyDeviceToHost, st));
     }
     tm.mark(9);
     const double* energySrc = h.energyBuf.p;
     if (nccl) {
         // slice energies of all ranks (and the list-overflow flags: every rank must take the same retry decision)
-        h.energyRecv.alloc(SNB_ENERGY_DOUBLES);
         NCCL_CHECK(nccl, nccl->AllReduce(h.energyBuf.p, h.energyRecv.p, SNB_ENERGY_DOUBLES, ncclFloat64, ncclSum, h.comm, st));
         energySrc = h.energyRecv.p;
     }
     CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, energySrc, sizeof(double)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
+    h.lastDirect = da;
+}
+
+void dropGraph(snb_handle& h) {
+    if (h.graphExec) cudaGraphExecDestroy(h.graphExec);
+    h.graphExec = nullptr;
+    h.graphKeyValid = false;
+}
+
+// One evaluation.  Returns false when a device-side capacity check asks for a repeat (buffers were grown).
+bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, void* forcesFixedOut) {
+    const bool includeDirect = flags&SNB_INCLUDE_DIRECT, includeRecip = flags&SNB_INCLUDE_RECIPROCAL, includeForces = flags&SNB_INCLUDE_FORCES;
+    const bool periodic = h.method >= SNB_CUTOFF_PERIODIC;
+    const bool pmeFamily = h.method == SNB_PME || h.method == SNB_LJPME;
+    cudaStream_t st = h.stream;
+    StepInputs in;
+    in.posqDev = posqDev; in.forcesFixedOut = forcesFixedOut; in.flags = flags; in.hostPositions = posqDev == nullptr;
+    in.pbcMode = prepareStep(h, box, periodic);
+
+    // reciprocal-space kernel table: rebuilt only when the box changes (outside the graph, same stream)
+    if (includeRecip && pmeFamily && h.rank == 0)
+        for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
+            PmeGrid& g = term == 0 ? h.pme : h.dpme;
+            const BoxD& bd = h.stepH.p->exact.boxd;
+            double key[6] = {bd.ax, bd.bx, bd.by, bd.cx, bd.cy, bd.cz};
+            if (!g.etermValid || memcmp(key, g.etermBox, sizeof(key)) != 0) {
+                // the kernel reads the box from StepParams: refresh the device copy first
+                CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
+                launchPmeEterm(pmeArgs(h, term, false), st);
+                memcpy(g.etermBox, key, sizeof(key));
+                g.etermValid = true;
+            }
+        }
+
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.flags = flags; key.hostPositions = in.hostPositions; key.pbcMode = in.pbcMode;
+    for (int k = 0; k < 3; k++) key.cellDim[k] = h.cellDim[k];
+    key.numCells = h.numCells; key.itemChunks = h.itemChunks;
+    key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
+    key.maxChunks = h.maxChunks; key.maxItems = h.maxItems;
+    key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p; key.workItems = h.workItems.p;
+    const bool graphable = h.useGraph && !h.timing && !h.comm;
+    const bool sameKey = h.graphKeyValid && memcmp(&key, &h.graphKey, sizeof(key)) == 0;
+    if (!graphable || !sameKey)
+        dropGraph(h);
+
+    CUDA_CHECK(cudaEventRecord(h.evBegin, st));
+    if (graphable && sameKey) {
+        if (!h.graphExec) {
+            // second evaluation with this shape: capture it (the first ran eagerly and did every lazy set-up)
+            cudaGraph_t graph = nullptr;
+            CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueueStep(h, in);
+            }
+            catch (...) {
+                cudaStreamEndCapture(st, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+            cudaError_t err = cudaGraphInstantiate(&h.graphExec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (err != cudaSuccess) {
+                h.graphExec = nullptr;
+                throw SnbException(SNB_ERR_CUDA, std::string("cudaGraphInstantiate: ")+cudaGetErrorString(err));
+            }
+        }
+        CUDA_CHECK(cudaGraphLaunch(h.graphExec, st));
+    }
+    else {
+        enqueueStep(h, in);
+        h.graphKey = key;
+        h.graphKeyValid = graphable;
+    }
     CUDA_CHECK(cudaEventRecord(h.evEnd, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    CUDA_CHECK(cudaEventElapsedTime(&h.lastDeviceMs, h.evBegin, h.evEnd));
     CUDA_CHECK(cudaGetLastError());
-    h.lastDirect = da;
+    CUDA_CHECK(cudaEventElapsedTime(&h.lastDeviceMs, h.evBegin, h.evEnd));
     h.listValid = includeDirect;
     if (includeDirect) {
-        const bool anyOverflow = nccl ? h.hEnergy.p[32*2*SNB_MAX_SLICES] != 0.0 : h.hCounters.p[2] != 0;
+        const bool anyOverflow = h.comm ? h.hEnergy.p[32*2*SNB_MAX_SLICES] != 0.0 : h.hCounters.p[2] != 0;
         if (h.hCounters.p[2]) {
             // list buffers too small: grow to what the device asked for and repeat
             h.maxChunks = (size_t) (h.hCounters.p[0]*1.25)+64;
@@ -873,12 +997,13 @@ bool runOnce(snb_handle& h, const double* box, int flags, bool hostPositions, vo
     }
     h.countersOut[1] = h.hCounters.p[0];
     h.countersOut[3] = h.hCounters.p[1];
+    h.countersOut[4] = h.graphExec ? 1 : 0;
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
     if (includeDirect) launches += (periodic ? 5 : 6)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
     if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 4 : 3)*(h.method == SNB_LJPME ? 2 : 1);
     if (includeForces || h.comm) launches += 1+(h.comm && h.rank == 0 ? 1 : 0);
-    if (!hostPositions) launches += 1;
+    if (posqDev) launches += 1;
     h.countersOut[2] = launches;
     return true;
 }
@@ -927,21 +1052,12 @@ void evaluate(snb_handle& h, const double* positions, const void* posqDev, const
         h.lastEnergy = 0;
         return;
     }
-    if (positions) {
+    if (positions)
         memcpy(h.hPos.p, positions, sizeof(double)*3*(size_t) h.N);
-        CUDA_CHECK(cudaMemcpyAsync(h.posd.p, h.hPos.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, h.stream));
-    }
-    else
-        launchConvertPositions((const float4*) posqDev, h.posd.p, h.N, h.stream);
-    if (h.comm) {
-        // rank 0's positions are authoritative: every rank then builds the identical sorted order
-        const NcclApi* nccl = ncclApi(nullptr);
-        NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, h.stream));
-    }
     double unitBox[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const double* b = periodic ? box : unitBox;
     for (int attempt = 0; attempt < 4; attempt++)
-        if (runOnce(h, b, flags, positions != nullptr, forcesFixedOut)) {
+        if (runOnce(h, b, flags, positions ? nullptr : posqDev, forcesFixedOut)) {
             finishEnergies(h, b, flags);
             h.lastFlags = flags;
             return;
@@ -980,6 +1096,10 @@ void snb_destroy(snb_handle* h) {
     }
     if (h->evCreated)
         for (auto& e : h->ev) cudaEventDestroy(e);
+    if (h->graphExec) cudaGraphExecDestroy(h->graphExec);
+    if (h->evInputs) cudaEventDestroy(h->evInputs);
+    if (h->evBondedDone) cudaEventDestroy(h->evBondedDone);
+    if (h->bondedStream) cudaStreamDestroy(h->bondedStream);
     cudaStream_t s = h->stream, s2 = h->pmeStream;
     if (h->evSorted) cudaEventDestroy(h->evSorted);
     if (h->evPmeDone) cudaEventDestroy(h->evPmeDone);
@@ -1169,6 +1289,9 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size) {
     NCCL_CHECK(nccl, nccl->CommInitRank(&h->comm, world_size, id, rank));
     h->rank = rank;
     h->world = world_size;
+    h->reduceSend.alloc(3*(size_t) h->N);
+    h->reduceRecv.alloc(3*(size_t) h->N);
+    h->energyRecv.alloc(SNB_ENERGY_DOUBLES);
     return SNB_OK;
     SNB_CATCH
 }

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) k_bonded(BondedArgs a) {
         const int slice = sliceOf(a.subset[i], a.subset[j]);
         // delta = pos[i] - pos[j]  (getDeltaR(pos[j], pos[i]))
         double d[3];
-        deltaExact(a.posd+3*(size_t) j, a.posd+3*(size_t) i, a.boxd, a.periodicExceptions != 0, d);
+        deltaExact(a.posd+3*(size_t) j, a.posd+3*(size_t) i, a.sp->exact.boxd, a.periodicExceptions != 0, d);
         const double r2 = d[0]*d[0]+d[1]*d[1]+d[2]*d[2];
         const double r = sqrt(r2), invR = 1.0/r;
         double fi = 0.0;            // force on i is  +fi * d, on j  -fi * d
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128) k_bonded(BondedArgs a) {
             const double erfAR = erf(alphaR);
             if (erfAR > 1e-6) {
                 const double dEdR = qq*invR*invR*invR*(erfAR-2*alphaR*exp(-alphaR*alphaR)/sqrt(M_PI));
-                fi -= a.lambdaC[slice]*dEdR;
+                fi -= a.sp->lambdaC[slice]*dEdR;
                 eC -= qq*invR*erfAR;
             }
             else
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128) k_bonded(BondedArgs a) {
                 const double ex = exp(-dar2);
                 eV += c6i*c6j*invR6*(1.0-ex*(1.0+dar2+0.5*dar4));
                 const double dEdR = -6.0*c6i*c6j*invR6*invR2*(1.0-ex*(1.0+dar2+0.5*dar4+dar6/6.0));
-                fi -= a.lambdaV[slice]*dEdR;
+                fi -= a.sp->lambdaV[slice]*dEdR;
             }
         }
         if (a.exceptionIs14[e]) {
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(128) k_bonded(BondedArgs a) {
             double sig2 = invR*sig;
             sig2 *= sig2;
             const double sig6 = sig2*sig2*sig2;
-            double dEdR = a.lambdaV[slice]*eps4*(12.0*sig6-6.0)*sig6;
-            dEdR += a.lambdaC[slice]*K*qq*invR;
+            double dEdR = a.sp->lambdaV[slice]*eps4*(12.0*sig6-6.0)*sig6;
+            dEdR += a.sp->lambdaC[slice]*K*qq*invR;
             dEdR *= invR*invR;
             fi += dEdR;
             eV += eps4*(sig6-1.0)*sig6;

@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     const R krf = (R) p.krfd, crf = (R) p.crfd;
     const R switchDist = (R) p.switchDistd, invSwitchWidth = (R) p.invSwitchWidthd;
     const R dalpha2 = (R) (p.dalphad*p.dalphad), dispShiftExp = (R) p.dispShiftExpd, invCut6 = (R) p.invCut6d;
-    const R bAx = (R) p.boxd.ax, bBy = (R) p.boxd.by, bCz = (R) p.boxd.cz;
-    const R iAx = (R) (1.0/p.boxd.ax), iBy = (R) (1.0/p.boxd.by), iCz = (R) (1.0/p.boxd.cz);
+    const BoxD boxd = a.sp->exact.boxd;
+    const R bAx = (R) boxd.ax, bBy = (R) boxd.by, bCz = (R) boxd.cz;
+    const R iAx = (R) (1.0/boxd.ax), iBy = (R) (1.0/boxd.by), iCz = (R) (1.0/boxd.cz);
     const unsigned kBit = 1u<<k;
     const int srcLane = (copy<<3)|((k+1)&7);       // the j accumulators move one lane down inside the copy
     // slice energies of this thread over all its work items, keyed by (own subset, j subset); reduced
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             int sl = sliceOf(max(subI, 0), s);
-            t.lamC[s] = s < numSub ? (R) p.lambdaCd[sl] : (R) 0;
-            t.lamV[s] = s < numSub ? (R) p.lambdaVd[sl] : (R) 0;
+            t.lamC[s] = s < numSub ? (R) a.sp->lambdaC[sl] : (R) 0;
+            t.lamV[s] = s < numSub ? (R) a.sp->lambdaV[sl] : (R) 0;
             t.EC[s] = t.EV[s] = 0.0;
         }
         double Fx = 0, Fy = 0, Fz = 0;
@@ -182,9 +183,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 }
                 else if (PBC == PBC_PAIR_TRICLINIC) {
                     R m = Real<R>::rint(dz*iCz);
-                    dx -= m*(R) p.boxd.cx; dy -= m*(R) p.boxd.cy; dz -= m*bCz;
+                    dx -= m*(R) boxd.cx; dy -= m*(R) boxd.cy; dz -= m*bCz;
                     m = Real<R>::rint(dy*iBy);
-                    dx -= m*(R) p.boxd.bx; dy -= m*bBy;
+                    dx -= m*(R) boxd.bx; dy -= m*bBy;
                     m = Real<R>::rint(dx*iAx);
                     dx -= m*bAx;
                 }
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 if (KIND != KIND_PLAIN) {
                     in = in && r2 < myCutHi;
                     if (in && r2 > cutoffLo)
-                        in = exactInRange(a.posd, origI, a.sortedAtom[sJ[slot]], a.exact);
+                        in = exactInRange(a.posd, origI, a.sortedAtom[sJ[slot]], &a.sp->exact);
                 }
                 else
                     in = in && iValid;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                     }
                     else {
                         const int sl = sliceOf(subI, (int) prm.z);
-                        lc = (R) p.lambdaCd[sl]; lv = (R) p.lambdaVd[sl];
+                        lc = (R) a.sp->lambdaC[sl]; lv = (R) a.sp->lambdaV[sl];
                     }
                     const R f = lv*fv+lc*fc;
                     fix += f*dx; fiy += f*dy; fiz += f*dz;

@@ -7,11 +7,9 @@
 struct SortArgs {
     int numAtoms, paddedAtoms, numBlocks, numCells, periodic;
     int cellDim[3];
-    float shiftLimit[3];    // halfBox - cutoff per axis: PBC_SHIFT needs every block's half extent below it
-    int checkShift;
-    int* counters;          // [4] set when a block violates shiftLimit
+    int* counters;
     float sqrtK;            // sqrt(ONE_4PI_EPS0): direct-space charges carry it
-    BoxD boxd;
+    const StepParams* sp;   // box
     const double* posd;
     const float4* params4;
     const double* paramsD;
@@ -30,8 +28,7 @@ void launchSort(const SortArgs& a, cudaStream_t stream);
 struct ListArgs {
     int numAtoms, numBlocks, pbcMode, periodic, useCutoff;
     float cutoff;           // padded by a safety margin for the single-precision tests
-    BoxF box;
-    BoxD boxd;
+    const StepParams* sp;   // box, shiftLimit
     const int* sortedAtom;
     const int* sortedPos;
     const float4* posqLocal;
@@ -49,12 +46,12 @@ struct ListArgs {
     const double* extent;   // non-periodic methods: bounding box of all atoms (min[3], max[3])
     int octLo, octHi;       // this rank's octets
     int bitmapWords;        // ceil(numBlocks/32)
-    float shiftLimit[3];    // halfBox - cutoff: i blocks wider than this cannot use one image per j atom
 };
 void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 
 struct DirectArgs {
     DirectParams p;
+    const StepParams* sp;          // box, lambdas, exact-predicate parameters
     int kind, useSwitch, numSubsets, needEnergy, doublePrecision;
     const int* sortedAtom;
     const float4* posqLocal;
@@ -64,7 +61,6 @@ struct DirectArgs {
     const double* blockCenter;
     const float4* octetCenter;
     const double* posd;
-    const ExactParams* exact;
     const int2* jList;
     const int4* workItems;
     int* counters;
@@ -81,14 +77,13 @@ struct BondedArgs {
     int numExceptions, periodicExceptions, ewald, ljpme, includeForces;
     int firstException;             // this rank's contiguous range is [firstException, firstException+numExceptions)
     double alpha, dalpha;
-    BoxD boxd;
+    const StepParams* sp;           // box, lambdas
     const double* posd;
     const double* paramsD;          // [N][3] sigma/2, 2 sqrt(eps), q
     const int* subset;
     const int2* exceptionAtoms;     // [X]
     const double* exception14;      // [X][3] sigma, 4 eps, chargeProd (after offsets)
     const int* exceptionIs14;       // [X]
-    double lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
     long long* forceOrig;           // [3][paddedAtoms]
     int paddedAtoms;
     double* energyBuf;
@@ -99,7 +94,7 @@ struct PmeArgs {
     int numAtoms, numSubsets, term;  // term 0 Coulomb, 1 dispersion
     int nx, ny, nz, doublePrecision;
     double alpha;
-    BoxD boxd;
+    const StepParams* sp;           // box, lambdas (term 0: lambdaC, term 1: lambdaV)
     const double* posd;
     const int* sortedAtom;
     const float4* params4;          // q in .x ; sigma/2, 2 sqrt(eps) in .y .z (dispersion "charge" = 8 s^3 e) ; subset bits in .w
@@ -109,7 +104,6 @@ struct PmeArgs {
     void* cgrid;                    // [S][nx][ny][nz/2+1] complex
     void* eterm;                    // [nx][ny][nz/2+1]
     const double* moduli[3];
-    double lambda[SNB_MAX_SLICES];  // of this term
     long long* forceOrig;
     int paddedAtoms;
     double* energyBuf;

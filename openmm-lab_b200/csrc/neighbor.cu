@@ -35,29 +35,29 @@ __device__ __forceinline__ float boxDist2(float dx, float dy, float dz, float3 h
 }
 
 // Smallest box distance over the periodic images the pair kernel can pick.
-__device__ __forceinline__ float imageDist2(float dx, float dy, float dz, float3 h, const ListArgs& a) {
-    if (a.pbcMode == PBC_NONE)
+__device__ __forceinline__ float imageDist2(float dx, float dy, float dz, float3 h, const int pbcMode, const BoxF& box) {
+    if (pbcMode == PBC_NONE)
         return boxDist2(dx, dy, dz, h);
-    if (a.pbcMode != PBC_PAIR_TRICLINIC) {
-        dx = wrapOrtho(dx, a.box.ax, a.box.invAx);
-        dy = wrapOrtho(dy, a.box.by, a.box.invBy);
-        dz = wrapOrtho(dz, a.box.cz, a.box.invCz);
+    if (pbcMode != PBC_PAIR_TRICLINIC) {
+        dx = wrapOrtho(dx, box.ax, box.invAx);
+        dy = wrapOrtho(dy, box.by, box.invBy);
+        dz = wrapOrtho(dz, box.cz, box.invCz);
         return boxDist2(dx, dy, dz, h);
     }
     // triclinic: reduce like the pair kernel does, then try the 27 neighbouring images
-    float s = rintf(dz*a.box.invCz);
-    dx -= s*a.box.cx; dy -= s*a.box.cy; dz -= s*a.box.cz;
-    s = rintf(dy*a.box.invBy);
-    dx -= s*a.box.bx; dy -= s*a.box.by;
-    s = rintf(dx*a.box.invAx);
-    dx -= s*a.box.ax;
+    float s = rintf(dz*box.invCz);
+    dx -= s*box.cx; dy -= s*box.cy; dz -= s*box.cz;
+    s = rintf(dy*box.invBy);
+    dx -= s*box.bx; dy -= s*box.by;
+    s = rintf(dx*box.invAx);
+    dx -= s*box.ax;
     float best = 3.0e38f;
     for (int k = -1; k <= 1; k++)
         for (int j = -1; j <= 1; j++)
             for (int i = -1; i <= 1; i++) {
-                float x = dx+i*a.box.ax+j*a.box.bx+k*a.box.cx;
-                float y = dy+j*a.box.by+k*a.box.cy;
-                float z = dz+k*a.box.cz;
+                float x = dx+i*box.ax+j*box.bx+k*box.cx;
+                float y = dy+j*box.by+k*box.cy;
+                float z = dz+k*box.cz;
                 best = fminf(best, boxDist2(x, y, z, h));
             }
     return best;
@@ -66,7 +66,7 @@ __device__ __forceinline__ float imageDist2(float dx, float dy, float dz, float3
 // Range of cells [lo, lo+n) (periodic: modulo dim) along every axis that the box centre +- half can touch.
 __device__ __forceinline__ void cellSpan(const ListArgs& a, const double c[3], const double half[3], int lo[3], int n[3]) {
     if (a.periodic) {
-        const double (*r)[3] = a.boxd.recip;
+        const double (*r)[3] = a.sp->exact.boxd.recip;
         double f[3], h[3];
         f[0] = c[0]*r[0][0]+c[1]*r[1][0]+c[2]*r[2][0];
         f[1] = c[1]*r[1][1]+c[2]*r[2][1];
@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     const float3 oe = make_float3(ext.x, ext.y, ext.z);
     const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
     const float cut2 = a.cutoff*a.cutoff;
+    const BoxF box = a.sp->box;
 
     // ---- 1. candidate blocks ------------------------------------------------------------------
     for (int k = wFirst+lane; k < a.bitmapWords; k += 32)
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     int nh = 0;
     bool first = true, dead = false;
     // octets too wide for the one-image-per-j-atom shortcut wrap every pair instead
-    const int wide = (a.pbcMode == PBC_SHIFT && (ext.x >= a.shiftLimit[0] || ext.y >= a.shiftLimit[1] || ext.z >= a.shiftLimit[2])) ? 1 : 0;
+    const int wide = (a.pbcMode == PBC_SHIFT && (ext.x >= a.sp->shiftLimit[0] || ext.y >= a.sp->shiftLimit[1] || ext.z >= a.sp->shiftLimit[2])) ? 1 : 0;
     const int ki = O*8+(lane&7);
     const int atomI = lane < 8 ? a.sortedAtom[ki] : -1;
 
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
                     const float4 pj = a.posqLocal[j];
                     const float px = pj.x+(float) (a.blockCenter[3*J]-cIx)-oc.x, py = pj.y+(float) (a.blockCenter[3*J+1]-cIy)-oc.y,
                                 pz = pj.z+(float) (a.blockCenter[3*J+2]-cIz)-oc.z;
-                    acc = acc && imageDist2(px, py, pz, oe, a) < cut2;
+                    acc = acc && imageDist2(px, py, pz, oe, a.pbcMode, box) < cut2;
                 }
                 const unsigned word = __ballot_sync(full, acc);
                 if (word) {

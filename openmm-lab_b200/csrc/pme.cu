@@ -49,9 +49,9 @@ template <typename R> __device__ __forceinline__ void bspline5(R w, R* th, R* dt
 template <typename R> __device__ __forceinline__ void gridCoord(const PmeArgs& a, int atom, int idx[3], R frac[3]) {
     const double x = a.posd[3*atom], y = a.posd[3*atom+1], z = a.posd[3*atom+2];
     double t[3];
-    t[0] = x*a.boxd.recip[0][0]+y*a.boxd.recip[1][0]+z*a.boxd.recip[2][0];
-    t[1] = y*a.boxd.recip[1][1]+z*a.boxd.recip[2][1];
-    t[2] = z*a.boxd.recip[2][2];
+    t[0] = x*a.sp->exact.boxd.recip[0][0]+y*a.sp->exact.boxd.recip[1][0]+z*a.sp->exact.boxd.recip[2][0];
+    t[1] = y*a.sp->exact.boxd.recip[1][1]+z*a.sp->exact.boxd.recip[2][1];
+    t[2] = z*a.sp->exact.boxd.recip[2][2];
     const int n[3] = {a.nx, a.ny, a.nz};
 #pragma unroll
     for (int d = 0; d < 3; d++) {
@@ -125,15 +125,15 @@ template <typename R>
 __global__ void k_pmeEterm(PmeArgs a, R* eterm) {
     const int nzc = a.nz/2+1;
     const size_t total = (size_t) a.nx*a.ny*nzc;
-    const double volume = a.boxd.ax*a.boxd.by*a.boxd.cz;
+    const double volume = a.sp->exact.boxd.ax*a.sp->exact.boxd.by*a.sp->exact.boxd.cz;
     for (size_t idx = blockIdx.x*(size_t) blockDim.x+threadIdx.x; idx < total; idx += (size_t) gridDim.x*blockDim.x) {
         const int kz = idx%nzc, ky = (idx/nzc)%a.ny, kx = idx/((size_t) nzc*a.ny);
         const double mx = kx < (a.nx+1)/2 ? kx : kx-a.nx;
         const double my = ky < (a.ny+1)/2 ? ky : ky-a.ny;
         const double mz = kz < (a.nz+1)/2 ? kz : kz-a.nz;
-        const double mhx = mx*a.boxd.recip[0][0];
-        const double mhy = mx*a.boxd.recip[1][0]+my*a.boxd.recip[1][1];
-        const double mhz = mx*a.boxd.recip[2][0]+my*a.boxd.recip[2][1]+mz*a.boxd.recip[2][2];
+        const double mhx = mx*a.sp->exact.boxd.recip[0][0];
+        const double mhy = mx*a.sp->exact.boxd.recip[1][0]+my*a.sp->exact.boxd.recip[1][1];
+        const double mhz = mx*a.sp->exact.boxd.recip[2][0]+my*a.sp->exact.boxd.recip[2][1]+mz*a.sp->exact.boxd.recip[2][2];
         const double m2 = mhx*mhx+mhy*mhy+mhz*mhz;
         const double bx = a.moduli[0][kx], by = a.moduli[1][ky], bz = a.moduli[2][kz];
         double e;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_pmeInterpolate(PmeArgs a) {
         const R* row = (const R*) a.grid+((size_t) x*a.ny+y)*a.nz;
         R s0 = 0, s1 = 0;           // sum_z theta_z * phi, sum_z dtheta_z * phi
         for (int sj = 0; sj < a.numSubsets; sj++) {
-            const R lam = (R) a.lambda[sliceOf(si, sj)];
+            const R lam = (R) (a.term == 0 ? a.sp->lambdaC : a.sp->lambdaV)[sliceOf(si, sj)];
 #pragma unroll
             for (int iz = 0; iz < ORDER; iz++) {
                 int z = idx[2]+iz;
@@ -259,9 +259,9 @@ __global__ void __launch_bounds__(256) k_pmeInterpolate(PmeArgs a) {
         // ReferencePME.cpp:698-700
         const double qd = q;
         const double gx = fx*a.nx, gy = fy*a.ny, gz = fz*a.nz;
-        const double Fx = -qd*(gx*a.boxd.recip[0][0]);
-        const double Fy = -qd*(gx*a.boxd.recip[1][0]+gy*a.boxd.recip[1][1]);
-        const double Fz = -qd*(gx*a.boxd.recip[2][0]+gy*a.boxd.recip[2][1]+gz*a.boxd.recip[2][2]);
+        const double Fx = -qd*(gx*a.sp->exact.boxd.recip[0][0]);
+        const double Fy = -qd*(gx*a.sp->exact.boxd.recip[1][0]+gy*a.sp->exact.boxd.recip[1][1]);
+        const double Fz = -qd*(gx*a.sp->exact.boxd.recip[2][0]+gy*a.sp->exact.boxd.recip[2][1]+gz*a.sp->exact.boxd.recip[2][2]);
         addFixed(&a.forceOrig[atom], toFixedD(Fx));
         addFixed(&a.forceOrig[a.paddedAtoms+atom], toFixedD(Fy));
         addFixed(&a.forceOrig[2*a.paddedAtoms+atom], toFixedD(Fz));

@@ -47,8 +47,6 @@ struct DirectParams {
     double cutoff2d;
     double alphad, krfd, crfd, switchDistd, invSwitchWidthd;
     double dalphad, dispShiftExpd, invCut6d;   // LJPME: alpha_d, [1-exp(-d_c^2)(1+d_c^2+d_c^4/2)], rc^-6
-    double lambdaCd[SNB_MAX_SLICES], lambdaVd[SNB_MAX_SLICES];
-    BoxD boxd;
 };
 
 // what the exact (double) cutoff predicate reads; lives in device memory so that the rare out-of-line
@@ -57,6 +55,17 @@ struct ExactParams {
     BoxD boxd;
     double cutoff2d;
     int periodic;
+};
+
+// Everything that may change from one evaluation to the next WITHOUT changing a launch shape: the box
+// and the slice lambdas.  One copy in device memory, refreshed by a single host->device copy from a
+// pinned mirror at the head of every evaluation, so that the whole evaluation can be replayed as a
+// CUDA graph (api.cu) with no per-node parameter updates.
+struct StepParams {
+    ExactParams exact;                  // exact.boxd is THE double-precision box
+    BoxF box;
+    float shiftLimit[3];                // halfBox - cutoff per axis (one-image-per-j-atom shortcut)
+    double lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
 };
 
 // ---- small device helpers ---------------------------------------------------------

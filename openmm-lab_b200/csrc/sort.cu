@@ -21,9 +21,9 @@ __global__ void k_assignCells(SortArgs a) {
     if (a.periodic) {
         // fractional coordinates, frac = pos * recip (lower triangular)
         double f[3];
-        f[0] = x*a.boxd.recip[0][0]+y*a.boxd.recip[1][0]+z*a.boxd.recip[2][0];
-        f[1] = y*a.boxd.recip[1][1]+z*a.boxd.recip[2][1];
-        f[2] = z*a.boxd.recip[2][2];
+        f[0] = x*a.sp->exact.boxd.recip[0][0]+y*a.sp->exact.boxd.recip[1][0]+z*a.sp->exact.boxd.recip[2][0];
+        f[1] = y*a.sp->exact.boxd.recip[1][1]+z*a.sp->exact.boxd.recip[2][1];
+        f[2] = z*a.sp->exact.boxd.recip[2][2];
         for (int d = 0; d < 3; d++) {
             double w = f[d]-floor(f[d]);
             c[d] = min(a.cellDim[d]-1, (int) (w*a.cellDim[d]));
@@ -154,12 +154,12 @@ __global__ void k_blockBounds(SortArgs a) {
     if (atom >= 0) {
         p[0] = a.posd[3*atom]; p[1] = a.posd[3*atom+1]; p[2] = a.posd[3*atom+2];
         if (a.periodic) {
-            double fz = floor(p[2]*a.boxd.recip[2][2]);
-            double fy = floor(p[1]*a.boxd.recip[1][1]+p[2]*a.boxd.recip[2][1]);
-            double fx = floor(p[0]*a.boxd.recip[0][0]+p[1]*a.boxd.recip[1][0]+p[2]*a.boxd.recip[2][0]);
-            p[0] -= fx*a.boxd.ax+fy*a.boxd.bx+fz*a.boxd.cx;
-            p[1] -= fy*a.boxd.by+fz*a.boxd.cy;
-            p[2] -= fz*a.boxd.cz;
+            double fz = floor(p[2]*a.sp->exact.boxd.recip[2][2]);
+            double fy = floor(p[1]*a.sp->exact.boxd.recip[1][1]+p[2]*a.sp->exact.boxd.recip[2][1]);
+            double fx = floor(p[0]*a.sp->exact.boxd.recip[0][0]+p[1]*a.sp->exact.boxd.recip[1][0]+p[2]*a.sp->exact.boxd.recip[2][0]);
+            p[0] -= fx*a.sp->exact.boxd.ax+fy*a.sp->exact.boxd.bx+fz*a.sp->exact.boxd.cx;
+            p[1] -= fy*a.sp->exact.boxd.by+fz*a.sp->exact.boxd.cy;
+            p[2] -= fz*a.sp->exact.boxd.cz;
         }
         prm = a.params4[atom];
         a.sortedPos[atom] = k;

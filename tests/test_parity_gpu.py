@@ -162,3 +162,41 @@ def test_deterministic_forces():
         b = evaluate("B200", w, properties=props)
         assert np.array_equal(a["forces"], b["forces"])
         assert a["energy"] == b["energy"] or abs(a["energy"]-b["energy"]) < 1e-9*abs(a["energy"])
+
+
+def test_graph_replay_follows_positions_box_and_lambdas():
+    # From the second evaluation of a given shape on, the platform replays a captured CUDA graph; the box,
+    # the lambdas and the positions reach it through device memory.  Every replay must still match the oracle.
+    w = systems.water_box()
+    rng = np.random.default_rng(11)
+    contexts = {}
+    for platform, props in (("Reference", None), ("B200", DOUBLE), ("B200", None)):
+        ctx = mm.Context(w.system, platform, props)
+        contexts[(platform, str(props))] = ctx
+    base = w.positions.copy()
+    L = w.box[0][0]
+    replays = 0
+    for step in range(5):
+        pos = (base+rng.normal(scale=0.004*step, size=base.shape)).astype(np.float32).astype(np.float64)
+        scale = np.float64(np.float32(1.0+0.002*step))
+        box = np.diag([L*scale]*3)
+        lam = [0.8, 0.1, 1.0, 0.55, 0.3][step]
+        results = {}
+        for key, ctx in contexts.items():
+            ctx.setPositions(pos*scale)
+            ctx.setPeriodicBoxVectors(*box)
+            ctx.setParameter("lambda", lam)
+            kernel = ctx._kernels[0][1]
+            ctx._forces = np.zeros((w.num_particles, 3))
+            ctx._energyParameterDerivatives = {}
+            e = kernel.execute(ctx, True, True, True, True)
+            results[key] = {"energy": e, "forces": ctx._forces.copy(), "slices": kernel.sliceEnergies.copy(),
+                            "derivs": dict(ctx._energyParameterDerivatives)}
+            if key[0] == "B200":
+                replays += kernel.getCounters()[4]
+        ref = results[("Reference", "None")]
+        assert_parity(ref, results[("B200", str(DOUBLE))], TOL, "graph replay step %d [double]" % step)
+        got = results[("B200", "None")]
+        assert abs(ref["energy"]-got["energy"]) <= 1e-5*max(abs(ref["energy"]), np.abs(ref["slices"]).sum())
+        assert np.abs(ref["forces"]-got["forces"]).max() <= 1e-4*np.sqrt((ref["forces"]**2).sum(axis=1).mean())
+    assert replays >= 6, "the CUDA-graph path was not exercised (%d replays)" % replays
