@@ -703,6 +703,17 @@ PmeArgs pmeArgs(snb_handle& h, int term, bool sorted) {
     return pa;
 }
 
+template <typename R> void fillConsts(DirectConsts<R>& c, const DirectParams& p) {
+    c.cutoffHi = (R) (p.cutoff2d+p.bandTol); c.cutoffLo = (R) (p.cutoff2d-p.bandTol);
+    c.alpha = (R) p.alphad; c.alpha2 = (R) (p.alphad*p.alphad); c.halfAlpha = (R) (0.5*p.alphad);
+    c.negAlpha2Log2e = (R) (-p.alphad*p.alphad*1.4426950408889634);
+    c.twoAlphaOverSqrtPi = (R) (2.0*p.alphad/1.772453850905516);
+    c.krf = (R) p.krfd; c.crf = (R) p.crfd; c.twoKrf = (R) (2.0*p.krfd);
+    // no switching function: the test `r > switchDist` must never fire
+    c.switchDist = p.invSwitchWidthd != 0.0 ? (R) p.switchDistd : (R) INFINITY; c.invSwitchWidth = (R) p.invSwitchWidthd;
+    c.dalpha2 = (R) (p.dalphad*p.dalphad); c.dispShiftExp = (R) p.dispShiftExpd; c.invCut6 = (R) p.invCut6d;
+}
+
 // Enqueue one whole evaluation on the handle's streams (no host synchronisation, no allocation: the
 // sequence is capturable as a CUDA graph).
 void enqueueStep(snb_handle& h, const StepInputs& in) {
@@ -835,6 +846,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         p.dalphad = h.dalpha;
         p.dispShiftExpd = 1.0-exp(-dc2)*(1.0+dc2+0.5*dc2*dc2);
         p.invCut6d = pow(h.cutoff, -6.0);
+        fillConsts(da.cf, p);
+        fillConsts(da.cd, p);
         da.sp = h.stepD.p;
         da.kind = h.method == SNB_NO_CUTOFF ? KIND_PLAIN : h.method <= SNB_CUTOFF_PERIODIC ? KIND_RF : h.method == SNB_LJPME ? KIND_LJPME : KIND_EWALD;
         da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
@@ -1001,7 +1014,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, v
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
     if (includeDirect) launches += (periodic ? 5 : 6)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
-    if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 4 : 3)*(h.method == SNB_LJPME ? 2 : 1);
+    if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 5 : 4)*(h.method == SNB_LJPME ? 2 : 1);    // spread (+finish), convolution, combine, interpolate
     if (includeForces || h.comm) launches += 1+(h.comm && h.rank == 0 ? 1 : 0);
     if (posqDev) launches += 1;
     h.countersOut[2] = launches;

@@ -51,6 +51,8 @@ void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 
 struct DirectArgs {
     DirectParams p;
+    DirectConsts<float> cf;
+    DirectConsts<double> cd;
     const StepParams* sp;          // box, lambdas, exact-predicate parameters
     int kind, useSwitch, numSubsets, needEnergy, doublePrecision;
     const int* sortedAtom;

@@ -26,6 +26,7 @@
 
 #define LIST_WARPS 4
 #define HIT_CAP 128            /* hit blocks buffered per batch; a fuller octet emits several batches */
+#define CAND_WORDS 512         /* 1024 unsigned shorts: the candidate blocks of one window of 32 bitmap words */
 
 __device__ __forceinline__ float wrapOrtho(float d, float L, float invL) { return d-L*rintf(d*invL); }
 
@@ -64,7 +65,10 @@ __device__ __forceinline__ float imageDist2(float dx, float dy, float dz, float3
 }
 
 // Range of cells [lo, lo+n) (periodic: modulo dim) along every axis that the box centre +- half can touch.
-__device__ __forceinline__ void cellSpan(const ListArgs& a, const double c[3], const double half[3], int lo[3], int n[3]) {
+// For axis-aligned cells (orthorhombic or non-periodic) it also returns what the per-cell distance test
+// needs: rel = position of cell `lo` relative to the centre, in cell units, and the cell size in nm.
+__device__ __forceinline__ void cellSpan(const ListArgs& a, const double c[3], const double half[3], int lo[3], int n[3],
+                                         float rel[3], float cellSize[3]) {
     if (a.periodic) {
         const double (*r)[3] = a.sp->exact.boxd.recip;
         double f[3], h[3];
@@ -78,8 +82,10 @@ __device__ __forceinline__ void cellSpan(const ListArgs& a, const double c[3], c
             const int dim = a.cellDim[d];
             const int l = (int) floor((f[d]-h[d])*dim), u = (int) floor((f[d]+h[d])*dim);
             n[d] = min(u-l+1, dim);
-            int m = l%dim;
-            lo[d] = n[d] == dim ? 0 : (m < 0 ? m+dim : m);
+            const int m = l%dim;
+            lo[d] = m < 0 ? m+dim : m;
+            rel[d] = (float) ((double) l-f[d]*dim);
+            cellSize[d] = (float) (1.0/(fabs(r[d][d])*dim));
         }
     }
     else {
@@ -87,14 +93,24 @@ __device__ __forceinline__ void cellSpan(const ListArgs& a, const double c[3], c
             const int dim = a.cellDim[d];
             const double e0 = a.extent[d], span = a.extent[3+d]-e0;
             int l = 0, u = 0;
+            rel[d] = 0.f;
+            cellSize[d] = 0.f;
             if (span > 0) {
                 l = max(0, min(dim-1, (int) floor((c[d]-half[d]-e0)/span*dim)));
                 u = max(0, min(dim-1, (int) floor((c[d]+half[d]-e0)/span*dim)));
+                rel[d] = (float) ((double) l-(c[d]-e0)/span*dim);
+                cellSize[d] = (float) (span/dim);
             }
             lo[d] = l;
             n[d] = u-l+1;
         }
     }
+}
+
+// distance along one axis between cell `i` of the span and the octet's box, in nm
+__device__ __forceinline__ float cellGap(float rel, int i, float halfCells, float cellSize) {
+    const float left = rel+(float) i;                   // the cell spans [left, left+1] around the box centre
+    return fmaxf(0.f, fmaxf(left-halfCells, -(left+1.f)-halfCells))*cellSize;
 }
 
 __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
@@ -106,10 +122,11 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     const float4 ext = a.octetExt[O];
     if (ext.x < 0.f)
         return;                                         // padding octet
-    unsigned* bm = sMem+(size_t) w*(a.bitmapWords+3*HIT_CAP);
+    unsigned* bm = sMem+(size_t) w*(a.bitmapWords+3*HIT_CAP+CAND_WORDS);
     int* hitJ = (int*) (bm+a.bitmapWords);
     unsigned* hitWord = (unsigned*) (hitJ+HIT_CAP);
     int* hitBase = (int*) (hitWord+HIT_CAP);
+    unsigned short* cand = (unsigned short*) (hitBase+HIT_CAP);     // candidates of the current window of 32 words
     const unsigned full = 0xffffffffu;
     const int I = O>>2, lastI = O*8+7, wFirst = I>>5;
     const float4 oc = a.octetCenter[O];
@@ -117,6 +134,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
     const float cut2 = a.cutoff*a.cutoff;
     const BoxF box = a.sp->box;
+    const int pbcMode = a.pbcMode;
 
     // ---- 1. candidate blocks ------------------------------------------------------------------
     for (int k = wFirst+lane; k < a.bitmapWords; k += 32)
@@ -137,7 +155,12 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
         const double c[3] = {cIx+(double) oc.x, cIy+(double) oc.y, cIz+(double) oc.z};
         const double half[3] = {(double) oe.x+a.cutoff+margin, (double) oe.y+a.cutoff+margin, (double) oe.z+a.cutoff+margin};
         int lo[3], n[3];
-        cellSpan(a, c, half, lo, n);
+        float rel[3], cs[3];
+        cellSpan(a, c, half, lo, n, rel, cs);
+        // axis-aligned cells: skip those farther than the cutoff from the octet's box (the corners of the span)
+        const bool prune = pbcMode != PBC_PAIR_TRICLINIC && cs[0] > 0.f && cs[1] > 0.f && cs[2] > 0.f;
+        const float hc0 = prune ? (oe.x+1e-5f)/cs[0] : 0.f, hc1 = prune ? (oe.y+1e-5f)/cs[1] : 0.f, hc2 = prune ? (oe.z+1e-5f)/cs[2] : 0.f;
+        const float pruneCut2 = (a.cutoff+1e-5f)*(a.cutoff+1e-5f);
         const int nyz = n[1]*n[2], total = n[0]*nyz;
         const int dy = a.cellDim[1], dz = a.cellDim[2], dx = a.cellDim[0];
         for (int base = 0; base < total; base += 128) {
@@ -149,11 +172,22 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
                 if (idx < total) {
                     const int ix = idx/nyz, s = idx-ix*nyz;
                     const int iy = s/n[2], iz = s-iy*n[2];
-                    int cx = lo[0]+ix, cy = lo[1]+iy, cz = lo[2]+iz;
-                    cx -= cx >= dx ? dx : 0;
-                    cy -= cy >= dy ? dy : 0;
-                    cz -= cz >= dz ? dz : 0;
-                    range[u] = a.cellRange[(cx*dy+cy)*dz+cz];
+                    bool near = true;
+                    if (prune) {
+                        // an axis whose span was clamped to the whole box may see a cell's other image closer
+                        float gx = cellGap(rel[0], ix, hc0, cs[0]), gy = cellGap(rel[1], iy, hc1, cs[1]), gz = cellGap(rel[2], iz, hc2, cs[2]);
+                        if (n[0] == dx) gx = fminf(gx, cellGap(rel[0], ix+dx, hc0, cs[0]));
+                        if (n[1] == dy) gy = fminf(gy, cellGap(rel[1], iy+dy, hc1, cs[1]));
+                        if (n[2] == dz) gz = fminf(gz, cellGap(rel[2], iz+dz, hc2, cs[2]));
+                        near = gx*gx+gy*gy+gz*gz < pruneCut2;
+                    }
+                    if (near) {
+                        int cx = lo[0]+ix, cy = lo[1]+iy, cz = lo[2]+iz;
+                        cx -= cx >= dx ? dx : 0;
+                        cy -= cy >= dy ? dy : 0;
+                        cz -= cz >= dz ? dz : 0;
+                        range[u] = a.cellRange[(cx*dy+cy)*dz+cz];
+                    }
                 }
             }
 #pragma unroll
@@ -171,9 +205,10 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     int nh = 0;
     bool first = true, dead = false;
     // octets too wide for the one-image-per-j-atom shortcut wrap every pair instead
-    const int wide = (a.pbcMode == PBC_SHIFT && (ext.x >= a.sp->shiftLimit[0] || ext.y >= a.sp->shiftLimit[1] || ext.z >= a.sp->shiftLimit[2])) ? 1 : 0;
+    const int wide = (pbcMode == PBC_SHIFT && (ext.x >= a.sp->shiftLimit[0] || ext.y >= a.sp->shiftLimit[1] || ext.z >= a.sp->shiftLimit[2])) ? 1 : 0;
     const int ki = O*8+(lane&7);
-    const int atomI = lane < 8 ? a.sortedAtom[ki] : -1;
+    const int atomK = a.sortedAtom[ki];                 // atom k = lane&7 of the octet, on every lane
+    const int atomI = lane < 8 ? atomK : -1;
 
     auto flush = [&]() {
         // positions of the batch's entries (the octet's own atoms occupy entries 0..7 of its first batch)
@@ -222,14 +257,16 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
                 out[hitBase[k]+__popc(wb&((1u<<lane)-1))] = make_int2(hitJ[k]*32+lane, 0);
         }
         __syncwarp();
-        // exclusion masks from the i side; partners before the octet are that octet's business
-        if (atomI >= 0) {
-            const int e0 = a.exclStart[atomI], e1 = a.exclStart[atomI+1];
-            for (int e = e0; e < e1; e++) {
+        // exclusion masks from the i side (4 lanes share an atom's list); partners before the octet are
+        // that octet's business
+        if (atomK >= 0) {
+            const int e0 = a.exclStart[atomK], e1 = a.exclStart[atomK+1];
+            const unsigned bit = 1u<<(lane&7);
+            for (int e = e0+(lane>>3); e < e1; e += 4) {
                 const int sp = a.sortedPos[a.exclList[e]];
                 if ((sp>>3) == O) {
-                    if (first && (sp&7) > lane)
-                        atomicOr(&out[sp&7].y, (int) (1u<<lane));
+                    if (first && (sp&7) > (lane&7))
+                        atomicOr(&out[sp&7].y, (int) bit);
                 }
                 else if (sp > lastI) {
                     // hit blocks are in ascending order: binary search for the partner's block
@@ -243,7 +280,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
                     if (found >= 0) {
                         const unsigned word = hitWord[found];
                         if ((word>>b)&1u)
-                            atomicOr(&out[hitBase[found]+__popc(word&((1u<<b)-1))].y, (int) (1u<<lane));
+                            atomicOr(&out[hitBase[found]+__popc(word&((1u<<b)-1))].y, (int) bit);
                     }
                 }
             }
@@ -253,29 +290,59 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
         nh = 0;
     };
 
+    // the interaction flags of one candidate block: 32 atoms against the octet's box
+    auto testBlock = [&](int J, const float4& pj, double bx, double by, double bz) -> unsigned {
+        const int j = J*32+lane;
+        bool acc = J >= 0 && j < a.numAtoms && j > lastI;
+        if (a.useCutoff && acc) {
+            const float px = pj.x+(float) (bx-cIx)-oc.x, py = pj.y+(float) (by-cIy)-oc.y, pz = pj.z+(float) (bz-cIz)-oc.z;
+            acc = imageDist2(px, py, pz, oe, pbcMode, box) < cut2;
+        }
+        return __ballot_sync(full, acc);
+    };
+
     for (int w0 = wFirst; w0 < a.bitmapWords && !dead; w0 += 32) {
-        const unsigned myWord = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
-        unsigned nz = __ballot_sync(full, myWord != 0u);
-        while (nz && !dead) {
-            const int src = __ffs(nz)-1;
-            nz &= nz-1;
-            unsigned wd = __shfl_sync(full, myWord, src);
-            const int Jbase = (w0+src)*32;
-            while (wd && !dead) {
-                const int J = Jbase+__ffs(wd)-1;
-                wd &= wd-1;
-                const int j = J*32+lane;
-                bool acc = j < a.numAtoms && j > lastI;
-                if (a.useCutoff) {
-                    const float4 pj = a.posqLocal[j];
-                    const float px = pj.x+(float) (a.blockCenter[3*J]-cIx)-oc.x, py = pj.y+(float) (a.blockCenter[3*J+1]-cIy)-oc.y,
-                                pz = pj.z+(float) (a.blockCenter[3*J+2]-cIz)-oc.z;
-                    acc = acc && imageDist2(px, py, pz, oe, a.pbcMode, box) < cut2;
+        // candidates of this window of 32 words, in ascending order
+        unsigned myWord = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
+        if (!__any_sync(full, myWord != 0u))
+            continue;
+        const int cnt = __popc(myWord);
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int nc = __shfl_sync(full, incl, 31);
+        if (nc == 0)
+            continue;
+        int pos = incl-cnt;
+        while (myWord) {
+            cand[pos++] = (unsigned short) (lane*32+__ffs(myWord)-1);
+            myWord &= myWord-1;
+        }
+        __syncwarp();
+        const int Jbase = w0*32;
+        for (int k0 = 0; k0 < nc && !dead; k0 += 4) {
+            // four candidates in flight: their loads are issued before the first test
+            int J[4];
+            float4 pj[4];
+            double bc[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                J[u] = k0+u < nc ? Jbase+cand[k0+u] : -1;
+                pj[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                bc[u][0] = bc[u][1] = bc[u][2] = 0.0;
+                if (J[u] >= 0 && a.useCutoff) {
+                    pj[u] = a.posqLocal[J[u]*32+lane];
+                    bc[u][0] = a.blockCenter[3*J[u]]; bc[u][1] = a.blockCenter[3*J[u]+1]; bc[u][2] = a.blockCenter[3*J[u]+2];
                 }
-                const unsigned word = __ballot_sync(full, acc);
-                if (word) {
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned word = testBlock(J[u], pj[u], bc[u][0], bc[u][1], bc[u][2]);
+                if (word && !dead) {
                     if (lane == 0) {
-                        hitJ[nh] = J;
+                        hitJ[nh] = J[u];
                         hitWord[nh] = word;
                     }
                     nh++;
@@ -285,6 +352,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
                 }
             }
         }
+        __syncwarp();
     }
     if (!dead && (first || nh > 0))
         flush();
@@ -295,7 +363,7 @@ void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs) {
     const int numOctets = a.octHi-a.octLo;
     if (numOctets <= 0)
         return;
-    const size_t smem = sizeof(unsigned)*(size_t) LIST_WARPS*(a.bitmapWords+3*HIT_CAP);
+    const size_t smem = sizeof(unsigned)*(size_t) LIST_WARPS*(a.bitmapWords+3*HIT_CAP+CAND_WORDS);
     static size_t attrSet = 0;
     if (smem > 48*1024 && smem > attrSet) {
         cudaFuncSetAttribute(k_buildList, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

@@ -71,46 +71,70 @@ template <typename R> __device__ __forceinline__ R pmeCharge(const PmeArgs& a, i
     return (R) (a.term == 0 ? prm.x : 8.0f*prm.y*prm.y*prm.y*prm.z);
 }
 
-// ---- spreading: one warp per atom (sorted order: neighbouring warps hit neighbouring cells);
-// lane -> (ix, iy) for the 25 xy offsets of the 5x5x5 stencil, 5 consecutive z points each.
-template <typename R, bool FIXED>
-__global__ void __launch_bounds__(256) k_pmeSpread(PmeArgs a) {
-    const int k = (blockIdx.x*blockDim.x+threadIdx.x)>>5, lane = threadIdx.x&31;
-    if (k >= a.numAtoms || lane >= ORDER*ORDER)
-        return;
-    const int atom = a.sortedAtom ? a.sortedAtom[k] : k;
-    if (atom < 0)
-        return;
-    const R q = pmeCharge<R>(a, atom);
-    if (q == 0)
-        return;
+// ---- spreading.  A CTA takes PME_ATOMS consecutive atoms of the sorted order (neighbouring atoms hit
+// neighbouring grid cells).  Phase 1, one thread per atom: grid index, order-5 B-spline weights and
+// charge, once, into shared memory.  Phase 2, one warp per atom: lane -> (iy, iz) of the 5x5 yz face of
+// the stencil, a serial walk over the 5 x planes, so that ONE atomic instruction of the warp covers 5
+// rows x 5 consecutive z points (5-10 sectors) instead of 25 different rows.
+#define PME_ATOMS 64             /* atoms per CTA */
+#define PME_THREADS 256          /* 8 warps: 8 atoms each in phase 2 */
+#define PME_ATOMS_PER_WARP (PME_ATOMS/(PME_THREADS/32))
+
+template <typename R> struct PmeAtom {
+    R th[3][ORDER];
+    R q;
     int idx[3];
-    R frac[3], tx[ORDER], ty[ORDER], tz[ORDER], dt[ORDER];
-    gridCoord<R>(a, atom, idx, frac);
-    bspline5<R>(frac[0], tx, dt);
-    bspline5<R>(frac[1], ty, dt);
-    bspline5<R>(frac[2], tz, dt);
-    const int subset = __float_as_int(a.params4[atom].w);
-    const int ix = lane/ORDER, iy = lane-ix*ORDER;
-    int x = idx[0]+ix, y = idx[1]+iy;
-    x -= x >= a.nx ? a.nx : 0;
-    y -= y >= a.ny ? a.ny : 0;
-    R wx = tx[0], wy = ty[0];
-#pragma unroll
-    for (int m = 1; m < ORDER; m++) {
-        wx = ix == m ? tx[m] : wx;
-        wy = iy == m ? ty[m] : wy;
+    int subset;         // -1: nothing to spread (padding, zero charge)
+};
+
+template <typename R, bool FIXED>
+__global__ void __launch_bounds__(PME_THREADS) k_pmeSpread(PmeArgs a) {
+    __shared__ PmeAtom<R> sAtom[PME_ATOMS];
+    if (threadIdx.x < PME_ATOMS) {
+        const int k = blockIdx.x*PME_ATOMS+threadIdx.x;
+        PmeAtom<R>& me = sAtom[threadIdx.x];
+        me.subset = -1;
+        if (k < a.numAtoms) {
+            const int atom = a.sortedAtom ? a.sortedAtom[k] : k;
+            if (atom >= 0) {
+                const R q = pmeCharge<R>(a, atom);
+                if (q != 0) {
+                    R frac[3], dt[ORDER];
+                    gridCoord<R>(a, atom, me.idx, frac);
+                    bspline5<R>(frac[0], me.th[0], dt);
+                    bspline5<R>(frac[1], me.th[1], dt);
+                    bspline5<R>(frac[2], me.th[2], dt);
+                    me.q = q;
+                    me.subset = __float_as_int(a.params4[atom].w);
+                }
+            }
+        }
     }
-    const R qxy = q*wx*wy;
-    const size_t row = (((size_t) subset*a.nx+x)*a.ny+y)*a.nz;
-#pragma unroll
-    for (int iz = 0; iz < ORDER; iz++) {
-        int z = idx[2]+iz;
+    __syncthreads();
+    const int lane = threadIdx.x&31, warp = threadIdx.x>>5;
+    if (lane >= ORDER*ORDER)
+        return;
+    const int iy = lane/ORDER, iz = lane-iy*ORDER;
+    for (int i = 0; i < PME_ATOMS_PER_WARP; i++) {
+        const PmeAtom<R>& at = sAtom[warp*PME_ATOMS_PER_WARP+i];
+        if (at.subset < 0)
+            continue;
+        int y = at.idx[1]+iy, z = at.idx[2]+iz;
+        y -= y >= a.ny ? a.ny : 0;
         z -= z >= a.nz ? a.nz : 0;
-        if (FIXED)
-            atomicAdd((unsigned long long*) a.gridFixed+row+z, (unsigned long long) __double2ll_rn((double) (qxy*tz[iz])*PME_FIXED_SCALE));
-        else
-            atomicAdd((R*) a.grid+row+z, qxy*tz[iz]);
+        const R wyz = at.q*at.th[1][iy]*at.th[2][iz];
+        const size_t plane = (size_t) a.ny*a.nz;
+        const size_t base = (size_t) at.subset*a.nx*plane+(size_t) y*a.nz+z;
+#pragma unroll
+        for (int ix = 0; ix < ORDER; ix++) {
+            int x = at.idx[0]+ix;
+            x -= x >= a.nx ? a.nx : 0;
+            const R v = wyz*at.th[0][ix];
+            if (FIXED)
+                atomicAdd((unsigned long long*) a.gridFixed+base+x*plane, (unsigned long long) __double2ll_rn((double) v*PME_FIXED_SCALE));
+            else
+                atomicAdd((R*) a.grid+base+x*plane, v);
+        }
     }
 }
 
@@ -201,70 +225,119 @@ __global__ void __launch_bounds__(256) k_pmeConvolution(PmeArgs a) {
             atomicAdd(&a.energyBuf[2*k+a.term], sE[k]);
 }
 
-// ---- interpolation: one warp per atom, lane -> (ix, iy), 5 z points x all subsets' potentials
+// ---- potentials seen by each subset: phi_i = sum_j lambda[slice(i,j)] * grid_j, in place, so that the
+// interpolation reads ONE value per stencil point whatever the number of subsets (the reference applies
+// the lambdas inside the interpolation loop, ReferencePME.cpp:634-701; same sums, reordered).
 template <typename R>
-__global__ void __launch_bounds__(256) k_pmeInterpolate(PmeArgs a) {
-    const int k = (blockIdx.x*blockDim.x+threadIdx.x)>>5, lane = threadIdx.x&31;
-    if (k >= a.numAtoms)
-        return;
-    const int atom = a.sortedAtom ? a.sortedAtom[k] : k;
-    if (atom < 0)
-        return;
-    const R q = pmeCharge<R>(a, atom);
-    if (q == 0)
-        return;
-    double fx = 0, fy = 0, fz = 0;
-    if (lane < ORDER*ORDER) {
-        int idx[3];
-        R frac[3], tx[ORDER], ty[ORDER], tz[ORDER], dtx[ORDER], dty[ORDER], dtz[ORDER];
-        gridCoord<R>(a, atom, idx, frac);
-        bspline5<R>(frac[0], tx, dtx);
-        bspline5<R>(frac[1], ty, dty);
-        bspline5<R>(frac[2], tz, dtz);
-        const int si = __float_as_int(a.params4[atom].w);
-        const size_t G = (size_t) a.nx*a.ny*a.nz;
-        const int ix = lane/ORDER, iy = lane-ix*ORDER;
-        int x = idx[0]+ix, y = idx[1]+iy;
-        x -= x >= a.nx ? a.nx : 0;
-        y -= y >= a.ny ? a.ny : 0;
-        R wx = tx[0], wy = ty[0], dwx = dtx[0], dwy = dty[0];
-#pragma unroll
-        for (int m = 1; m < ORDER; m++) {
-            wx = ix == m ? tx[m] : wx; dwx = ix == m ? dtx[m] : dwx;
-            wy = iy == m ? ty[m] : wy; dwy = iy == m ? dty[m] : dwy;
+__global__ void __launch_bounds__(256) k_pmeCombine(PmeArgs a, size_t G) {
+    __shared__ R sLambda[SNB_MAX_SUBSETS*SNB_MAX_SUBSETS];
+    const int S = a.numSubsets;
+    if (threadIdx.x < S*S) {
+        const int si = threadIdx.x/S, sj = threadIdx.x-si*S;
+        sLambda[threadIdx.x] = (R) (a.term == 0 ? a.sp->lambdaC : a.sp->lambdaV)[sliceOf(si, sj)];
+    }
+    __syncthreads();
+    R* grid = (R*) a.grid;
+    for (size_t i = blockIdx.x*(size_t) blockDim.x+threadIdx.x; i < G; i += (size_t) gridDim.x*blockDim.x) {
+        R v[SNB_MAX_SUBSETS];
+        for (int j = 0; j < S; j++)
+            v[j] = grid[j*G+i];
+        for (int k = 0; k < S; k++) {
+            R phi = 0;
+            for (int j = 0; j < S; j++)
+                phi += sLambda[k*S+j]*v[j];
+            grid[k*G+i] = phi;
         }
-        const R* row = (const R*) a.grid+((size_t) x*a.ny+y)*a.nz;
-        R s0 = 0, s1 = 0;           // sum_z theta_z * phi, sum_z dtheta_z * phi
-        for (int sj = 0; sj < a.numSubsets; sj++) {
-            const R lam = (R) (a.term == 0 ? a.sp->lambdaC : a.sp->lambdaV)[sliceOf(si, sj)];
-#pragma unroll
-            for (int iz = 0; iz < ORDER; iz++) {
-                int z = idx[2]+iz;
-                z -= z >= a.nz ? a.nz : 0;
-                const R v = lam*row[sj*G+z];
-                s0 += tz[iz]*v;
-                s1 += dtz[iz]*v;
+    }
+}
+
+// ---- interpolation: same two phases; phase 2 gathers 5 x planes of the 5x5 yz face per lane, for every
+// subset's potential grid weighted by the lambda of the slice it forms with the atom's subset, and reduces
+// the three force components over the 25 lanes by warp shuffle.
+template <typename R> struct PmeAtomD {
+    R th[3][ORDER], dth[3][ORDER];
+    R q;
+    int idx[3];
+    int subset, atom;   // subset -1: nothing to do
+    R f[3];             // phase 2 result: sums over the stencil of (dtheta theta theta, ...) * phi
+};
+
+template <typename R>
+__global__ void __launch_bounds__(PME_THREADS) k_pmeInterpolate(PmeArgs a) {
+    __shared__ PmeAtomD<R> sAtom[PME_ATOMS];
+    if (threadIdx.x < PME_ATOMS) {
+        const int k = blockIdx.x*PME_ATOMS+threadIdx.x;
+        PmeAtomD<R>& me = sAtom[threadIdx.x];
+        me.subset = -1;
+        if (k < a.numAtoms) {
+            const int atom = a.sortedAtom ? a.sortedAtom[k] : k;
+            if (atom >= 0) {
+                const R q = pmeCharge<R>(a, atom);
+                if (q != 0) {
+                    R frac[3];
+                    gridCoord<R>(a, atom, me.idx, frac);
+                    bspline5<R>(frac[0], me.th[0], me.dth[0]);
+                    bspline5<R>(frac[1], me.th[1], me.dth[1]);
+                    bspline5<R>(frac[2], me.th[2], me.dth[2]);
+                    me.q = q;
+                    me.subset = __float_as_int(a.params4[atom].w);
+                    me.atom = atom;
+                }
             }
         }
-        fx = dwx*wy*s0;
-        fy = wx*dwy*s0;
-        fz = wx*wy*s1;
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, o);
-        fy += __shfl_xor_sync(0xffffffffu, fy, o);
-        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    __syncthreads();
+    const int lane = threadIdx.x&31, warp = threadIdx.x>>5;
+    const bool active = lane < ORDER*ORDER;
+    const int iy = active ? lane/ORDER : 0, iz = active ? lane-iy*ORDER : 0;
+    const size_t plane = (size_t) a.ny*a.nz, G = plane*a.nx;
+    for (int i = 0; i < PME_ATOMS_PER_WARP; i++) {
+        PmeAtomD<R>& at = sAtom[warp*PME_ATOMS_PER_WARP+i];
+        if (at.subset < 0)
+            continue;
+        R fx = 0, fy = 0, fz = 0;
+        if (active) {
+            int y = at.idx[1]+iy, z = at.idx[2]+iz;
+            y -= y >= a.ny ? a.ny : 0;
+            z -= z >= a.nz ? a.nz : 0;
+            const R* cell = (const R*) a.grid+(size_t) y*a.nz+z;
+            R s0 = 0, s1 = 0;               // sum_x theta_x * phi, sum_x dtheta_x * phi
+#pragma unroll
+            for (int ix = 0; ix < ORDER; ix++) {
+                int x = at.idx[0]+ix;
+                x -= x >= a.nx ? a.nx : 0;
+                const R phi = cell[at.subset*G+x*plane];     // already lambda-combined for this subset (k_pmeCombine)
+                s0 += at.th[0][ix]*phi;
+                s1 += at.dth[0][ix]*phi;
+            }
+            fx = s1*at.th[1][iy]*at.th[2][iz];
+            fy = s0*at.dth[1][iy]*at.th[2][iz];
+            fz = s0*at.th[1][iy]*at.dth[2][iz];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (lane == 0) {
+            at.f[0] = fx; at.f[1] = fy; at.f[2] = fz;
+        }
     }
-    if (lane == 0) {
-        // ReferencePME.cpp:698-700
-        const double qd = q;
-        const double gx = fx*a.nx, gy = fy*a.ny, gz = fz*a.nz;
-        const double Fx = -qd*(gx*a.sp->exact.boxd.recip[0][0]);
-        const double Fy = -qd*(gx*a.sp->exact.boxd.recip[1][0]+gy*a.sp->exact.boxd.recip[1][1]);
-        const double Fz = -qd*(gx*a.sp->exact.boxd.recip[2][0]+gy*a.sp->exact.boxd.recip[2][1]+gz*a.sp->exact.boxd.recip[2][2]);
-        addFixed(&a.forceOrig[atom], toFixedD(Fx));
-        addFixed(&a.forceOrig[a.paddedAtoms+atom], toFixedD(Fy));
-        addFixed(&a.forceOrig[2*a.paddedAtoms+atom], toFixedD(Fz));
+    __syncthreads();
+    // phase 3, one thread per atom: to Cartesian forces (ReferencePME.cpp:698-700), in double
+    if (threadIdx.x < PME_ATOMS) {
+        const PmeAtomD<R>& at = sAtom[threadIdx.x];
+        if (at.subset >= 0) {
+            const BoxD boxd = a.sp->exact.boxd;
+            const double qd = at.q;
+            const double gx = (double) at.f[0]*a.nx, gy = (double) at.f[1]*a.ny, gz = (double) at.f[2]*a.nz;
+            const double Fx = -qd*(gx*boxd.recip[0][0]);
+            const double Fy = -qd*(gx*boxd.recip[1][0]+gy*boxd.recip[1][1]);
+            const double Fz = -qd*(gx*boxd.recip[2][0]+gy*boxd.recip[2][1]+gz*boxd.recip[2][2]);
+            addFixed(&a.forceOrig[at.atom], toFixedD(Fx));
+            addFixed(&a.forceOrig[a.paddedAtoms+at.atom], toFixedD(Fy));
+            addFixed(&a.forceOrig[2*a.paddedAtoms+at.atom], toFixedD(Fz));
+        }
     }
 }
 
@@ -274,23 +347,23 @@ void launchPmeEterm(const PmeArgs& a, cudaStream_t stream) {
 }
 void launchPmeSpread(const PmeArgs& a, cudaStream_t stream) {
     const size_t total = (size_t) a.numSubsets*a.nx*a.ny*a.nz;
-    const int blocks = (int) (((size_t) a.numAtoms*32+255)/256);
+    const int blocks = (a.numAtoms+PME_ATOMS-1)/PME_ATOMS;
     if (a.gridFixed) {
         cudaMemsetAsync(a.gridFixed, 0, sizeof(long long)*total, stream);
         int fb = (int) std::min<size_t>((total+255)/256, 2368);
         if (a.doublePrecision) {
-            k_pmeSpread<double, true><<<blocks, 256, 0, stream>>>(a);
+            k_pmeSpread<double, true><<<blocks, PME_THREADS, 0, stream>>>(a);
             k_pmeFinishSpread<double><<<fb, 256, 0, stream>>>(a, total);
         }
         else {
-            k_pmeSpread<float, true><<<blocks, 256, 0, stream>>>(a);
+            k_pmeSpread<float, true><<<blocks, PME_THREADS, 0, stream>>>(a);
             k_pmeFinishSpread<float><<<fb, 256, 0, stream>>>(a, total);
         }
     }
     else {
         cudaMemsetAsync(a.grid, 0, (a.doublePrecision ? 8 : 4)*total, stream);
-        if (a.doublePrecision) k_pmeSpread<double, false><<<blocks, 256, 0, stream>>>(a);
-        else k_pmeSpread<float, false><<<blocks, 256, 0, stream>>>(a);
+        if (a.doublePrecision) k_pmeSpread<double, false><<<blocks, PME_THREADS, 0, stream>>>(a);
+        else k_pmeSpread<float, false><<<blocks, PME_THREADS, 0, stream>>>(a);
     }
 }
 void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream) {
@@ -300,7 +373,11 @@ void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream) {
     else k_pmeConvolution<float><<<blocks, 256, 0, stream>>>(a);
 }
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream) {
-    const int blocks = (int) (((size_t) a.numAtoms*32+255)/256);
-    if (a.doublePrecision) k_pmeInterpolate<double><<<blocks, 256, 0, stream>>>(a);
-    else k_pmeInterpolate<float><<<blocks, 256, 0, stream>>>(a);
+    const int blocks = (a.numAtoms+PME_ATOMS-1)/PME_ATOMS;
+    const size_t G = (size_t) a.nx*a.ny*a.nz;
+    const int cb = (int) std::min<size_t>((G+255)/256, 2368);
+    if (a.doublePrecision) k_pmeCombine<double><<<cb, 256, 0, stream>>>(a, G);
+    else k_pmeCombine<float><<<cb, 256, 0, stream>>>(a, G);
+    if (a.doublePrecision) k_pmeInterpolate<double><<<blocks, PME_THREADS, 0, stream>>>(a);
+    else k_pmeInterpolate<float><<<blocks, PME_THREADS, 0, stream>>>(a);
 }

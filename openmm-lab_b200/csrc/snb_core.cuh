@@ -49,6 +49,16 @@ struct DirectParams {
     double dalphad, dispShiftExpd, invCut6d;   // LJPME: alpha_d, [1-exp(-d_c^2)(1+d_c^2+d_c^4/2)], rc^-6
 };
 
+// The pair arithmetic's constants, precomputed on the host in the kernel's own precision: they sit in the
+// kernel-parameter constant bank and are used as instruction operands (no in-loop conversions).
+template <typename R> struct DirectConsts {
+    R cutoffHi, cutoffLo;               // cutoff^2 +- band: inside the band the exact double predicate decides
+    R alpha, alpha2, halfAlpha, negAlpha2Log2e, twoAlphaOverSqrtPi;
+    R krf, crf, twoKrf;
+    R switchDist, invSwitchWidth;
+    R dalpha2, dispShiftExp, invCut6;
+};
+
 // what the exact (double) cutoff predicate reads; lives in device memory so that the rare out-of-line
 // call takes a pointer instead of forcing the kernel's parameter block onto the stack
 struct ExactParams {
@@ -95,6 +105,22 @@ __device__ __forceinline__ float erfcxPoly(float x) {
     const float m = 0.66666666666666663f, h = 0.33333333333333337f;   // t in [1/3, 1]
     float t = fastRcp(fmaf(0.5f, x, 1.0f));
     float u = (t-m)*(1.0f/h);
+    float p = -7.5385177448e-07f;
+    p = fmaf(p, u, -8.2052179778e-06f);
+    p = fmaf(p, u, 3.4861879002e-05f);
+    p = fmaf(p, u, 9.8919924926e-05f);
+    p = fmaf(p, u, -8.6138957608e-04f);
+    p = fmaf(p, u, -1.6015017984e-03f);
+    p = fmaf(p, u, 2.2509531568e-02f);
+    p = fmaf(p, u, 1.4242693719e-01f);
+    p = fmaf(p, u, 4.0981802125e-01f);
+    p = fmaf(p, u, 4.2758357745e-01f);
+    return p;
+}
+
+// same polynomial, taking t = 1/(1 + x/2) (the caller folds alpha into the reciprocal's argument)
+__device__ __forceinline__ float erfcxPolyT(float t) {
+    const float u = fmaf(t, 3.0f, -2.0f);
     float p = -7.5385177448e-07f;
     p = fmaf(p, u, -8.2052179778e-06f);
     p = fmaf(p, u, 3.4861879002e-05f);
