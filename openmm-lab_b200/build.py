@@ -24,6 +24,7 @@ def _stale(target, deps):
 
 def build(verbose=False, force=False):
     nvcc = os.environ.get("NVCC", "nvcc")
+    extra = os.environ.get("SNB_NVCC_EXTRA", "").split()       # tuning experiments, e.g. -DDIRECT_CTAS_PER_SM=16
     headers = [os.path.join(CSRC, h) for h in HEADERS]
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -31,7 +32,7 @@ def build(verbose=False, force=False):
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(obj, [os.path.join(CSRC, src)]+headers):
-            jobs.append([nvcc]+NVCC_FLAGS+["-c", os.path.join(CSRC, src), "-o", obj])
+            jobs.append([nvcc]+NVCC_FLAGS+extra+["-c", os.path.join(CSRC, src), "-o", obj])
 
     def run(cmd):
         out = subprocess.run(cmd, capture_output=True, text=True)

@@ -160,9 +160,9 @@ struct PmeGrid {
 // same nodes with the same arguments (the box and the lambdas travel through StepParams in device
 // memory), so the second one onwards replays a captured CUDA graph.
 struct GraphKey {
-    int flags, hostPositions, pbcMode, cellDim[3], numCells, itemChunks, needEnergy;
-    size_t maxChunks, maxItems;
-    const void *posqDev, *forcesFixedOut, *jList, *workItems;
+    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy;
+    size_t maxChunks;
+    const void *posqDev, *forcesFixedOut, *jList;
 };
 
 #define SNB_ENERGY_DOUBLES (32*2*SNB_MAX_SLICES+8)   /* 32 replicas of [slice][term] + flags ([0] = list overflow) */
@@ -173,7 +173,6 @@ struct snb_handle {
     double cutoff = 1, switchDist = 0, rfDielectric = 78.3, alpha = 0, dalpha = 0;
     bool useSwitch = false, exceptionsPeriodic = false, useDispersion = false;
     bool doublePrecision = false, deterministic = false;
-    int itemChunks = SNB_ITEM_CHUNKS;
     int grid[3] = {0, 0, 0}, dgrid[3] = {0, 0, 0};
     std::vector<int> subsets;
     std::vector<std::array<double, 3>> baseParticle;          // q, sigma, eps
@@ -206,17 +205,17 @@ struct snb_handle {
     cudaEvent_t evSorted = nullptr, evPmeDone = nullptr, evBegin = nullptr, evEnd = nullptr;
     float lastDeviceMs = 0;
     int numSMs = 148;
-    DevBuf<double> posd, paramsD, exception14, blockCenter, extent, energyBuf, forcesOutD;
-    DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt;
+    DevBuf<double> posd, paramsD, exception14, extent, energyBuf, forcesOutD;
+    DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt, blockCenter;
     DevBuf<double4> posqLocalD, sparamsD;
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
                 exclStart, exclList, is14D, counters, cellScratch;
     DevBuf<int2> exceptionAtomsD, jList, cellRange;
-    DevBuf<int4> workItems;
+    DevBuf<int> chunkOctet;
     DevBuf<long long> forceSorted, forceOrig;
     PinnedBuf<double> hPos, hForces, hEnergy;
     PinnedBuf<int> hCounters;
-    size_t maxChunks = 0, maxItems = 0;
+    size_t maxChunks = 0;
     PmeGrid pme, dpme;
     // ---- multi-GPU (comm.cuh): tile list and exceptions partitioned, reciprocal space on rank 0 ----
     ncclComm_t comm = nullptr;
@@ -466,7 +465,7 @@ snb_handle* createHandle(const snb_desc& d) {
         h.sortedAtom.alloc(h.NP); h.sortedPos.alloc(h.N);
         h.posqLocal.alloc(h.NP); h.sparams.alloc(h.NP);
         if (h.doublePrecision) { h.posqLocalD.alloc(h.NP); h.sparamsD.alloc(h.NP); }
-        h.blockCenter.alloc(3*(size_t) h.NB); h.blockExt.alloc(h.NB);
+        h.blockCenter.alloc(h.NB); h.blockExt.alloc(h.NB);
         h.octetCenter.alloc(4*(size_t) h.NB); h.octetExt.alloc(4*(size_t) h.NB);
         h.extent.alloc(6);
         h.energyBuf.alloc(SNB_ENERGY_DOUBLES);    // 32 replicas of the slice-energy table (direct.cu), summed on the host, + flags
@@ -623,12 +622,8 @@ void ensureListCapacity(snb_handle& h, const double* box, bool periodic) {
         perOctet = std::min<size_t>((size_t) (atoms/32)+2, (size_t) h.NB+2);
     }
     h.maxChunks = std::max<size_t>(64, perOctet*4*h.NB);
-    // work items of 1..8 chunks: small systems need short items to fill 148 SMs many times over
-    size_t expectedChunks = h.maxChunks*2/3;
-    h.itemChunks = (int) std::max<size_t>(2, std::min<size_t>(SNB_ITEM_CHUNKS, expectedChunks/((size_t) h.numSMs*24*6)));
-    h.maxItems = h.maxChunks/h.itemChunks+8*(size_t) h.NB+16;
     h.jList.alloc(h.maxChunks*32);
-    h.workItems.alloc(h.maxItems);
+    h.chunkOctet.alloc(h.maxChunks);
 }
 
 struct Timer {
@@ -822,8 +817,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         la.sortedAtom = h.sortedAtom.p; la.sortedPos = h.sortedPos.p; la.posqLocal = h.posqLocal.p;
         la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p; la.octetCenter = h.octetCenter.p; la.octetExt = h.octetExt.p;
         la.exclStart = h.exclStart.p; la.exclList = h.exclList.p;
-        la.jList = h.jList.p; la.workItems = h.workItems.p; la.counters = h.counters.p;
-        la.maxChunks = (int) h.maxChunks; la.maxItems = (int) h.maxItems; la.itemChunks = h.itemChunks;
+        la.jList = h.jList.p; la.chunkOctet = h.chunkOctet.p; la.counters = h.counters.p;
+        la.maxChunks = (int) h.maxChunks;
         la.cellRange = h.cellRange.p; la.extent = h.extent.p;
         for (int k = 0; k < 3; k++) la.cellDim[k] = h.cellDim[k];
         int64_t lo = 0, hi = 4*(int64_t) h.NB;
@@ -853,7 +848,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
         da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
         da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
-        da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.workItems = h.workItems.p;
+        da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.chunkOctet = h.chunkOctet.p; da.maxChunks = (int) h.maxChunks;
         da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
         launchDirect(da, st, h.numSMs);
         tm.mark(3);
@@ -948,10 +943,10 @@ bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, v
     memset(&key, 0, sizeof(key));
     key.flags = flags; key.hostPositions = in.hostPositions; key.pbcMode = in.pbcMode;
     for (int k = 0; k < 3; k++) key.cellDim[k] = h.cellDim[k];
-    key.numCells = h.numCells; key.itemChunks = h.itemChunks;
+    key.numCells = h.numCells;
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
-    key.maxChunks = h.maxChunks; key.maxItems = h.maxItems;
-    key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p; key.workItems = h.workItems.p;
+    key.maxChunks = h.maxChunks;
+    key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p;
     const bool graphable = h.useGraph && !h.timing && !h.comm;
     const bool sameKey = h.graphKeyValid && memcmp(&key, &h.graphKey, sizeof(key)) == 0;
     if (!graphable || !sameKey)
@@ -996,9 +991,8 @@ bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, v
         if (h.hCounters.p[2]) {
             // list buffers too small: grow to what the device asked for and repeat
             h.maxChunks = (size_t) (h.hCounters.p[0]*1.25)+64;
-            h.maxItems = std::max<size_t>(h.maxItems, (size_t) (h.hCounters.p[1]*1.25)+64);
             h.jList.alloc(h.maxChunks*32);
-            h.workItems.alloc(h.maxItems);
+            h.chunkOctet.alloc(h.maxChunks);
         }
         if (anyOverflow)
             return false;       // all ranks repeat together (the flag travelled with the all-reduce)
@@ -1009,7 +1003,6 @@ bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, v
         CUDA_CHECK(cudaEventElapsedTime(&h.phaseMs[SNB_PHASE_TOTAL], h.ev[0], h.ev[9]));
     }
     h.countersOut[1] = h.hCounters.p[0];
-    h.countersOut[3] = h.hCounters.p[1];
     h.countersOut[4] = h.graphExec ? 1 : 0;
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;

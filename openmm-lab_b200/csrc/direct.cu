@@ -4,7 +4,7 @@
 template <int KIND> void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid);
 
 void launchDirect(const DirectArgs& a, cudaStream_t st, int numSMs) {
-    int grid = numSMs*24;       // one-warp CTAs, persistent, dynamic work fetch
+    int grid = numSMs*DIRECT_CTAS_PER_SM;       // one-warp CTAs, all resident, equal contiguous shares of the chunk list
     switch (a.kind) {
         case KIND_PLAIN: launchDirectKind<KIND_PLAIN>(a, st, grid); break;
         case KIND_RF: launchDirectKind<KIND_RF>(a, st, grid); break;

@@ -1,13 +1,21 @@
 // Direct-space tile kernel (north-star subsystem 2).
 //
-// One warp per work item = one octet of i atoms against up to SNB_ITEM_CHUNKS chunks of 32 compacted
-// j atoms.  The octet is held four times over in the warp (lane = 8*copy + k, atom k of the octet);
-// copy c owns j slots 8c..8c+7 of the chunk, so a chunk is 8 steps of 32 pairs.  A chunk's j atoms are
-// gathered with coalesced float4 loads, shifted into the octet's frame (one periodic image per j atom
-// where the box allows it) and staged in shared memory.  In step s lane (c,k) works on slot
-// 8c + (k+s)%8: every step touches 32 different pairs, the j-force accumulators travel between the 8
-// lanes of a copy by warp shuffle and are home after 8 steps, so no reduction tree is needed; the four
-// copies' i forces are summed by shuffle once per work item.
+// The tile list is a flat array of chunks: 32 compacted j atoms against one octet of i atoms.  Every warp
+// (one-warp CTAs) takes an equal, contiguous range of chunks -- chunks cost the same, so the static split
+// balances -- and streams through it:
+//   * the octet is held four times over in the warp (lane = 8*copy + k, atom k of the octet); copy c owns
+//     j slots 8c..8c+7 of the chunk, so a chunk is 8 steps of 32 pairs.  In step s lane (c,k) works on slot
+//     8c + (k+s)%8: every step touches 32 different pairs, the j-force accumulators travel between the 8
+//     lanes of a copy by warp shuffle and are home after 8 steps, so no reduction tree is needed; the four
+//     copies' i forces are summed by shuffle when the octet changes;
+//   * a chunk's j atoms (position+charge, parameters, block centre) are gathered two chunks ahead: the list
+//     entry by a plain load, the atom data by cp.async straight into the other half of a double-buffered
+//     shared-memory stage, so the gather's two dependent global-memory latencies hide behind the pair
+//     arithmetic of the current chunk; one fix-up pass shifts the staged atoms into the octet's frame
+//     (exact float block-centre differences, one periodic image per j atom where the box allows it);
+//   * the pair arithmetic is branch-free in single precision: out-of-range / excluded lanes compute on a
+//     harmless r^2 and are masked out by selects (nearly every step has some lane in range, so a branch
+//     saves no issue slots and only blocks the scheduler from overlapping the steps).
 // Pair arithmetic is FP32 (MUFU rsqrt + Newton step, MUFU ex2, polynomial erfc); i forces are carried
 // in FP64 across chunks; all forces leave as 2^32 fixed-point 64-bit atomics (order independent =>
 // bit-reproducible); slice energies are accumulated per j subset in FP32 per chunk and FP64 beyond.
@@ -18,7 +26,6 @@
 // (behavioural cross-reference on the GPU side: platforms/common/src/kernels/coulombLennardJones.cc:1-124).
 #include "kernels.cuh"
 
-#define DIRECT_CTAS_PER_SM 24
 #define ENERGY_REPLICAS 32      /* copies of the slice-energy table, to spread the final atomics */
 
 template <int KIND> void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid);
@@ -84,9 +91,11 @@ __device__ __forceinline__ unsigned opaque(unsigned x) {
     asm volatile("mov.u32 %0, %0;" : "+r"(x));
     return x;
 }
+// One stage buffer: pos[32] | prm[32] | ctr[32] (float4 block centres) | aux[32] (int2: j, mask); slot
+// stride = sizeof(vec4) for pos/prm, 16 for ctr, 8 for aux.
 template <typename R> struct Stage;
 template <> struct Stage<float> {
-    enum { STRIDE = 16, PRM = 512, AUX = 1024, BYTES = 1536 };
+    enum { STRIDE = 16, PRM = 512, CTR = 1024, AUX = 1536, BYTES = 1792 };
     static __device__ __forceinline__ float4 ld4(unsigned ad) {
         float4 v;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ad) : "memory");
@@ -97,7 +106,7 @@ template <> struct Stage<float> {
     }
 };
 template <> struct Stage<double> {
-    enum { STRIDE = 32, PRM = 1024, AUX = 2048, BYTES = 3072 };
+    enum { STRIDE = 32, PRM = 1024, CTR = 2048, AUX = 2560, BYTES = 2816 };
     static __device__ __forceinline__ double4 ld4(unsigned ad) {
         double4 v;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ad) : "memory");
@@ -109,6 +118,17 @@ template <> struct Stage<double> {
         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(ad+16), "d"(v.z), "d"(v.w) : "memory");
     }
 };
+__device__ __forceinline__ float4 ldSharedF4(unsigned ad) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ad) : "memory");
+    return v;
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS): no registers, completion tracked per thread in groups
+__device__ __forceinline__ void cpAsync16(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ unsigned ldSharedU32(unsigned ad) {
     unsigned v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ad) : "memory");
@@ -199,7 +219,7 @@ static __device__ __noinline__ void bandPairs(DirectOut o, DirectConsts<R> c, un
         const int slot = (copy<<3)|((k+s)&7);
         const vec4 q = *(const vec4*) (stage+slot*Stage<R>::STRIDE);
         const vec4 prm = *(const vec4*) (stage+Stage<R>::PRM+slot*Stage<R>::STRIDE);
-        const int j = *(const int*) (stage+Stage<R>::AUX+slot*Stage<R>::STRIDE);
+        const int j = *(const int*) (stage+Stage<R>::AUX+slot*8);
         const int origJ = o.sortedAtom[j];
         if (!exactInRange(o.posd, origI, origJ, &o.sp->exact))
             continue;
@@ -241,30 +261,32 @@ template <typename R, int KIND, int PBC, int NSUB, bool ENERGY, bool DUMP>
 __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? DIRECT_CTAS_PER_SM/2 : DIRECT_CTAS_PER_SM) : 8) k_direct(DirectArgs a) {
     constexpr int NS = NSUB > 0 ? NSUB : SNB_MAX_SUBSETS;
     constexpr bool TWO = NSUB == 2;         // subsets 0/1 travel as the floats 0.0/1.0: lambdas and energies by FMA
+    constexpr int STEP_UNROLL = DIRECT_UNROLL;
+    constexpr bool BRANCHY = sizeof(R) == 8 || NSUB == 0;   // double precision: skip the arithmetic of masked lanes
     typedef typename Real<R>::vec4 vec4;
     typedef Stage<R> St;
-    // one warp per CTA: the staging area is addressed by the slot alone
-    __shared__ __align__(256) unsigned char sStage[St::BYTES];
+    // one warp per CTA: the two stage buffers are addressed by the slot alone
+    __shared__ __align__(256) unsigned char sStage[2][St::BYTES+(256-St::BYTES%256)%256];
+    constexpr unsigned BUF = sizeof(sStage[0]);
     const int lane = threadIdx.x;
     const int copy = lane>>3, k = lane&7;
     const unsigned full = 0xffffffffu;
-    const DirectParams& p = a.p;
     const DirectConsts<R>& c = Real<R>::consts(a);
     const int numSub = NSUB > 0 ? NSUB : a.numSubsets;
-    const int numItems = a.counters[1];
+    // this warp's contiguous share of the chunks
+    const int numChunks = min(a.counters[0], a.maxChunks);
+    const int per = (numChunks+(int) gridDim.x-1)/(int) gridDim.x;
+    const int cBegin = min(numChunks, (int) blockIdx.x*per), cEnd = min(numChunks, cBegin+per);
     const BoxD boxd = a.sp->exact.boxd;
     const R bAx = (R) boxd.ax, bBy = (R) boxd.by, bCz = (R) boxd.cz;
     const R iAx = (R) (1.0/boxd.ax), iBy = (R) (1.0/boxd.by), iCz = (R) (1.0/boxd.cz);
     const unsigned kBit = opaque(1u<<k);
     const int srcLane = (int) opaque((unsigned) ((copy<<3)|((k+1)&7)));     // the j accumulators move one lane down inside the copy
-    const unsigned stageBase = (unsigned) __cvta_generic_to_shared(sStage);
-    const unsigned myAddr = opaque(stageBase+lane*St::STRIDE);
+    const unsigned stageBase = opaque((unsigned) __cvta_generic_to_shared(&sStage[0][0]));
     // slot of step s = 8*copy + (k+s)%8: address = copyBase | ((kOff + s*STRIDE) & (7*STRIDE)), two instructions
-    const unsigned copyBase = opaque(stageBase+(copy<<3)*St::STRIDE), kOff = opaque(k*St::STRIDE);
-    (void) p;
-    // slice energies of this thread over all its work items, keyed by (own subset, j subset), kept in
-    // shared memory (they are touched once per work item; registers are worth more in the pair loop);
-    // reduced over the warp once, at the end of the kernel
+    const unsigned copyOff = opaque((copy<<3)*St::STRIDE), kOff = opaque(k*St::STRIDE);
+    // slice energies of this thread over all its chunks, keyed by (own subset, j subset), kept in shared
+    // memory (touched once per octet; registers are worth more in the pair loop); reduced over the warp once
     constexpr int NA = NS > 4 ? 1 : NS;
     __shared__ double sAccC[NA*NA][32], sAccV[NA*NA][32];
     if (ENERGY && NSUB > 0) {
@@ -272,183 +294,39 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
         for (int s = 0; s < NA*NA; s++)
             sAccC[s][lane] = sAccV[s][lane] = 0.0;
     }
-    for (;;) {
-        int item = 0;
-        if (lane == 0)
-            item = atomicAdd(&a.counters[3], 1);
-        item = __shfl_sync(full, item, 0);
-        if (item >= numItems)
-            break;
-        const int4 wi = a.workItems[item];
-        const int O = wi.x, I = O>>2;
-        const bool perPair = PBC == PBC_SHIFT && wi.w != 0;    // octet too wide for one image per j atom
-        const int ki = O*8+k;
-        const vec4 pi = Real<R>::pos(a)[ki];
-        const vec4 si4 = Real<R>::prm(a)[ki];
-        const int subI = (int) si4.z;           // subsets travel as exact small reals, -1 = padding lane
-        const bool iValid = subI >= 0;
-        const int origI = a.sortedAtom[ki];
-        const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
-        const float4 oc = a.octetCenter[O];
-        // a padding lane can never be "in range": its bounds are negative
-        const R myCutHi = iValid ? c.cutoffHi : (R) -1, myCutLo = iValid ? c.cutoffLo : (R) -1;
-        SubsetTable<R, NSUB> t;
+
+    // gather of chunk `ch` into stage buffer `buf`: list entry -> aux, atom data by cp.async
+    auto gather = [&](const int2 ent, unsigned buf) {
+        const int j = max(ent.x, 0);        // padding entries copy atom 0: never in range (mask 0xff)
+        const unsigned dst = stageBase+buf*BUF;
+        const char* ps = (const char*) (Real<R>::pos(a)+j);
+        const char* qs = (const char*) (Real<R>::prm(a)+j);
 #pragma unroll
-        for (int s = 0; s < NS; s++) {
-            int sl = sliceOf(max(subI, 0), s);
-            t.lamC[s] = s < numSub ? (R) a.sp->lambdaC[sl] : (R) 0;
-            t.lamV[s] = s < numSub ? (R) a.sp->lambdaV[sl] : (R) 0;
-            t.EC[s] = t.EV[s] = 0.0;
+        for (int b = 0; b < (int) sizeof(vec4); b += 16) {
+            cpAsync16(dst+lane*St::STRIDE+b, ps+b);
+            cpAsync16(dst+St::PRM+lane*St::STRIDE+b, qs+b);
         }
-        const R dLamC = TWO ? t.lamC[1]-t.lamC[0] : (R) 0, dLamV = TWO ? t.lamV[1]-t.lamV[0] : (R) 0;
-        double Fx = 0, Fy = 0, Fz = 0;
-        for (int ch = 0; ch < wi.z; ch++) {
-            // ---- gather and stage the chunk's j atoms -------------------------------------
-            const int2 ent = a.jList[(size_t) (wi.y+ch)*32+lane];
-            vec4 pj, sj4;
-            pj.x = pj.y = pj.z = pj.w = 0; sj4.x = sj4.y = sj4.z = sj4.w = 0;
-            if (ent.x >= 0) {
-                pj = Real<R>::pos(a)[ent.x];
-                sj4 = Real<R>::prm(a)[ent.x];
-                const int J = ent.x>>5;
-                R ox = (R) (a.blockCenter[3*J]-cIx), oy = (R) (a.blockCenter[3*J+1]-cIy), oz = (R) (a.blockCenter[3*J+2]-cIz);
-                pj.x += ox; pj.y += oy; pj.z += oz;
-                if (PBC == PBC_SHIFT && !perPair) {
-                    // one image per j atom, chosen relative to the octet's centre (valid while
-                    // halfBox - cutoff exceeds the octet's half extent; the list build flags the rest)
-                    pj.x -= bAx*Real<R>::rint((pj.x-(R) oc.x)*iAx);
-                    pj.y -= bBy*Real<R>::rint((pj.y-(R) oc.y)*iBy);
-                    pj.z -= bCz*Real<R>::rint((pj.z-(R) oc.z)*iCz);
-                }
-            }
-            __syncwarp();
-            St::st4(myAddr, pj);
-            St::st4(myAddr+St::PRM, sj4);
-            stSharedV2U32(myAddr+St::AUX, (unsigned) ent.x, (unsigned) ent.y);
-            __syncwarp();
-            R fix = 0, fiy = 0, fiz = 0, fjx = 0, fjy = 0, fjz = 0;
-            R eCt = 0, eVt = 0, eC1 = 0, eV1 = 0;       // TWO: totals and the j-subset-1 parts
-            unsigned bandMask = 0;
+        cpAsync16(dst+St::CTR+lane*16, a.blockCenter+(j>>5));
+        stSharedV2U32(dst+St::AUX+lane*8, (unsigned) ent.x, (unsigned) ent.y);
+        cpAsyncCommit();
+    };
+
+    // ---- the octet in flight
+    int curO = -1, ki = 0, origI = -1, subI = -1;
+    bool iValid = false, perPair = false;
+    vec4 pi, si4;
+    pi.x = pi.y = pi.z = pi.w = 0; si4 = pi;
+    float4 cI = make_float4(0.f, 0.f, 0.f, 0.f), oc = cI;
+    R myCutHi = -1, myCutLo = -1, dLamC = 0, dLamV = 0;
+    SubsetTable<R, NSUB> t;
 #pragma unroll
-            for (int s = 0; s < NS; s++)
-                t.eC[s] = t.eV[s] = 0;
-            // ---- 8 steps of 32 pairs --------------------------------------------------------
-#pragma unroll
-            for (int s = 0; s < 8; s++) {
-                const unsigned ad = copyBase|((kOff+s*St::STRIDE)&(7*St::STRIDE));
-                const vec4 q = St::ld4(ad);
-                const unsigned mj = ldSharedU32(ad+St::AUX+4);
-                R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
-                if (PBC == PBC_SHIFT && perPair) {
-                    dx -= bAx*Real<R>::rint(dx*iAx);
-                    dy -= bBy*Real<R>::rint(dy*iBy);
-                    dz -= bCz*Real<R>::rint(dz*iCz);
-                }
-                else if (PBC == PBC_PAIR_TRICLINIC) {
-                    R m = Real<R>::rint(dz*iCz);
-                    dx -= m*(R) boxd.cx; dy -= m*(R) boxd.cy; dz -= m*bCz;
-                    m = Real<R>::rint(dy*iBy);
-                    dx -= m*(R) boxd.bx; dy -= m*bBy;
-                    m = Real<R>::rint(dx*iAx);
-                    dx -= m*bAx;
-                }
-                const R r2 = dx*dx+dy*dy+dz*dz;
-                // the hot path takes the pairs safely inside the cutoff; those inside the band around it (about
-                // 1e-5 of all pairs) are only noted, and settled exactly after the eight steps (bandPairs)
-                const bool ok = !(mj&kBit);
-                bool in;
-                if (KIND != KIND_PLAIN) {
-                    in = ok && r2 < myCutLo;
-                    if (ok && !(r2 < myCutLo) && r2 < myCutHi)
-                        bandMask |= 1u<<s;
-                }
-                else
-                    in = ok && iValid;
-                if (in) {
-                    const vec4 prm = St::ld4(ad+St::PRM);
-                    R fc, fv, ec, ev, invR2;
-                    pairMath<R, KIND>(c, r2, pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
-                    R lc, lv;
-                    if (NSUB == 1) {
-                        lc = t.lamC[0]; lv = t.lamV[0];
-                    }
-                    else if (TWO) {
-                        lc = fma(prm.z, dLamC, t.lamC[0]);
-                        lv = fma(prm.z, dLamV, t.lamV[0]);
-                    }
-                    else if (NSUB > 0) {
-                        lc = t.lamC[0]; lv = t.lamV[0];
-#pragma unroll
-                        for (int u = 1; u < NS; u++) {
-                            lc = prm.z == (R) u ? t.lamC[u] : lc;
-                            lv = prm.z == (R) u ? t.lamV[u] : lv;
-                        }
-                    }
-                    else {
-                        const int sl = sliceOf(subI, (int) prm.z);
-                        lc = (R) a.sp->lambdaC[sl]; lv = (R) a.sp->lambdaV[sl];
-                    }
-                    const R f = (lv*fv+lc*fc)*invR2;
-                    fix += f*dx; fiy += f*dy; fiz += f*dz;
-                    fjx -= f*dx; fjy -= f*dy; fjz -= f*dz;
-                    if (ENERGY) {
-                        if (TWO) {
-                            eCt += ec; eVt += ev;
-                            eC1 = fma(prm.z, ec, eC1); eV1 = fma(prm.z, ev, eV1);
-                        }
-                        else if (NSUB > 0) {
-#pragma unroll
-                            for (int u = 0; u < NS; u++) {
-                                t.eC[u] += prm.z == (R) u ? ec : (R) 0;
-                                t.eV[u] += prm.z == (R) u ? ev : (R) 0;
-                            }
-                        }
-                        else {
-                            // many subsets: straight to the global table (rare configuration)
-                            double* table = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
-                            atomicAdd(&table[2*sliceOf(subI, (int) prm.z)], (double) ec);
-                            atomicAdd(&table[2*sliceOf(subI, (int) prm.z)+1], (double) ev);
-                        }
-                    }
-                    if (DUMP) {
-                        const int origJ = a.sortedAtom[(int) ldSharedU32(ad+St::AUX)];
-                        unsigned long long idx = atomicAdd(a.pairDumpCount, 1ull);
-                        if ((long long) idx < a.pairDumpCapacity)
-                            a.pairDump[idx] = make_int2(min(origI, origJ), max(origI, origJ));
-                    }
-                }
-                fjx = __shfl_sync(full, fjx, srcLane);
-                fjy = __shfl_sync(full, fjy, srcLane);
-                fjz = __shfl_sync(full, fjz, srcLane);
-            }
-            if (KIND != KIND_PLAIN && __any_sync(full, bandMask != 0u)) {
-                if (bandMask) {
-                    DirectOut o;
-                    o.posd = a.posd; o.sortedAtom = a.sortedAtom; o.sp = a.sp; o.forceSorted = a.forceSorted; o.paddedAtoms = a.paddedAtoms;
-                    o.energyTable = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
-                    o.pairDump = a.pairDump; o.pairDumpCount = a.pairDumpCount; o.pairDumpCapacity = a.pairDumpCapacity;
-                    bandPairs<R, KIND, PBC, ENERGY, DUMP>(o, c, bandMask, lane, ki, origI, pi, si4, perPair ? 1 : 0, sStage);
-                }
-            }
-            if (ent.x >= 0) {
-                addFixed(&a.forceSorted[ent.x], Real<R>::fixed(fjx));
-                addFixed(&a.forceSorted[a.paddedAtoms+ent.x], Real<R>::fixed(fjy));
-                addFixed(&a.forceSorted[2*a.paddedAtoms+ent.x], Real<R>::fixed(fjz));
-            }
-            Fx += fix; Fy += fiy; Fz += fiz;
-            if (ENERGY && TWO) {
-                t.EC[0] += eCt-eC1; t.EC[1] += eC1;
-                t.EV[0] += eVt-eV1; t.EV[1] += eV1;
-            }
-            else if (ENERGY && NSUB > 0) {
-#pragma unroll
-                for (int u = 0; u < NS; u++) {
-                    t.EC[u] += t.eC[u];
-                    t.EV[u] += t.eV[u];
-                }
-            }
-        }
-        // the four copies of the octet: sum their i forces (and energies) onto copy 0
+    for (int s = 0; s < NS; s++) {
+        t.lamC[s] = t.lamV[s] = 0;
+        t.EC[s] = t.EV[s] = 0.0;
+    }
+    double Fx = 0, Fy = 0, Fz = 0;
+    auto flushOctet = [&]() {
+        // the four copies of the octet: sum their i forces onto copy 0
         for (int o = 8; o < 32; o <<= 1) {
             Fx += __shfl_xor_sync(full, Fx, o);
             Fy += __shfl_xor_sync(full, Fy, o);
@@ -466,7 +344,217 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 sAccV[subI*NA+u][lane] += t.EV[u];
             }
         }
+        Fx = Fy = Fz = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            t.EC[s] = t.EV[s] = 0.0;
+    };
+
+    // ---- prologue: chunk cBegin is gathered, the entry of cBegin+1 is on its way
+    int2 entNext = make_int2(-1, 0xff);
+    int jCur = -1, octCur = 0, octNext = 0;
+    if (cBegin < cEnd) {
+        const int2 e0 = a.jList[(size_t) cBegin*32+lane];
+        octCur = a.chunkOctet[cBegin];
+        jCur = e0.x;
+        gather(e0, 0);
+        if (cBegin+1 < cEnd) {
+            entNext = a.jList[(size_t) (cBegin+1)*32+lane];
+            octNext = a.chunkOctet[cBegin+1];
+        }
     }
+    for (int ch = cBegin; ch < cEnd; ch++) {
+        const unsigned buf = (unsigned) (ch-cBegin)&1u;
+        const unsigned sb = stageBase+buf*BUF;
+        __syncwarp();                       // every lane is done reading the other buffer (chunk ch-1)
+        // ---- keep the pipeline full: gather chunk ch+1, fetch the entry of chunk ch+2
+        const int jNext = entNext.x;
+        const int octNext1 = octNext;
+        if (ch+1 < cEnd) {
+            gather(entNext, buf^1u);
+            if (ch+2 < cEnd) {
+                entNext = a.jList[(size_t) (ch+2)*32+lane];
+                octNext = a.chunkOctet[ch+2];
+            }
+            cpAsyncWait<1>();               // chunk ch has landed (all but the newest group)
+        }
+        else
+            cpAsyncWait<0>();
+        // ---- octet switch
+        const int O = octCur&0x3fffffff;
+        if (O != curO) {
+            if (curO >= 0)
+                flushOctet();
+            curO = O;
+            ki = O*8+k;
+            pi = Real<R>::pos(a)[ki];
+            si4 = Real<R>::prm(a)[ki];
+            subI = (int) si4.z;             // subsets travel as exact small reals, -1 = padding lane
+            iValid = subI >= 0;
+            origI = a.sortedAtom[ki];
+            cI = a.blockCenter[O>>2];
+            oc = a.octetCenter[O];
+            // a padding lane can never be "in range": its bounds are negative
+            myCutHi = iValid ? c.cutoffHi : (R) -1; myCutLo = iValid ? c.cutoffLo : (R) -1;
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                const int sl = sliceOf(max(subI, 0), s);
+                t.lamC[s] = s < numSub ? (R) a.sp->lambdaC[sl] : (R) 0;
+                t.lamV[s] = s < numSub ? (R) a.sp->lambdaV[sl] : (R) 0;
+            }
+            if (TWO) { dLamC = t.lamC[1]-t.lamC[0]; dLamV = t.lamV[1]-t.lamV[0]; }
+        }
+        perPair = PBC == PBC_SHIFT && (octCur&0x40000000) != 0;     // octet too wide for one image per j atom
+        // ---- fix-up: the staged j atom of this lane moves into the octet's block frame
+        {
+            vec4 pj = St::ld4(sb+lane*St::STRIDE);
+            const float4 cJ = ldSharedF4(sb+St::CTR+lane*16);
+            pj.x += (R) (cJ.x-cI.x); pj.y += (R) (cJ.y-cI.y); pj.z += (R) (cJ.z-cI.z);
+            if (PBC == PBC_SHIFT && !perPair) {
+                // one image per j atom, chosen relative to the octet's centre (valid while
+                // halfBox - cutoff exceeds the octet's half extent; the list build flags the rest)
+                pj.x -= bAx*Real<R>::rint((pj.x-(R) oc.x)*iAx);
+                pj.y -= bBy*Real<R>::rint((pj.y-(R) oc.y)*iBy);
+                pj.z -= bCz*Real<R>::rint((pj.z-(R) oc.z)*iCz);
+            }
+            St::st4(sb+lane*St::STRIDE, pj);
+        }
+        __syncwarp();
+        R fix = 0, fiy = 0, fiz = 0, fjx = 0, fjy = 0, fjz = 0;
+        R eCt = 0, eVt = 0, eC1 = 0, eV1 = 0;       // TWO: totals and the j-subset-1 parts
+        unsigned bandMask = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            t.eC[s] = t.eV[s] = 0;
+        const unsigned copyBase = sb+copyOff;
+        // ---- 8 steps of 32 pairs --------------------------------------------------------
+#pragma unroll STEP_UNROLL
+        for (int s = 0; s < 8; s++) {
+            const unsigned so = (kOff+s*St::STRIDE)&(7*St::STRIDE);
+            const unsigned ad = copyBase+so;
+            const unsigned slot = (copyOff+so)/St::STRIDE;
+            const vec4 q = St::ld4(ad);
+            const unsigned mj = ldSharedU32(sb+St::AUX+slot*8+4);
+            R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
+            if (PBC == PBC_SHIFT && perPair) {
+                dx -= bAx*Real<R>::rint(dx*iAx);
+                dy -= bBy*Real<R>::rint(dy*iBy);
+                dz -= bCz*Real<R>::rint(dz*iCz);
+            }
+            else if (PBC == PBC_PAIR_TRICLINIC) {
+                R m = Real<R>::rint(dz*iCz);
+                dx -= m*(R) boxd.cx; dy -= m*(R) boxd.cy; dz -= m*bCz;
+                m = Real<R>::rint(dy*iBy);
+                dx -= m*(R) boxd.bx; dy -= m*bBy;
+                m = Real<R>::rint(dx*iAx);
+                dx -= m*bAx;
+            }
+            const R r2 = dx*dx+dy*dy+dz*dz;
+            // the hot path takes the pairs safely inside the cutoff; those inside the band around it (about
+            // 1e-5 of all pairs) are only noted, and settled exactly after the eight steps (bandPairs)
+            const bool ok = !(mj&kBit);
+            bool in;
+            if (KIND != KIND_PLAIN) {
+                in = ok && r2 < myCutLo;
+                if (ok && !(r2 < myCutLo) && r2 < myCutHi)
+                    bandMask |= 1u<<s;
+            }
+            else
+                in = ok && iValid;
+            if (!BRANCHY || in) {
+                const vec4 prm = St::ld4(ad+St::PRM);
+                R fc, fv, ec, ev, invR2;
+                // masked lanes compute on r^2 = 1 (self pairs have r = 0, excluded neighbours overflow r^-12)
+                pairMath<R, KIND>(c, BRANCHY ? r2 : (in ? r2 : (R) 1), pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
+                R lc, lv;
+                if (NSUB == 1) {
+                    lc = t.lamC[0]; lv = t.lamV[0];
+                }
+                else if (TWO) {
+                    lc = fma(prm.z, dLamC, t.lamC[0]);
+                    lv = fma(prm.z, dLamV, t.lamV[0]);
+                }
+                else if (NSUB > 0) {
+                    lc = t.lamC[0]; lv = t.lamV[0];
+#pragma unroll
+                    for (int u = 1; u < NS; u++) {
+                        lc = prm.z == (R) u ? t.lamC[u] : lc;
+                        lv = prm.z == (R) u ? t.lamV[u] : lv;
+                    }
+                }
+                else {
+                    const int sl = sliceOf(subI, (int) prm.z);
+                    lc = (R) a.sp->lambdaC[sl]; lv = (R) a.sp->lambdaV[sl];
+                }
+                R f = (lv*fv+lc*fc)*invR2;
+                if (!BRANCHY) {
+                    f = in ? f : (R) 0;
+                    ec = in ? ec : (R) 0;
+                    ev = in ? ev : (R) 0;
+                }
+                fix += f*dx; fiy += f*dy; fiz += f*dz;
+                fjx -= f*dx; fjy -= f*dy; fjz -= f*dz;
+                if (ENERGY) {
+                    if (TWO) {
+                        eCt += ec; eVt += ev;
+                        eC1 = fma(prm.z, ec, eC1); eV1 = fma(prm.z, ev, eV1);
+                    }
+                    else if (NSUB > 0) {
+#pragma unroll
+                        for (int u = 0; u < NS; u++) {
+                            t.eC[u] += prm.z == (R) u ? ec : (R) 0;
+                            t.eV[u] += prm.z == (R) u ? ev : (R) 0;
+                        }
+                    }
+                    else {
+                        // many subsets: straight to the global table (rare configuration)
+                        double* table = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
+                        atomicAdd(&table[2*sliceOf(subI, (int) prm.z)], (double) ec);
+                        atomicAdd(&table[2*sliceOf(subI, (int) prm.z)+1], (double) ev);
+                    }
+                }
+                if (DUMP && in) {
+                    const int origJ = a.sortedAtom[(int) ldSharedU32(sb+St::AUX+slot*8)];
+                    unsigned long long idx = atomicAdd(a.pairDumpCount, 1ull);
+                    if ((long long) idx < a.pairDumpCapacity)
+                        a.pairDump[idx] = make_int2(min(origI, origJ), max(origI, origJ));
+                }
+            }
+            fjx = __shfl_sync(full, fjx, srcLane);
+            fjy = __shfl_sync(full, fjy, srcLane);
+            fjz = __shfl_sync(full, fjz, srcLane);
+        }
+        if (KIND != KIND_PLAIN && __any_sync(full, bandMask != 0u)) {
+            if (bandMask) {
+                DirectOut o;
+                o.posd = a.posd; o.sortedAtom = a.sortedAtom; o.sp = a.sp; o.forceSorted = a.forceSorted; o.paddedAtoms = a.paddedAtoms;
+                o.energyTable = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
+                o.pairDump = a.pairDump; o.pairDumpCount = a.pairDumpCount; o.pairDumpCapacity = a.pairDumpCapacity;
+                bandPairs<R, KIND, PBC, ENERGY, DUMP>(o, c, bandMask, lane, ki, origI, pi, si4, perPair ? 1 : 0, &sStage[buf][0]);
+            }
+        }
+        if (jCur >= 0) {
+            addFixed(&a.forceSorted[jCur], Real<R>::fixed(fjx));
+            addFixed(&a.forceSorted[a.paddedAtoms+jCur], Real<R>::fixed(fjy));
+            addFixed(&a.forceSorted[2*a.paddedAtoms+jCur], Real<R>::fixed(fjz));
+        }
+        Fx += fix; Fy += fiy; Fz += fiz;
+        if (ENERGY && TWO) {
+            t.EC[0] += eCt-eC1; t.EC[1] += eC1;
+            t.EV[0] += eVt-eV1; t.EV[1] += eV1;
+        }
+        else if (ENERGY && NSUB > 0) {
+#pragma unroll
+            for (int u = 0; u < NS; u++) {
+                t.EC[u] += t.eC[u];
+                t.EV[u] += t.eV[u];
+            }
+        }
+        jCur = jNext;
+        octCur = octNext1;
+    }
+    if (curO >= 0)
+        flushOctet();
     if (ENERGY && NSUB > 0) {
         double* table = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
 #pragma unroll

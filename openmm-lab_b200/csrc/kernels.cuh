@@ -19,7 +19,7 @@ struct SortArgs {
     int2* cellRange;        // [numCells] sorted range (first, end) of every cell, by LINEAR cell index
     float4 *posqLocal, *sparams;
     double4 *posqLocalD, *sparamsD;  // double-precision mode only (else null)
-    double* blockCenter;
+    float4* blockCenter;    // [numBlocks] centre of every block (exact in float, see k_blockBounds)
     float4* blockExt;
     float4 *octetCenter, *octetExt;  // [4*numBlocks] block-local centre / half extents of every octet
 };
@@ -32,15 +32,15 @@ struct ListArgs {
     const int* sortedAtom;
     const int* sortedPos;
     const float4* posqLocal;
-    const double* blockCenter;
+    const float4* blockCenter;
     const float4* blockExt;
     const float4 *octetCenter, *octetExt;
     const int* exclStart;   // CSR over ORIGINAL atom indices: partners of each atom (both directions)
     const int* exclList;
     int2* jList;
-    int4* workItems;
-    int* counters;          // [0] chunks allocated, [1] work items, [2] overflow flag, [3] next work item
-    int maxChunks, maxItems, itemChunks;
+    int* chunkOctet;        // [maxChunks] octet of every chunk (bit 30: per-pair periodic wrapping)
+    int* counters;          // [0] chunks allocated, [2] overflow flag
+    int maxChunks;
     const int2* cellRange;  // [numCells] sorted range of every cell, by linear cell index ((x*dimY+y)*dimZ+z)
     int cellDim[3];
     const double* extent;   // non-periodic methods: bounding box of all atoms (min[3], max[3])
@@ -48,6 +48,14 @@ struct ListArgs {
     int bitmapWords;        // ceil(numBlocks/32)
 };
 void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
+
+#ifndef DIRECT_CTAS_PER_SM
+#define DIRECT_CTAS_PER_SM 16       /* one-warp CTAs of the direct-space kernel resident per SM (register budget 65536/32/this) */
+#endif
+
+#ifndef DIRECT_UNROLL
+#define DIRECT_UNROLL 8
+#endif
 
 struct DirectArgs {
     DirectParams p;
@@ -60,11 +68,12 @@ struct DirectArgs {
     const float4* sparams;
     const double4* posqLocalD;     // double-precision mode only
     const double4* sparamsD;
-    const double* blockCenter;
+    const float4* blockCenter;
     const float4* octetCenter;
     const double* posd;
     const int2* jList;
-    const int4* workItems;
+    const int* chunkOctet;
+    int maxChunks;
     int* counters;
     long long* forceSorted;     // [3][paddedAtoms]
     int paddedAtoms;

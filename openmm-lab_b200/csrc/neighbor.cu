@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     const int I = O>>2, lastI = O*8+7, wFirst = I>>5;
     const float4 oc = a.octetCenter[O];
     const float3 oe = make_float3(ext.x, ext.y, ext.z);
-    const double cIx = a.blockCenter[3*I], cIy = a.blockCenter[3*I+1], cIz = a.blockCenter[3*I+2];
+    const float4 cI = a.blockCenter[I];
     const float cut2 = a.cutoff*a.cutoff;
     const BoxF box = a.sp->box;
     const int pbcMode = a.pbcMode;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     }
     else {
         const double margin = 1e-5;     // block-local float coordinates vs the double coordinates the cells were cut from
-        const double c[3] = {cIx+(double) oc.x, cIy+(double) oc.y, cIz+(double) oc.z};
+        const double c[3] = {(double) cI.x+(double) oc.x, (double) cI.y+(double) oc.y, (double) cI.z+(double) oc.z};
         const double half[3] = {(double) oe.x+a.cutoff+margin, (double) oe.y+a.cutoff+margin, (double) oe.z+a.cutoff+margin};
         int lo[3], n[3];
         float rel[3], cs[3];
@@ -228,23 +228,20 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
         const int total = running, n = (total+31)>>5;
         if (n == 0)
             return;
-        const int numItemsHere = (n+a.itemChunks-1)/a.itemChunks;
-        int c0g = 0, item0 = 0;
+        int c0g = 0;
         if (lane == 0) {
             c0g = atomicAdd(&a.counters[0], n);
-            item0 = atomicAdd(&a.counters[1], numItemsHere);
-            if (c0g+n > a.maxChunks || item0+numItemsHere > a.maxItems)
+            if (c0g+n > a.maxChunks)
                 a.counters[2] = 1;                      // overflow: the host grows the buffers and repeats
         }
         c0g = __shfl_sync(full, c0g, 0);
-        item0 = __shfl_sync(full, item0, 0);
-        if (c0g+n > a.maxChunks || item0+numItemsHere > a.maxItems) {
+        if (c0g+n > a.maxChunks) {
             dead = true;
             return;
         }
         int2* out = a.jList+(size_t) c0g*32;
-        for (int k = lane; k < numItemsHere; k += 32)
-            a.workItems[item0+k] = make_int4(O, c0g+k*a.itemChunks, min(a.itemChunks, n-k*a.itemChunks), wide);
+        for (int k = lane; k < n; k += 32)
+            a.chunkOctet[c0g+k] = O|(wide<<30);
         // own atoms first (lower triangle masked: every pair once), then the tail padding
         if (first && lane < 8)
             out[lane] = atomI >= 0 ? make_int2(ki, (int) ((0xffu<<lane)&0xffu)) : make_int2(-1, 0xff);
@@ -291,11 +288,11 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     };
 
     // the interaction flags of one candidate block: 32 atoms against the octet's box
-    auto testBlock = [&](int J, const float4& pj, double bx, double by, double bz) -> unsigned {
+    auto testBlock = [&](int J, const float4& pj, const float4& cJ) -> unsigned {
         const int j = J*32+lane;
         bool acc = J >= 0 && j < a.numAtoms && j > lastI;
         if (a.useCutoff && acc) {
-            const float px = pj.x+(float) (bx-cIx)-oc.x, py = pj.y+(float) (by-cIy)-oc.y, pz = pj.z+(float) (bz-cIz)-oc.z;
+            const float px = pj.x+(cJ.x-cI.x)-oc.x, py = pj.y+(cJ.y-cI.y)-oc.y, pz = pj.z+(cJ.z-cI.z)-oc.z;
             acc = imageDist2(px, py, pz, oe, pbcMode, box) < cut2;
         }
         return __ballot_sync(full, acc);
@@ -325,21 +322,19 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
         for (int k0 = 0; k0 < nc && !dead; k0 += 4) {
             // four candidates in flight: their loads are issued before the first test
             int J[4];
-            float4 pj[4];
-            double bc[4][3];
+            float4 pj[4], bc[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 J[u] = k0+u < nc ? Jbase+cand[k0+u] : -1;
-                pj[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                bc[u][0] = bc[u][1] = bc[u][2] = 0.0;
+                pj[u] = bc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (J[u] >= 0 && a.useCutoff) {
                     pj[u] = a.posqLocal[J[u]*32+lane];
-                    bc[u][0] = a.blockCenter[3*J[u]]; bc[u][1] = a.blockCenter[3*J[u]+1]; bc[u][2] = a.blockCenter[3*J[u]+2];
+                    bc[u] = a.blockCenter[J[u]];
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const unsigned word = testBlock(J[u], pj[u], bc[u][0], bc[u][1], bc[u][2]);
+                const unsigned word = testBlock(J[u], pj[u], bc[u]);
                 if (word && !dead) {
                     if (lane == 0) {
                         hitJ[nh] = J[u];

@@ -8,9 +8,9 @@
 //   sortedPos  int[N]        inverse permutation
 //   posqLocal float4[NP]     (x,y,z relative to the block centre, q)           sorted order
 //   sparams   float4[NP]     (sigma/2, 2 sqrt(eps), bitcast subset, c6)        sorted order
-//   blockCenter double[NB][3], blockExt float4[NB] (half extents)
+//   blockCenter float4[NB] (2^-10 nm lattice: exact in float), blockExt float4[NB] (half extents)
 //   jList     int2[cap]      (sorted j, exclusion mask over the 32 i lanes), 32 entries per chunk
-//   workItems int4[cap]      (i-block, first chunk, number of chunks, unused)
+//   chunkOctet int[cap]      octet (8 i atoms) of every chunk; bit 30: per-pair periodic wrapping
 //   forceSorted / forceOrig  long long[3][NP]  2^32 fixed point
 //   energyBuf double[numSlices][2] (+ counters)
 #ifndef SNB_CORE_CUH_
@@ -27,7 +27,6 @@
 #define SNB_BLOCK 32
 #define SNB_FORCE_SCALE 4294967296.0f       /* 2^32, as the reference's fixed-point forces (realToFixedPoint.cu:1-2) */
 #define SNB_FORCE_SCALE_D 4294967296.0
-#define SNB_ITEM_CHUNKS 8                   /* most chunks of 32 j atoms per work item */
 
 enum { PBC_NONE = 0, PBC_SHIFT = 1, PBC_PAIR_ORTHO = 2, PBC_PAIR_TRICLINIC = 3 };
 enum { KIND_PLAIN = 0, KIND_RF = 1, KIND_EWALD = 2, KIND_LJPME = 3 };

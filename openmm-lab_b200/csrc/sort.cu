@@ -173,9 +173,12 @@ __global__ void k_blockBounds(SortArgs a) {
             hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
         }
     }
+    // the centre is snapped to a 2^-10 nm lattice and rounded to float: every centre, and every difference of
+    // two centres (up to 8 um apart), is then EXACT in single precision, so the kernels shift a j atom into
+    // an i block's frame with float arithmetic and lose nothing
     double c[3];
     for (int d = 0; d < 3; d++)
-        c[d] = 0.5*(lo[d]+hi[d]);
+        c[d] = (double) (float) (rint(0.5*(lo[d]+hi[d])*1024.0)*(1.0/1024.0));
     float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
     if (atom >= 0)
         pl = make_float4((float) (p[0]-c[0]), (float) (p[1]-c[1]), (float) (p[2]-c[2]), prm.x*a.sqrtK);
@@ -195,7 +198,7 @@ __global__ void k_blockBounds(SortArgs a) {
         a.sparamsD[k] = sd;
     }
     if (lane == 0) {
-        a.blockCenter[3*warp] = c[0]; a.blockCenter[3*warp+1] = c[1]; a.blockCenter[3*warp+2] = c[2];
+        a.blockCenter[warp] = make_float4((float) c[0], (float) c[1], (float) c[2], 0.f);
         // half extents, rounded up so the box is conservative in single precision
         a.blockExt[warp] = make_float4(__double2float_ru(0.5*(hi[0]-lo[0])), __double2float_ru(0.5*(hi[1]-lo[1])),
                                        __double2float_ru(0.5*(hi[2]-lo[2])), 0.f);
