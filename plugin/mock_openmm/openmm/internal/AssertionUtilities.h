@@ -1,0 +1,6 @@
+/* STAND-IN for openmm/internal/AssertionUtilities.h (compile check only). */
+#ifndef MOCK_OPENMM_ASSERTIONUTILITIES_H_
+#define MOCK_OPENMM_ASSERTIONUTILITIES_H_
+#include <string>
+namespace OpenMM { void throwException(const char* file, int line, const std::string& details); }
+#endif

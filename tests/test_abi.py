@@ -1,0 +1,78 @@
+"""The drop-in boundary on CPU: the C-ABI library loads without a GPU and exports every entry point
+include/slicednb.h declares (no compute calls here), host-only entry points behave, and the C++ OpenMM
+plugin adapter (plugin/) compiles against the reference's own headers where they are available."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "slicednb.h")
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(snb_[a-z0-9_]+)\s*\(", text)
+    return sorted(set(n for n in names if n != "snb_slice_index"))      # static inline helper, not exported
+
+
+def test_library_exports_every_declared_symbol():
+    import openmmlab_b200 as mm
+    lib = mm.load_library()
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "%s is declared in include/slicednb.h but not exported" % n
+
+
+def test_oracle_exports_the_same_kernel_interface():
+    from oracle import oracle_kernel
+    oracle_kernel.build()
+    lib = C.CDLL(oracle_kernel.PORT_LIB)
+    for n in ("create", "destroy", "execute", "update_parameters", "get_pme_parameters", "get_ljpme_parameters", "last_error"):
+        assert hasattr(lib, "snb_oracle_"+n)
+
+
+def test_host_only_entry_points():
+    import openmmlab_b200 as mm
+    lib = mm.load_library()
+    lib.snb_version.restype = C.c_char_p
+    assert b"sm_100a" in lib.snb_version()
+    lib.snb_last_error.restype = C.c_char_p
+    assert isinstance(lib.snb_last_error(), bytes)
+    # a descriptor of the wrong size is refused before any CUDA call
+    desc = mm._abi.SnbDesc()
+    desc.struct_size = 8
+    handle = C.c_void_p()
+    lib.snb_create.argtypes = [C.POINTER(mm._abi.SnbDesc), C.POINTER(C.c_void_p)]
+    assert lib.snb_create(C.byref(desc), C.byref(handle)) == mm._abi.ERR_INVALID
+    assert b"struct_size" in lib.snb_last_error()
+
+
+def test_descriptor_layout_matches_header():
+    # the ctypes mirror and the C struct must agree on the size (the library checks struct_size at run time)
+    import openmmlab_b200 as mm
+    src = '#include "slicednb.h"\n#include <stdio.h>\nint main(void) { printf("%zu", sizeof(snb_desc)); return 0; }\n'
+    exe = os.path.join(ROOT, "tests", ".sizeof_desc")
+    out = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-x", "c", "-", "-o", exe], input=src, text=True, capture_output=True)
+    assert out.returncode == 0, out.stderr
+    try:
+        size = int(subprocess.run([exe], capture_output=True, text=True).stdout)
+    finally:
+        os.remove(exe)
+    assert size == C.sizeof(mm._abi.SnbDesc)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/openmmapi/include"), reason="the reference's headers are not on this machine")
+def test_openmm_plugin_adapter_compiles_against_reference_headers():
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "plugin"), "-B", "check"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout+out.stderr
+    obj = os.path.join(ROOT, "plugin", "build", "B200OpenMMLabKernels.check.o")
+    syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    for needed in ("registerKernelFactories", "registerPlatforms", "B200CalcSlicedNonbondedForceKernel::execute",
+                   "B200CalcSlicedNonbondedForceKernel::initialize", "B200CalcSlicedNonbondedForceKernel::copyParametersToContext",
+                   "B200OpenMMLabKernelFactory::createKernelImpl"):
+        assert needed in syms
