@@ -165,7 +165,10 @@ struct GraphKey {
     const void *posqDev, *forcesFixedOut, *jList;
 };
 
-#define SNB_ENERGY_DOUBLES (32*2*SNB_MAX_SLICES+8)   /* 32 replicas of [slice][term] + flags ([0] = list overflow) */
+#define SNB_ENERGY_FLAGS 32
+#define SNB_ENERGY_DOUBLES (32*2*SNB_MAX_SLICES+SNB_ENERGY_FLAGS)   /* 32 replicas of [slice][term] + flags: [0] list overflow,
+                                                                      [1] rank 0's reciprocal-space ms, [2+r] rank r's list+direct ms,
+                                                                      [10+r] rank r's ms until its forces were ready (r < 8) */
 
 struct snb_handle {
     // ---- snapshot of the force (ReferenceOpenMMLabKernels.cpp:65-191) ----
@@ -223,6 +226,10 @@ struct snb_handle {
     double rank0Share = -1;             // < 0: cost-model default
     DevBuf<long long> reduceSend, reduceRecv;
     DevBuf<double> energyRecv;
+    cudaEvent_t evDirBegin = nullptr, evDirEnd = nullptr, evRecBegin = nullptr, evRecEnd = nullptr, evReady = nullptr;
+    PinnedBuf<double> loadH;            // this rank's measured times of the previous evaluation, sent with the all-reduce
+    bool loadValid = false, autoBalance = true;
+    double tunedShare = -1;
     // ---- results of the last execute ----
     std::vector<double> sliceEnergies;
     double lastEnergy = 0;
@@ -644,8 +651,9 @@ double rank0Share(const snb_handle& h) {
     if (h.world <= 1) return 1.0;
     if (h.rank0Share >= 0) return h.rank0Share;
     if (const char* env = getenv("SNB_RANK0_SHARE")) return std::max(0.0, atof(env));
+    if (h.tunedShare >= 0) return h.tunedShare;         // measured (runOnce): same value on every rank
     if (h.method != SNB_PME && h.method != SNB_LJPME) return 1.0;
-    const double rho = h.method == SNB_LJPME ? 1.2 : 0.7;
+    const double rho = h.method == SNB_LJPME ? 0.8 : 0.4;
     const double f0 = std::max(0.0, (1.0-(h.world-1)*rho)/h.world);
     return f0*(h.world-1)/(1.0-f0);
 }
@@ -803,9 +811,12 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     const bool doRecip = includeRecip && pmeFamily && h.rank == 0;
     if (doRecip && !h.timing) {
         CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.evSorted, 0));
+        if (nccl) CUDA_CHECK(cudaEventRecord(h.evRecBegin, h.pmeStream));
         reciprocal(h.pmeStream);
+        if (nccl) CUDA_CHECK(cudaEventRecord(h.evRecEnd, h.pmeStream));
         CUDA_CHECK(cudaEventRecord(h.evPmeDone, h.pmeStream));
     }
+    if (nccl && includeDirect) CUDA_CHECK(cudaEventRecord(h.evDirBegin, st));
 
     if (includeDirect) {
         ListArgs la;
@@ -851,6 +862,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.chunkOctet = h.chunkOctet.p; da.maxChunks = (int) h.maxChunks;
         da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
         launchDirect(da, st, h.numSMs);
+        if (nccl) CUDA_CHECK(cudaEventRecord(h.evDirEnd, st));
         tm.mark(3);
         if (h.X > 0 && !bondedForked)
             bonded(st);
@@ -870,6 +882,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
 
     // ---- outputs ----
+    if (nccl) CUDA_CHECK(cudaEventRecord(h.evReady, st));
     if (includeForces || nccl) {
         FinishArgs fa;
         memset(&fa, 0, sizeof(fa));
@@ -899,7 +912,10 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     tm.mark(9);
     const double* energySrc = h.energyBuf.p;
     if (nccl) {
-        // slice energies of all ranks (and the list-overflow flags: every rank must take the same retry decision)
+        // slice energies of all ranks, the list-overflow flags (every rank must take the same retry decision) and the
+        // times every rank measured in its PREVIOUS evaluation (every rank then derives the same new partition)
+        if (h.loadValid)
+            CUDA_CHECK(cudaMemcpyAsync(h.energyBuf.p+32*2*SNB_MAX_SLICES+1, h.loadH.p+1, sizeof(double)*(SNB_ENERGY_FLAGS-1), cudaMemcpyHostToDevice, st));
         NCCL_CHECK(nccl, nccl->AllReduce(h.energyBuf.p, h.energyRecv.p, SNB_ENERGY_DOUBLES, ncclFloat64, ncclSum, h.comm, st));
         energySrc = h.energyRecv.p;
     }
@@ -986,6 +1002,29 @@ bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, v
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventElapsedTime(&h.lastDeviceMs, h.evBegin, h.evEnd));
     h.listValid = includeDirect;
+    if (h.comm && includeDirect && !h.timing) {
+        // load balance: what was measured one evaluation ago has just come back from the all-reduce, identical on every rank
+        const double* got = h.hEnergy.p+32*2*SNB_MAX_SLICES;
+        const int W = h.world;
+        double D = 0, others = 0;
+        for (int r = 0; r < W && r < 8; r++) D += got[2+r];
+        for (int r = 1; r < W && r < 8; r++) others += got[10+r]/(W-1);
+        const double t0 = got[10];
+        if (h.autoBalance && h.rank0Share < 0 && D > 0 && t0 > 0 && W <= 8 && getenv("SNB_RANK0_SHARE") == nullptr) {
+            // Newton step on t_others(f0) - t_0(f0) = 0 with dt_0/df0 = D, dt_others/df0 = -D/(W-1); D = summed direct-phase time
+            const double cur = rank0Share(h), f0 = cur/(cur+(W-1));
+            const double f0new = std::min(1.0/W, std::max(0.0, f0+0.7*(others-t0)*(W-1)/(W*D)));
+            h.tunedShare = f0new*(W-1)/(1.0-f0new);
+        }
+        // this evaluation's own times, for the next all-reduce
+        float ms = 0;
+        for (int k = 0; k < SNB_ENERGY_FLAGS; k++) h.loadH.p[k] = 0.0;
+        if (h.rank < 8 && cudaEventElapsedTime(&ms, h.evDirBegin, h.evDirEnd) == cudaSuccess) h.loadH.p[2+h.rank] = ms;
+        if (h.rank < 8 && cudaEventElapsedTime(&ms, h.evBegin, h.evReady) == cudaSuccess) h.loadH.p[10+h.rank] = ms;
+        if (h.rank == 0 && (flags&SNB_INCLUDE_RECIPROCAL) && pmeFamily && cudaEventElapsedTime(&ms, h.evRecBegin, h.evRecEnd) == cudaSuccess) h.loadH.p[1] = ms;
+        h.loadValid = true;
+        cudaGetLastError();     // an unrecorded event above must not poison the next evaluation's error check
+    }
     if (includeDirect) {
         const bool anyOverflow = h.comm ? h.hEnergy.p[32*2*SNB_MAX_SLICES] != 0.0 : h.hCounters.p[2] != 0;
         if (h.hCounters.p[2]) {
@@ -1103,6 +1142,8 @@ void snb_destroy(snb_handle* h) {
     if (h->evCreated)
         for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->graphExec) cudaGraphExecDestroy(h->graphExec);
+    for (cudaEvent_t e : {h->evDirBegin, h->evDirEnd, h->evRecBegin, h->evRecEnd, h->evReady})
+        if (e) cudaEventDestroy(e);
     if (h->evInputs) cudaEventDestroy(h->evInputs);
     if (h->evBondedDone) cudaEventDestroy(h->evBondedDone);
     if (h->bondedStream) cudaStreamDestroy(h->bondedStream);
@@ -1297,6 +1338,13 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size) {
     h->world = world_size;
     h->reduceSend.alloc(3*(size_t) h->N);
     h->reduceRecv.alloc(3*(size_t) h->N);
+    h->loadH.alloc(SNB_ENERGY_FLAGS);
+    if (!h->evDirBegin) {
+        CUDA_CHECK(cudaEventCreate(&h->evDirBegin)); CUDA_CHECK(cudaEventCreate(&h->evDirEnd));
+        CUDA_CHECK(cudaEventCreate(&h->evRecBegin)); CUDA_CHECK(cudaEventCreate(&h->evRecEnd));
+        CUDA_CHECK(cudaEventCreate(&h->evReady));
+    }
+    h->loadValid = false; h->tunedShare = -1;
     h->energyRecv.alloc(SNB_ENERGY_DOUBLES);
     return SNB_OK;
     SNB_CATCH

@@ -16,9 +16,9 @@
 //   * the pair arithmetic is branch-free in single precision: out-of-range / excluded lanes compute on a
 //     harmless r^2 and are masked out by selects (nearly every step has some lane in range, so a branch
 //     saves no issue slots and only blocks the scheduler from overlapping the steps).
-// Pair arithmetic is FP32 (MUFU rsqrt + Newton step, MUFU ex2, polynomial erfc); i forces are carried
-// in FP64 across chunks; all forces leave as 2^32 fixed-point 64-bit atomics (order independent =>
-// bit-reproducible); slice energies are accumulated per j subset in FP32 per chunk and FP64 beyond.
+// Pair arithmetic is FP32 (MUFU rsqrt + Newton step, MUFU ex2, polynomial erfc); every chunk's force
+// sums are converted to 2^32 fixed point and all further accumulation is in 64-bit integers (order and
+// partition independent => bit-reproducible, also across GPUs); slice energies are accumulated per j subset in FP32 per chunk and FP64 beyond.
 //
 // Pair arithmetic follows the reference's Reference platform:
 //   Ewald/PME/LJPME direct:  platforms/reference/src/ReferenceSlicedLJCoulombIxn.cpp:351-429
@@ -324,7 +324,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
         t.lamC[s] = t.lamV[s] = 0;
         t.EC[s] = t.EV[s] = 0.0;
     }
-    double Fx = 0, Fy = 0, Fz = 0;
+    // i forces: every chunk's FP32 partial sum is converted to 2^32 fixed point before it is added, so the
+    // total does not depend on how the chunks are grouped into warps, GPUs or octet runs (integer sums)
+    long long Fx = 0, Fy = 0, Fz = 0;
     auto flushOctet = [&]() {
         // the four copies of the octet: sum their i forces onto copy 0
         for (int o = 8; o < 32; o <<= 1) {
@@ -333,9 +335,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             Fz += __shfl_xor_sync(full, Fz, o);
         }
         if (iValid && copy == 0) {
-            addFixed(&a.forceSorted[ki], toFixedD(Fx));
-            addFixed(&a.forceSorted[a.paddedAtoms+ki], toFixedD(Fy));
-            addFixed(&a.forceSorted[2*a.paddedAtoms+ki], toFixedD(Fz));
+            addFixed(&a.forceSorted[ki], Fx);
+            addFixed(&a.forceSorted[a.paddedAtoms+ki], Fy);
+            addFixed(&a.forceSorted[2*a.paddedAtoms+ki], Fz);
         }
         if (ENERGY && NSUB > 0 && iValid) {
 #pragma unroll
@@ -538,7 +540,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             addFixed(&a.forceSorted[a.paddedAtoms+jCur], Real<R>::fixed(fjy));
             addFixed(&a.forceSorted[2*a.paddedAtoms+jCur], Real<R>::fixed(fjz));
         }
-        Fx += fix; Fy += fiy; Fz += fiz;
+        Fx += Real<R>::fixed(fix); Fy += Real<R>::fixed(fiy); Fz += Real<R>::fixed(fiz);
         if (ENERGY && TWO) {
             t.EC[0] += eCt-eC1; t.EC[1] += eC1;
             t.EV[0] += eVt-eV1; t.EV[1] += eV1;

@@ -640,6 +640,12 @@ int snb_oracle_dump_pairs(void* h, int32_t** pairs, int64_t* count) {
     return dumpPairs(o.neighbors, pairs, count);
 }
 
+/* number of pairs in the neighbour list of the last execute (full-size checks: no copy, no sort) */
+long long snb_oracle_count_pairs(void* h) {
+    Oracle& o = *(Oracle*) h;
+    return o.neighborsValid ? (long long) o.neighbors.size() : -1;
+}
+
 /* O(N^2) enumeration, to validate the cell-list search itself */
 int snb_oracle_brute_pairs(void* h, const double* positions, const double* box, int32_t** pairs, int64_t* count) {
     Oracle& o = *(Oracle*) h;

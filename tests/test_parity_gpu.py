@@ -200,3 +200,9 @@ def test_graph_replay_follows_positions_box_and_lambdas():
         assert abs(ref["energy"]-got["energy"]) <= 1e-5*max(abs(ref["energy"]), np.abs(ref["slices"]).sum())
         assert np.abs(ref["forces"]-got["forces"]).max() <= 1e-4*np.sqrt((ref["forces"]**2).sum(axis=1).mean())
     assert replays >= 6, "the CUDA-graph path was not exercised (%d replays)" % replays
+
+
+def test_apoa1_size():
+    # BASELINE.json configs[2]: 92,224 atoms, 4 subsets / 10 slices, three scaling parameters with derivatives.
+    # Oracle: direct and reciprocal space separately and together; Precision=double at 1e-5, mixed by its criteria.
+    _check(systems.apoa1_like(), energy_tol=1e-5)
