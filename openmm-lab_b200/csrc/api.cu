@@ -46,13 +46,18 @@ struct SnbException : public std::exception {
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owner = true;
+    void view(void* ptr, size_t count) {     // a window into another allocation
+        release();
+        p = (T*) ptr; n = count; owner = false;
+    }
     void alloc(size_t count) {
         if (count <= n && p) return;
         release();
         CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1)*sizeof(T)));
         n = std::max<size_t>(count, 1);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && owner) cudaFree(p); p = nullptr; n = 0; owner = true; }
     void upload(const T* src, size_t count, cudaStream_t s) {
         alloc(count);
         if (count) CUDA_CHECK(cudaMemcpyAsync(p, src, count*sizeof(T), cudaMemcpyHostToDevice, s));
@@ -162,7 +167,7 @@ struct PmeGrid {
 struct GraphKey {
     int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy;
     size_t maxChunks;
-    const void *posqDev, *forcesFixedOut, *jList;
+    const void *posqDev, *forcesFixedOut, *jList, *hostPos;
 };
 
 #define SNB_ENERGY_FLAGS 32
@@ -212,10 +217,12 @@ struct snb_handle {
     DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt, blockCenter;
     DevBuf<double4> posqLocalD, sparamsD;
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
-                exclStart, exclList, is14D, counters, cellScratch;
+                exclStart, exclList, is14D, counters, cellScratch, tileSum;
     DevBuf<int2> exceptionAtomsD, jList, cellRange;
     DevBuf<int> chunkOctet;
     DevBuf<long long> forceSorted, forceOrig;
+    DevBuf<char> zeroBlock;
+    size_t zeroBytes = 0;
     PinnedBuf<double> hPos, hForces, hEnergy;
     PinnedBuf<int> hCounters;
     size_t maxChunks = 0;
@@ -475,9 +482,17 @@ snb_handle* createHandle(const snb_desc& d) {
         h.blockCenter.alloc(h.NB); h.blockExt.alloc(h.NB);
         h.octetCenter.alloc(4*(size_t) h.NB); h.octetExt.alloc(4*(size_t) h.NB);
         h.extent.alloc(6);
-        h.energyBuf.alloc(SNB_ENERGY_DOUBLES);    // 32 replicas of the slice-energy table (direct.cu), summed on the host, + flags
-        h.counters.alloc(8);
-        h.forceSorted.alloc(3*(size_t) h.NP); h.forceOrig.alloc(3*(size_t) h.NP);
+        // everything an evaluation must find zeroed lives in ONE allocation, cleared by one memset: the two
+        // fixed-point force accumulators, the slice-energy table (32 replicas, summed on the host, + flags), the counters
+        {
+            const size_t f = 3*(size_t) h.NP*sizeof(long long), e = SNB_ENERGY_DOUBLES*sizeof(double);
+            h.zeroBytes = 2*f+e+8*sizeof(int);
+            h.zeroBlock.alloc(h.zeroBytes);
+            h.forceSorted.view(h.zeroBlock.p, 3*(size_t) h.NP);
+            h.forceOrig.view(h.zeroBlock.p+f, 3*(size_t) h.NP);
+            h.energyBuf.view(h.zeroBlock.p+2*f, SNB_ENERGY_DOUBLES);
+            h.counters.view(h.zeroBlock.p+2*f+e, 8);
+        }
         h.forcesOutD.alloc(3*(size_t) h.N);
         h.hPos.alloc(3*(size_t) h.N); h.hForces.alloc(3*(size_t) h.N);
         h.hEnergy.alloc(SNB_ENERGY_DOUBLES);
@@ -611,8 +626,11 @@ void setupCells(snb_handle& h, const double* box, bool periodic) {
     h.cellRank.upload(rank.data(), rank.size(), h.stream);
     CUDA_CHECK(cudaStreamSynchronize(h.stream));
     h.cellCount.alloc(h.numCells);
+    CUDA_CHECK(cudaMemsetAsync(h.cellCount.p, 0, sizeof(int)*h.numCells, h.stream));    // k_scatterAtoms re-zeroes it after every use
+    CUDA_CHECK(cudaStreamSynchronize(h.stream));
     h.cellStart.alloc(h.numCells+1);
     h.cellRange.alloc(h.numCells);
+    h.tileSum.alloc(h.numCells/1024+2);
 }
 
 void ensureListCapacity(snb_handle& h, const double* box, bool periodic) {
@@ -659,7 +677,8 @@ double rank0Share(const snb_handle& h) {
 }
 
 struct StepInputs {
-    const void* posqDev;        // device float4 positions, or null when the positions come from hPos
+    const double* hostPos;      // host positions to copy from: the caller's own buffer when it is page-locked, else the pinned mirror
+    const void* posqDev;        // device float4 positions, or null when the positions come from the host
     void* forcesFixedOut;
     int flags;
     bool hostPositions;
@@ -732,16 +751,13 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
 
     // ---- inputs ----
     if (in.hostPositions)
-        CUDA_CHECK(cudaMemcpyAsync(h.posd.p, h.hPos.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(h.posd.p, in.hostPos, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
     else
         launchConvertPositions((const float4*) in.posqDev, h.posd.p, h.N, st);
     if (nccl)   // rank 0's positions are authoritative: every rank then builds the identical sorted order
         NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, st));
     CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemsetAsync(h.forceSorted.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
-    CUDA_CHECK(cudaMemsetAsync(h.forceOrig.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
-    CUDA_CHECK(cudaMemsetAsync(h.energyBuf.p, 0, sizeof(double)*SNB_ENERGY_DOUBLES, st));
-    CUDA_CHECK(cudaMemsetAsync(h.counters.p, 0, sizeof(int)*8, st));
+    CUDA_CHECK(cudaMemsetAsync(h.zeroBlock.p, 0, h.zeroBytes, st));
     tm.mark(0);
 
     // ---- exceptions / exclusion corrections: need the inputs only, so they run beside the sort ----
@@ -780,7 +796,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         sa.sp = h.stepD.p;
         sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.paramsD = h.paramsD.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
         sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
-        sa.cellRange = h.cellRange.p; sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
+        sa.cellRange = h.cellRange.p; sa.tileSum = h.tileSum.p; sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
         launchSort(sa, st);
@@ -832,9 +848,9 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         la.maxChunks = (int) h.maxChunks;
         la.cellRange = h.cellRange.p; la.extent = h.extent.p;
         for (int k = 0; k < 3; k++) la.cellDim[k] = h.cellDim[k];
-        int64_t lo = 0, hi = 4*(int64_t) h.NB;
-        partitionRange(4*(int64_t) h.NB, h.world, h.rank, rank0Share(h), &lo, &hi);
-        la.octLo = (int) lo; la.octHi = (int) hi;
+        int64_t lo = 0, hi = h.NB;
+        partitionRange(h.NB, h.world, h.rank, rank0Share(h), &lo, &hi);
+        la.blockLo = (int) lo; la.blockHi = (int) hi;
         la.bitmapWords = (h.NB+31)/32;
         launchBuildList(la, st, h.numSMs);
         tm.mark(2);
@@ -931,13 +947,13 @@ void dropGraph(snb_handle& h) {
 }
 
 // One evaluation.  Returns false when a device-side capacity check asks for a repeat (buffers were grown).
-bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, void* forcesFixedOut) {
+bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos, const void* posqDev, void* forcesFixedOut) {
     const bool includeDirect = flags&SNB_INCLUDE_DIRECT, includeRecip = flags&SNB_INCLUDE_RECIPROCAL, includeForces = flags&SNB_INCLUDE_FORCES;
     const bool periodic = h.method >= SNB_CUTOFF_PERIODIC;
     const bool pmeFamily = h.method == SNB_PME || h.method == SNB_LJPME;
     cudaStream_t st = h.stream;
     StepInputs in;
-    in.posqDev = posqDev; in.forcesFixedOut = forcesFixedOut; in.flags = flags; in.hostPositions = posqDev == nullptr;
+    in.hostPos = hostPos; in.posqDev = posqDev; in.forcesFixedOut = forcesFixedOut; in.flags = flags; in.hostPositions = posqDev == nullptr;
     in.pbcMode = prepareStep(h, box, periodic);
 
     // reciprocal-space kernel table: rebuilt only when the box changes (outside the graph, same stream)
@@ -962,7 +978,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, v
     key.numCells = h.numCells;
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     key.maxChunks = h.maxChunks;
-    key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p;
+    key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p; key.hostPos = hostPos;
     const bool graphable = h.useGraph && !h.timing && !h.comm;
     const bool sameKey = h.graphKeyValid && memcmp(&key, &h.graphKey, sizeof(key)) == 0;
     if (!graphable || !sameKey)
@@ -1045,7 +1061,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const void* posqDev, v
     h.countersOut[4] = h.graphExec ? 1 : 0;
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
-    if (includeDirect) launches += (periodic ? 5 : 6)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
+    if (includeDirect) launches += (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
     if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 5 : 4)*(h.method == SNB_LJPME ? 2 : 1);    // spread (+finish), convolution, combine, interpolate
     if (includeForces || h.comm) launches += 1+(h.comm && h.rank == 0 ? 1 : 0);
     if (posqDev) launches += 1;
@@ -1097,12 +1113,22 @@ void evaluate(snb_handle& h, const double* positions, const void* posqDev, const
         h.lastEnergy = 0;
         return;
     }
-    if (positions)
-        memcpy(h.hPos.p, positions, sizeof(double)*3*(size_t) h.N);
+    const double* hostPos = nullptr;
+    if (positions) {
+        // a page-locked caller buffer is read by the copy engine directly; anything else is staged through the pinned mirror
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, positions) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+            hostPos = positions;
+        else {
+            cudaGetLastError();
+            memcpy(h.hPos.p, positions, sizeof(double)*3*(size_t) h.N);
+            hostPos = h.hPos.p;
+        }
+    }
     double unitBox[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const double* b = periodic ? box : unitBox;
     for (int attempt = 0; attempt < 4; attempt++)
-        if (runOnce(h, b, flags, positions ? nullptr : posqDev, forcesFixedOut)) {
+        if (runOnce(h, b, flags, hostPos, positions ? nullptr : posqDev, forcesFixedOut)) {
             finishEnergies(h, b, flags);
             h.lastFlags = flags;
             return;

@@ -26,6 +26,8 @@
 // (behavioural cross-reference on the GPU side: platforms/common/src/kernels/coulombLennardJones.cc:1-124).
 #include "kernels.cuh"
 
+#include <type_traits>
+
 #define ENERGY_REPLICAS 32      /* copies of the slice-energy table, to spread the final atomics */
 
 template <int KIND> void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid);
@@ -140,7 +142,7 @@ __device__ __forceinline__ void stSharedV2U32(unsigned ad, unsigned x, unsigned 
 
 // ---- one pair: Coulomb and van der Waals terms as (energy, dE/dr * r); the common 1/r^2 of the force is
 // returned separately and applied once, to the lambda-weighted sum.
-template <typename R, int KIND>
+template <typename R, int KIND, bool SWITCH>
 __device__ __forceinline__ void pairMath(const DirectConsts<R>& c, R r2, R qq, R sigI, R epsI, R c6I, R sigJ, R epsJ, R c6J,
                                          R& fc, R& fv, R& ec, R& ev, R& invR2) {
     const R invR = Real<R>::rsqrt(r2);
@@ -180,14 +182,13 @@ __device__ __forceinline__ void pairMath(const DirectConsts<R>& c, R r2, R qq, R
         const R sc6 = sc2*sc2*sc2*c.invCut6;
         ev += eps*(1-sc6)*sc6-c6*c.invCut6*c.dispShiftExp;
     }
-    if (KIND != KIND_PLAIN && KIND != KIND_LJPME) {
-        if (r > c.switchDist) {             // +inf when the switching function is off
-            const R x = (r-c.switchDist)*c.invSwitchWidth;
-            const R sw = 1+x*x*x*(-10+x*(15-x*6));
-            const R dsw = x*x*(-30+x*(60-x*30))*c.invSwitchWidth;
-            fv = sw*fv-ev*dsw*r;
-            ev *= sw;
-        }
+    if (SWITCH) {
+        // branch-free: below the switching distance x = 0, hence sw = 1 and dsw = 0
+        const R x = max((R) 0, (r-c.switchDist)*c.invSwitchWidth);
+        const R sw = 1+x*x*x*(-10+x*(15-x*6));
+        const R dsw = x*x*(-30+x*(60-x*30))*c.invSwitchWidth;
+        fv = sw*fv-ev*dsw*r;
+        ev *= sw;
     }
 }
 
@@ -207,7 +208,7 @@ struct DirectOut {
 
 // The pairs of one chunk that fell inside the band around the cutoff (about 1e-5 of all pairs): decided
 // exactly, then evaluated here and added with atomics, so that the pair loop itself carries no call.
-template <typename R, int KIND, int PBC, bool ENERGY, bool DUMP>
+template <typename R, int KIND, int PBC, bool ENERGY, bool DUMP, bool SWITCH>
 static __device__ __noinline__ void bandPairs(DirectOut o, DirectConsts<R> c, unsigned bandMask, int lane, int ki, int origI,
                                               typename Real<R>::vec4 pi, typename Real<R>::vec4 si4, int perPair, const unsigned char* stage) {
     typedef typename Real<R>::vec4 vec4;
@@ -239,7 +240,7 @@ static __device__ __noinline__ void bandPairs(DirectOut o, DirectConsts<R> c, un
         }
         const R r2 = dx*dx+dy*dy+dz*dz;
         R fc, fv, ec, ev, invR2;
-        pairMath<R, KIND>(c, r2, pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
+        pairMath<R, KIND, SWITCH>(c, r2, pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
         const int slice = sliceOf((int) si4.z, (int) prm.z);
         const R f = ((R) o.sp->lambdaV[slice]*fv+(R) o.sp->lambdaC[slice]*fc)*invR2;
         const long long fx = Real<R>::fixed(f*dx), fy = Real<R>::fixed(f*dy), fz = Real<R>::fixed(f*dz);
@@ -257,7 +258,7 @@ static __device__ __noinline__ void bandPairs(DirectOut o, DirectConsts<R> c, un
     }
 }
 
-template <typename R, int KIND, int PBC, int NSUB, bool ENERGY, bool DUMP>
+template <typename R, int KIND, int PBC, int NSUB, bool ENERGY, bool DUMP, bool SWITCH>
 __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? DIRECT_CTAS_PER_SM/2 : DIRECT_CTAS_PER_SM) : 8) k_direct(DirectArgs a) {
     constexpr int NS = NSUB > 0 ? NSUB : SNB_MAX_SUBSETS;
     constexpr bool TWO = NSUB == 2;         // subsets 0/1 travel as the floats 0.0/1.0: lambdas and energies by FMA
@@ -274,7 +275,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     const DirectConsts<R>& c = Real<R>::consts(a);
     const int numSub = NSUB > 0 ? NSUB : a.numSubsets;
     // this warp's contiguous share of the chunks
-    const int numChunks = min(a.counters[0], a.maxChunks);
+    // (values loaded from a uniform address are broadcast through a shuffle so that the compiler KNOWS they are
+    // warp-uniform: the loops and branches they steer then carry no divergence bookkeeping)
+    const int numChunks = __shfl_sync(full, min(a.counters[0], a.maxChunks), 0);
     const int per = (numChunks+(int) gridDim.x-1)/(int) gridDim.x;
     const int cBegin = min(numChunks, (int) blockIdx.x*per), cEnd = min(numChunks, cBegin+per);
     const BoxD boxd = a.sp->exact.boxd;
@@ -357,12 +360,12 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     int jCur = -1, octCur = 0, octNext = 0;
     if (cBegin < cEnd) {
         const int2 e0 = a.jList[(size_t) cBegin*32+lane];
-        octCur = a.chunkOctet[cBegin];
+        octCur = __shfl_sync(full, a.chunkOctet[cBegin], 0);
         jCur = e0.x;
         gather(e0, 0);
         if (cBegin+1 < cEnd) {
             entNext = a.jList[(size_t) (cBegin+1)*32+lane];
-            octNext = a.chunkOctet[cBegin+1];
+            octNext = __shfl_sync(full, a.chunkOctet[cBegin+1], 0);
         }
     }
     for (int ch = cBegin; ch < cEnd; ch++) {
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             gather(entNext, buf^1u);
             if (ch+2 < cEnd) {
                 entNext = a.jList[(size_t) (ch+2)*32+lane];
-                octNext = a.chunkOctet[ch+2];
+                octNext = __shfl_sync(full, a.chunkOctet[ch+2], 0);
             }
             cpAsyncWait<1>();               // chunk ch has landed (all but the newest group)
         }
@@ -429,7 +432,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
         for (int s = 0; s < NS; s++)
             t.eC[s] = t.eV[s] = 0;
         const unsigned copyBase = sb+copyOff;
-        // ---- 8 steps of 32 pairs --------------------------------------------------------
+        // ---- 8 steps of 32 pairs: straight-line code (the rare per-pair-wrapping octets take their own copy) ----
+        auto steps = [&](auto perPairTag) {
+        constexpr bool PERPAIR = decltype(perPairTag)::value;
 #pragma unroll STEP_UNROLL
         for (int s = 0; s < 8; s++) {
             const unsigned so = (kOff+s*St::STRIDE)&(7*St::STRIDE);
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             const vec4 q = St::ld4(ad);
             const unsigned mj = ldSharedU32(sb+St::AUX+slot*8+4);
             R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
-            if (PBC == PBC_SHIFT && perPair) {
+            if (PBC == PBC_SHIFT && PERPAIR) {
                 dx -= bAx*Real<R>::rint(dx*iAx);
                 dy -= bBy*Real<R>::rint(dy*iBy);
                 dz -= bCz*Real<R>::rint(dz*iCz);
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 const vec4 prm = St::ld4(ad+St::PRM);
                 R fc, fv, ec, ev, invR2;
                 // masked lanes compute on r^2 = 1 (self pairs have r = 0, excluded neighbours overflow r^-12)
-                pairMath<R, KIND>(c, BRANCHY ? r2 : (in ? r2 : (R) 1), pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
+                pairMath<R, KIND, SWITCH>(c, BRANCHY ? r2 : (in ? r2 : (R) 1), pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
                 R lc, lv;
                 if (NSUB == 1) {
                     lc = t.lamC[0]; lv = t.lamV[0];
@@ -526,13 +531,18 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             fjy = __shfl_sync(full, fjy, srcLane);
             fjz = __shfl_sync(full, fjz, srcLane);
         }
+        };
+        if (PBC == PBC_SHIFT && perPair)
+            steps(std::true_type());
+        else
+            steps(std::false_type());
         if (KIND != KIND_PLAIN && __any_sync(full, bandMask != 0u)) {
             if (bandMask) {
                 DirectOut o;
                 o.posd = a.posd; o.sortedAtom = a.sortedAtom; o.sp = a.sp; o.forceSorted = a.forceSorted; o.paddedAtoms = a.paddedAtoms;
                 o.energyTable = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
                 o.pairDump = a.pairDump; o.pairDumpCount = a.pairDumpCount; o.pairDumpCapacity = a.pairDumpCapacity;
-                bandPairs<R, KIND, PBC, ENERGY, DUMP>(o, c, bandMask, lane, ki, origI, pi, si4, perPair ? 1 : 0, &sStage[buf][0]);
+                bandPairs<R, KIND, PBC, ENERGY, DUMP, SWITCH>(o, c, bandMask, lane, ki, origI, pi, si4, perPair ? 1 : 0, &sStage[buf][0]);
             }
         }
         if (jCur >= 0) {
@@ -576,20 +586,29 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     }
 }
 
-template <int KIND, int PBC, int NSUB>
-static void launch4(const DirectArgs& a, cudaStream_t st, int grid) {
+template <int KIND, int PBC, int NSUB, bool SWITCH>
+static void launch5(const DirectArgs& a, cudaStream_t st, int grid) {
     if (a.doublePrecision) {
         // the double-precision mode is a correctness mode: one instantiation (energies always on)
-        if (a.pairDump) k_direct<double, KIND, PBC, NSUB, true, true><<<grid/3, 32, 0, st>>>(a);
-        else k_direct<double, KIND, PBC, NSUB, true, false><<<grid/3, 32, 0, st>>>(a);
+        if (a.pairDump) k_direct<double, KIND, PBC, NSUB, true, true, SWITCH><<<grid/2, 32, 0, st>>>(a);
+        else k_direct<double, KIND, PBC, NSUB, true, false, SWITCH><<<grid/2, 32, 0, st>>>(a);
         return;
     }
     if (a.pairDump)
-        k_direct<float, KIND, PBC, NSUB, true, true><<<grid, 32, 0, st>>>(a);
+        k_direct<float, KIND, PBC, NSUB, true, true, SWITCH><<<grid, 32, 0, st>>>(a);
     else if (a.needEnergy)
-        k_direct<float, KIND, PBC, NSUB, true, false><<<grid, 32, 0, st>>>(a);
+        k_direct<float, KIND, PBC, NSUB, true, false, SWITCH><<<grid, 32, 0, st>>>(a);
     else
-        k_direct<float, KIND, PBC, NSUB, false, false><<<grid, 32, 0, st>>>(a);
+        k_direct<float, KIND, PBC, NSUB, false, false, SWITCH><<<grid, 32, 0, st>>>(a);
+}
+
+template <int KIND, int PBC, int NSUB>
+static void launch4(const DirectArgs& a, cudaStream_t st, int grid) {
+    // the switching function exists for the cutoff and Ewald/PME kinds only (LJPME and NoCutoff have none)
+    if ((KIND == KIND_RF || KIND == KIND_EWALD) && a.useSwitch)
+        launch5<KIND, PBC, NSUB, (KIND == KIND_RF || KIND == KIND_EWALD)>(a, st, grid);
+    else
+        launch5<KIND, PBC, NSUB, false>(a, st, grid);
 }
 
 template <int KIND, int PBC>

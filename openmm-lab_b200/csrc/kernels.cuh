@@ -16,6 +16,7 @@ struct SortArgs {
     const int* cellRank;
     double* extent;
     int *cellCount, *cellStart, *atomCell, *atomSlot, *cellScratch, *sortedAtom, *sortedPos;
+    int* tileSum;           // [ceil(numCells/1024)] scratch of the tiled scan (large cell grids)
     int2* cellRange;        // [numCells] sorted range (first, end) of every cell, by LINEAR cell index
     float4 *posqLocal, *sparams;
     double4 *posqLocalD, *sparamsD;  // double-precision mode only (else null)
@@ -44,7 +45,7 @@ struct ListArgs {
     const int2* cellRange;  // [numCells] sorted range of every cell, by linear cell index ((x*dimY+y)*dimZ+z)
     int cellDim[3];
     const double* extent;   // non-periodic methods: bounding box of all atoms (min[3], max[3])
-    int octLo, octHi;       // this rank's octets
+    int blockLo, blockHi;   // this rank's i blocks
     int bitmapWords;        // ceil(numBlocks/32)
 };
 void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);

@@ -1,4 +1,5 @@
-// Tile-list build (north-star subsystem 1b): one fused kernel, one warp per octet.
+// Tile-list build (north-star subsystem 1b): one fused kernel, one CTA of four warps per block of 32 i
+// atoms, one warp per octet.
 //
 // The sorted atoms are cut into blocks of 32 (j side) and octets of 8 (i side; 4 per block).  For
 // every octet the list holds the later atoms that come within the cutoff of the octet's bounding
@@ -7,17 +8,19 @@
 // ~40% of the pairs a tile visits are in range instead of ~27%.
 //
 // Candidate search is O(N): the atoms were binned into small cells (sort.cu) whose sorted ranges
-// are known, so a warp
-//   1. marks, in a per-warp bitmap over the j blocks, the blocks owning atoms of the cells that
-//      overlap the octet's box dilated by the cutoff (periodic wrap in fractional coordinates,
-//      so triclinic boxes need nothing special);
-//   2. walks the set bits in ascending order and tests the 32 atoms of each candidate block against
-//      the octet's box (one ballot -> one 32-bit word of interaction flags per block);
-//   3. prefix-sums the popcounts, takes a contiguous range of chunks from the global list with one
-//      atomicAdd, writes the entries (ascending j: the tile kernel's gathers stay coalesced) and ORs
-//      the exclusion masks in from the octet's own (short) exclusion lists.
+// are known, so a CTA
+//   1. marks, in a shared bitmap over the j blocks, the blocks owning atoms of the cells that overlap the
+//      i block's box dilated by the cutoff (cells farther than the cutoff pruned; periodic wrap in
+//      fractional coordinates, so triclinic boxes need nothing special) -- all 128 threads;
+//   2. walks the set bits in ascending order; the candidates are split between the four warps, each of
+//      which loads a candidate block's 32 atoms ONCE (four candidates in flight) and tests them against
+//      all four octet boxes (one ballot -> one 32-bit word of interaction flags per octet);
+//   3. every warp then gathers its own octet's non-empty words, prefix-sums the popcounts, takes a
+//      contiguous range of chunks from the global list with one atomicAdd, writes the entries (ascending
+//      j: the tile kernel's gathers stay coalesced) and ORs the exclusion masks in from the octet's own
+//      (short) exclusion lists.
 // No order-dependent atomics: chunk CONTENTS are deterministic, only their location in the list varies.
-// A rank of a multi-GPU run builds the lists of its own octet range [octLo, octHi) only.
+// A rank of a multi-GPU run builds the lists of its own block range [blockLo, blockHi) only.
 //
 // No counterpart source exists in the reference tree (OpenMM's CudaNonbondedUtilities does this job
 // there, un-vendored); exclusion semantics: every exception excludes its pair
@@ -26,7 +29,8 @@
 
 #define LIST_WARPS 4
 #define HIT_CAP 128            /* hit blocks buffered per batch; a fuller octet emits several batches */
-#define CAND_WORDS 512         /* 1024 unsigned shorts: the candidate blocks of one window of 32 bitmap words */
+#define CAND_CAP 1024          /* candidate blocks of one window of 32 bitmap words (unsigned shorts) */
+#define TEST_BATCH 128         /* candidates tested between two CTA barriers: 32 per warp */
 
 __device__ __forceinline__ float wrapOrtho(float d, float L, float invL) { return d-L*rintf(d*invL); }
 
@@ -116,33 +120,45 @@ __device__ __forceinline__ float cellGap(float rel, int i, float halfCells, floa
 __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     extern __shared__ unsigned sMem[];
     const int lane = threadIdx.x&31, w = threadIdx.x>>5;
-    const int O = a.octLo+blockIdx.x*LIST_WARPS+w;      // octet
-    if (O >= a.octHi)
+    const int I = a.blockLo+blockIdx.x;                 // i block; warp w owns its octet w
+    if (I >= a.blockHi)
         return;
-    const float4 ext = a.octetExt[O];
-    if (ext.x < 0.f)
-        return;                                         // padding octet
-    unsigned* bm = sMem+(size_t) w*(a.bitmapWords+3*HIT_CAP+CAND_WORDS);
-    int* hitJ = (int*) (bm+a.bitmapWords);
-    unsigned* hitWord = (unsigned*) (hitJ+HIT_CAP);
-    int* hitBase = (int*) (hitWord+HIT_CAP);
-    unsigned short* cand = (unsigned short*) (hitBase+HIT_CAP);     // candidates of the current window of 32 words
+    const int O = 4*I+w;
+    // shared: bitmap | candidates of the window | flag words of the batch under test | per-octet hit lists
+    unsigned* bm = sMem;
+    unsigned short* cand = (unsigned short*) (bm+a.bitmapWords);
+    unsigned* tmpWord = (unsigned*) (cand+CAND_CAP);                // [4][TEST_BATCH]
+    int* hitJ = (int*) (tmpWord+4*TEST_BATCH)+w*HIT_CAP;            // this warp's rows of [4][HIT_CAP]
+    unsigned* hitWord = (unsigned*) ((int*) (tmpWord+4*TEST_BATCH)+4*HIT_CAP)+w*HIT_CAP;
+    int* hitBase = (int*) (tmpWord+4*TEST_BATCH)+8*HIT_CAP+w*HIT_CAP;
+    __shared__ int sNc;
     const unsigned full = 0xffffffffu;
-    const int I = O>>2, lastI = O*8+7, wFirst = I>>5;
-    const float4 oc = a.octetCenter[O];
-    const float3 oe = make_float3(ext.x, ext.y, ext.z);
+    const int lastI = O*8+7, wFirst = I>>5;
     const float4 cI = a.blockCenter[I];
     const float cut2 = a.cutoff*a.cutoff;
     const BoxF box = a.sp->box;
     const int pbcMode = a.pbcMode;
+    // the four octet boxes of the block (every warp tests candidates against all four)
+    float4 oc[4];
+    float3 oe[4];
+    bool ov[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        oc[o] = a.octetCenter[4*I+o];
+        const float4 e = a.octetExt[4*I+o];
+        oe[o] = make_float3(e.x, e.y, e.z);
+        ov[o] = e.x >= 0.f;                             // false: padding octet
+    }
+    const float4 ext = a.octetExt[O];
+    const bool mine = ext.x >= 0.f;
 
-    // ---- 1. candidate blocks ------------------------------------------------------------------
-    for (int k = wFirst+lane; k < a.bitmapWords; k += 32)
+    // ---- 1. candidate blocks of the whole i block (all 128 threads) -------------------------------
+    for (int k = wFirst+threadIdx.x; k < a.bitmapWords; k += blockDim.x)
         bm[k] = 0u;
-    __syncwarp();
+    __syncthreads();
     if (!a.useCutoff) {
         // no cutoff: every later atom interacts
-        for (int k = wFirst+lane; k < a.bitmapWords; k += 32) {
+        for (int k = wFirst+threadIdx.x; k < a.bitmapWords; k += blockDim.x) {
             unsigned word = full;
             if (k == wFirst) word &= full<<(I&31);
             const int rem = a.numBlocks-k*32;
@@ -152,22 +168,23 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
     }
     else {
         const double margin = 1e-5;     // block-local float coordinates vs the double coordinates the cells were cut from
-        const double c[3] = {(double) cI.x+(double) oc.x, (double) cI.y+(double) oc.y, (double) cI.z+(double) oc.z};
-        const double half[3] = {(double) oe.x+a.cutoff+margin, (double) oe.y+a.cutoff+margin, (double) oe.z+a.cutoff+margin};
+        const float4 be = a.blockExt[I];
+        const double c[3] = {(double) cI.x, (double) cI.y, (double) cI.z};
+        const double half[3] = {(double) be.x+a.cutoff+margin, (double) be.y+a.cutoff+margin, (double) be.z+a.cutoff+margin};
         int lo[3], n[3];
         float rel[3], cs[3];
         cellSpan(a, c, half, lo, n, rel, cs);
-        // axis-aligned cells: skip those farther than the cutoff from the octet's box (the corners of the span)
+        // axis-aligned cells: skip those farther than the cutoff from the block's box (the corners of the span)
         const bool prune = pbcMode != PBC_PAIR_TRICLINIC && cs[0] > 0.f && cs[1] > 0.f && cs[2] > 0.f;
-        const float hc0 = prune ? (oe.x+1e-5f)/cs[0] : 0.f, hc1 = prune ? (oe.y+1e-5f)/cs[1] : 0.f, hc2 = prune ? (oe.z+1e-5f)/cs[2] : 0.f;
+        const float hc0 = prune ? (be.x+1e-5f)/cs[0] : 0.f, hc1 = prune ? (be.y+1e-5f)/cs[1] : 0.f, hc2 = prune ? (be.z+1e-5f)/cs[2] : 0.f;
         const float pruneCut2 = (a.cutoff+1e-5f)*(a.cutoff+1e-5f);
         const int nyz = n[1]*n[2], total = n[0]*nyz;
         const int dy = a.cellDim[1], dz = a.cellDim[2], dx = a.cellDim[0];
-        for (int base = 0; base < total; base += 128) {
-            int2 range[4];
+        for (int base = 0; base < total; base += 2*LIST_WARPS*32) {
+            int2 range[2];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int idx = base+u*32+lane;
+            for (int u = 0; u < 2; u++) {
+                const int idx = base+u*LIST_WARPS*32+(int) threadIdx.x;
                 range[u] = make_int2(0, 0);
                 if (idx < total) {
                     const int ix = idx/nyz, s = idx-ix*nyz;
@@ -191,23 +208,23 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int s0 = max(range[u].x, lastI+1), e0 = range[u].y;
+            for (int u = 0; u < 2; u++) {
+                const int s0 = max(range[u].x, I*32), e0 = range[u].y;
                 if (e0 > s0)
                     for (int b = s0>>5; b <= (e0-1)>>5; b++)
                         atomicOr(&bm[b>>5], 1u<<(b&31));
             }
         }
     }
-    __syncwarp();
+    __syncthreads();
 
-    // ---- 2. + 3. walk the candidates, buffer the hit blocks, emit batches ------------------------
+    // ---- 2. + 3. test the candidates (shared between the warps), keep this octet's hits, emit batches ----
     int nh = 0;
     bool first = true, dead = false;
     // octets too wide for the one-image-per-j-atom shortcut wrap every pair instead
     const int wide = (pbcMode == PBC_SHIFT && (ext.x >= a.sp->shiftLimit[0] || ext.y >= a.sp->shiftLimit[1] || ext.z >= a.sp->shiftLimit[2])) ? 1 : 0;
     const int ki = O*8+(lane&7);
-    const int atomK = a.sortedAtom[ki];                 // atom k = lane&7 of the octet, on every lane
+    const int atomK = mine ? a.sortedAtom[ki] : -1;     // atom k = lane&7 of the octet, on every lane
     const int atomI = lane < 8 ? atomK : -1;
 
     auto flush = [&]() {
@@ -287,82 +304,105 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
         nh = 0;
     };
 
-    // the interaction flags of one candidate block: 32 atoms against the octet's box
-    auto testBlock = [&](int J, const float4& pj, const float4& cJ) -> unsigned {
-        const int j = J*32+lane;
-        bool acc = J >= 0 && j < a.numAtoms && j > lastI;
-        if (a.useCutoff && acc) {
-            const float px = pj.x+(cJ.x-cI.x)-oc.x, py = pj.y+(cJ.y-cI.y)-oc.y, pz = pj.z+(cJ.z-cI.z)-oc.z;
-            acc = imageDist2(px, py, pz, oe, pbcMode, box) < cut2;
+    for (int w0 = wFirst; w0 < a.bitmapWords; w0 += 32) {
+        // candidates of this window of 32 bitmap words, in ascending order (warp 0 lists them for everyone)
+        {
+            const unsigned probe = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
+            if (!__any_sync(full, probe != 0u))
+                continue;                   // same answer in every warp: no barrier is skipped by some only
         }
-        return __ballot_sync(full, acc);
-    };
-
-    for (int w0 = wFirst; w0 < a.bitmapWords && !dead; w0 += 32) {
-        // candidates of this window of 32 words, in ascending order
-        unsigned myWord = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
-        if (!__any_sync(full, myWord != 0u))
-            continue;
-        const int cnt = __popc(myWord);
-        int incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(full, incl, o);
-            if (lane >= o) incl += t;
+        if (w == 0) {
+            unsigned myWord = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
+            const int cnt = __popc(myWord);
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(full, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int pos = incl-cnt;
+            while (myWord) {
+                cand[pos++] = (unsigned short) (lane*32+__ffs(myWord)-1);
+                myWord &= myWord-1;
+            }
+            if (lane == 31)
+                sNc = incl;
         }
-        const int nc = __shfl_sync(full, incl, 31);
-        if (nc == 0)
-            continue;
-        int pos = incl-cnt;
-        while (myWord) {
-            cand[pos++] = (unsigned short) (lane*32+__ffs(myWord)-1);
-            myWord &= myWord-1;
-        }
-        __syncwarp();
+        __syncthreads();
+        const int nc = sNc;
         const int Jbase = w0*32;
-        for (int k0 = 0; k0 < nc && !dead; k0 += 4) {
-            // four candidates in flight: their loads are issued before the first test
-            int J[4];
-            float4 pj[4], bc[4];
+        __syncthreads();                    // everyone has read sNc before warp 0 may rewrite it
+        for (int c0 = 0; c0 < nc; c0 += TEST_BATCH) {
+            // warp w tests candidates c0 + 32 w .. +31 against all four octet boxes
+            const int kEnd = min(nc, c0+32*w+32);
+            for (int k0 = c0+32*w; k0 < kEnd; k0 += 4) {
+                int J[4];
+                float4 pj[4], bc[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                J[u] = k0+u < nc ? Jbase+cand[k0+u] : -1;
-                pj[u] = bc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (J[u] >= 0 && a.useCutoff) {
-                    pj[u] = a.posqLocal[J[u]*32+lane];
-                    bc[u] = a.blockCenter[J[u]];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const unsigned word = testBlock(J[u], pj[u], bc[u]);
-                if (word && !dead) {
-                    if (lane == 0) {
-                        hitJ[nh] = J[u];
-                        hitWord[nh] = word;
+                for (int u = 0; u < 4; u++) {
+                    J[u] = k0+u < kEnd ? Jbase+cand[k0+u] : -1;
+                    pj[u] = bc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (J[u] >= 0 && a.useCutoff) {
+                        pj[u] = a.posqLocal[J[u]*32+lane];
+                        bc[u] = a.blockCenter[J[u]];
                     }
-                    nh++;
-                    __syncwarp();
-                    if (nh == HIT_CAP)
-                        flush();
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (J[u] < 0)
+                        continue;
+                    const int j = J[u]*32+lane;
+                    const bool atom = j < a.numAtoms;
+                    const float px = pj[u].x+(bc[u].x-cI.x), py = pj[u].y+(bc[u].y-cI.y), pz = pj[u].z+(bc[u].z-cI.z);
+                    unsigned keep = 0u;
+#pragma unroll
+                    for (int o = 0; o < 4; o++) {
+                        bool acc = atom && ov[o] && j > (4*I+o)*8+7;
+                        if (a.useCutoff && acc)
+                            acc = imageDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o], pbcMode, box) < cut2;
+                        const unsigned word = __ballot_sync(full, acc);
+                        if (lane == o)
+                            keep = word;
+                    }
+                    if (lane < 4)
+                        tmpWord[lane*TEST_BATCH+(k0+u-c0)] = keep;
                 }
             }
+            __syncthreads();
+            // this warp gathers its own octet's non-empty words, in candidate (= ascending j) order
+            const int nb = min(TEST_BATCH, nc-c0);
+            if (mine && !dead)
+                for (int k0 = 0; k0 < nb; k0 += 32) {
+                    if (nh > HIT_CAP-32)
+                        flush();
+                    if (dead)
+                        break;
+                    const unsigned word = k0+lane < nb ? tmpWord[w*TEST_BATCH+k0+lane] : 0u;
+                    const unsigned nz = __ballot_sync(full, word != 0u);
+                    if (word) {
+                        const int pos = nh+__popc(nz&((1u<<lane)-1));
+                        hitJ[pos] = Jbase+cand[c0+k0+lane];
+                        hitWord[pos] = word;
+                    }
+                    nh += __popc(nz);
+                    __syncwarp();
+                }
+            __syncthreads();
         }
-        __syncwarp();
     }
-    if (!dead && (first || nh > 0))
+    if (mine && !dead && (first || nh > 0))
         flush();
 }
 
 void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs) {
     (void) numSMs;
-    const int numOctets = a.octHi-a.octLo;
-    if (numOctets <= 0)
+    const int numBlocks = a.blockHi-a.blockLo;
+    if (numBlocks <= 0)
         return;
-    const size_t smem = sizeof(unsigned)*(size_t) LIST_WARPS*(a.bitmapWords+3*HIT_CAP+CAND_WORDS);
+    const size_t smem = sizeof(unsigned)*((size_t) a.bitmapWords+CAND_CAP/2+4*TEST_BATCH+12*HIT_CAP);
     static size_t attrSet = 0;
     if (smem > 48*1024 && smem > attrSet) {
         cudaFuncSetAttribute(k_buildList, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         attrSet = smem;
     }
-    k_buildList<<<(numOctets+LIST_WARPS-1)/LIST_WARPS, LIST_WARPS*32, smem, stream>>>(a);
+    k_buildList<<<numBlocks, LIST_WARPS*32, smem, stream>>>(a);
 }

@@ -71,41 +71,86 @@ __global__ void k_extent(const double* posd, int numAtoms, double* extent) {
     }
 }
 
-// ---- 2. exclusive scan of the cell counts (single block, 1024 threads, tiled) ---------
-__global__ void k_scanCells(const int* __restrict__ count, int* __restrict__ start, int numCells) {
-    __shared__ int warpSums[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0)
-        carry = 0;
+// ---- 2. exclusive scan of the cell counts -----------------------------------------------------------
+// Small grids (<= SCAN_SINGLE cells): one block, every thread owns a contiguous run of cells.
+// Large grids: tiles of SCAN_TILE cells -- per-tile sums, a one-block scan of those, per-tile scans (coalesced).
+#define SCAN_SINGLE 16384
+#define SCAN_TILE 1024
+
+__device__ __forceinline__ int blockExclusiveScan(int v, int* warpSums, int& total) {
+    // exclusive prefix of v over the block (blockDim.x <= 1024); total = sum over the block
+    const int lane = threadIdx.x&31, warp = threadIdx.x>>5;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warpSums[warp] = incl;
     __syncthreads();
-    int lane = threadIdx.x&31, warp = threadIdx.x>>5;
-    for (int base = 0; base < numCells; base += blockDim.x) {
-        int i = base+threadIdx.x;
-        int v = i < numCells ? count[i] : 0;
-        int incl = v;
+    if (warp == 0) {
+        int w = lane < (int) (blockDim.x+31)/32 ? warpSums[lane] : 0;
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
-        if (lane == 31) warpSums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = warpSums[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            warpSums[lane] = w;
-        }
-        __syncthreads();
-        int prefix = carry+(warp > 0 ? warpSums[warp-1] : 0)+incl-v;
-        if (i < numCells) start[i] = prefix;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x-1) carry = prefix+v;
+        warpSums[lane] = w;
+    }
+    __syncthreads();
+    total = warpSums[31];
+    return (warp > 0 ? warpSums[warp-1] : 0)+incl-v;
+}
+
+__global__ void __launch_bounds__(1024) k_scanCells(const int* __restrict__ count, int* __restrict__ start, int numCells) {
+    __shared__ int warpSums[32];
+    const int per = (numCells+blockDim.x-1)/blockDim.x;
+    const int first = min(numCells, (int) threadIdx.x*per), last = min(numCells, first+per);
+    int sum = 0;
+    for (int i = first; i < last; i++)
+        sum += count[i];
+    int total;
+    int running = blockExclusiveScan(sum, warpSums, total);
+    for (int i = first; i < last; i++) {
+        start[i] = running;
+        running += count[i];
+    }
+    if (threadIdx.x == 0)
+        start[numCells] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_TILE) k_scanTileSums(const int* __restrict__ count, int* __restrict__ tileSum, int numCells) {
+    __shared__ int warpSums[32];
+    const int i = blockIdx.x*SCAN_TILE+threadIdx.x;
+    int total;
+    blockExclusiveScan(i < numCells ? count[i] : 0, warpSums, total);
+    if (threadIdx.x == 0)
+        tileSum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scanTileOffsets(int* __restrict__ tileSum, int numTiles, int* __restrict__ start, int numCells) {
+    // exclusive scan of the tile sums in place (numTiles can exceed the block: carried loop)
+    __shared__ int warpSums[32];
+    int carry = 0;
+    for (int base = 0; base < numTiles; base += blockDim.x) {
+        const int i = base+threadIdx.x;
+        const int v = i < numTiles ? tileSum[i] : 0;
+        int total;
+        const int excl = blockExclusiveScan(v, warpSums, total);
+        if (i < numTiles)
+            tileSum[i] = carry+excl;
+        carry += total;
         __syncthreads();
     }
     if (threadIdx.x == 0)
         start[numCells] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_TILE) k_scanTiles(const int* __restrict__ count, const int* __restrict__ tileOffset, int* __restrict__ start, int numCells) {
+    __shared__ int warpSums[32];
+    const int i = blockIdx.x*SCAN_TILE+threadIdx.x;
+    int total;
+    const int excl = blockExclusiveScan(i < numCells ? count[i] : 0, warpSums, total);
+    if (i < numCells)
+        start[i] = tileOffset[blockIdx.x]+excl;
 }
 
 // ---- 3. scatter + deterministic order inside each cell --------------------------------
@@ -120,6 +165,7 @@ __global__ void k_scatterAtoms(SortArgs a) {
     if (i < a.numCells) {
         const int r = a.cellRank[i];
         a.cellRange[i] = make_int2(a.cellStart[r], a.cellStart[r+1]);
+        a.cellCount[i] = 0;         // ready for the next evaluation's k_assignCells (saves a memset per evaluation)
     }
     // padding slots of the last block
     int pad = a.numAtoms+i;
@@ -232,11 +278,17 @@ __global__ void k_blockBounds(SortArgs a) {
 void launchSort(const SortArgs& a, cudaStream_t stream) {
     int threads = 256;
     int atomBlocks = (a.paddedAtoms+threads-1)/threads;
-    cudaMemsetAsync(a.cellCount, 0, sizeof(int)*a.numCells, stream);
     if (!a.periodic)
         k_extent<<<1, 256, 0, stream>>>(a.posd, a.numAtoms, a.extent);
     k_assignCells<<<atomBlocks, threads, 0, stream>>>(a);
-    k_scanCells<<<1, 1024, 0, stream>>>(a.cellCount, a.cellStart, a.numCells);
+    if (a.numCells <= SCAN_SINGLE)
+        k_scanCells<<<1, 1024, 0, stream>>>(a.cellCount, a.cellStart, a.numCells);
+    else {
+        const int tiles = (a.numCells+SCAN_TILE-1)/SCAN_TILE;
+        k_scanTileSums<<<tiles, SCAN_TILE, 0, stream>>>(a.cellCount, a.tileSum, a.numCells);
+        k_scanTileOffsets<<<1, 1024, 0, stream>>>(a.tileSum, tiles, a.cellStart, a.numCells);
+        k_scanTiles<<<tiles, SCAN_TILE, 0, stream>>>(a.cellCount, a.tileSum, a.cellStart, a.numCells);
+    }
     k_scatterAtoms<<<(max(a.paddedAtoms, a.numCells)+threads-1)/threads, threads, 0, stream>>>(a);
     k_rankInCell<<<atomBlocks, threads, 0, stream>>>(a);
     k_blockBounds<<<(a.numBlocks*32+threads-1)/threads, threads, 0, stream>>>(a);

@@ -34,6 +34,7 @@ class CalcSlicedNonbondedForceKernel:
         self._device_index = device_index
         self._flags = flags
         self._packed = None
+        self._execute = None
 
     def _fn(self, name):
         return getattr(self._lib, self._prefix+name)
@@ -62,17 +63,21 @@ class CalcSlicedNonbondedForceKernel:
     def execute(self, context, includeForces, includeEnergy, includeDirect, includeReciprocal):
         flags = (_abi.INCLUDE_FORCES if includeForces else 0) | (_abi.INCLUDE_ENERGY if includeEnergy else 0) | \
                 (_abi.INCLUDE_DIRECT if includeDirect else 0) | (_abi.INCLUDE_RECIPROCAL if includeReciprocal else 0)
-        pos = np.ascontiguousarray(context._positions, dtype=np.float64)
+        pos = context._positions
+        if pos.dtype != np.float64 or not pos.flags.c_contiguous:
+            pos = np.ascontiguousarray(pos, dtype=np.float64)
         box = np.ascontiguousarray(context._box, dtype=np.float64).reshape(9)
         params = np.array([context.getParameter(n) for n in self.globalNames], dtype=np.float64)
         derivs = np.zeros(max(1, len(self.derivativeNames)))
         energy = C.c_double(0.0)
-        fn = self._fn("execute")
-        fn.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, _dp, C.POINTER(C.c_double), _dp, _dp]
+        fn = self._execute
+        if fn is None:
+            fn = self._execute = self._fn("execute")
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         forces = context._forces
-        self._check(fn(self._handle, pos.ctypes.data_as(_dp), box.ctypes.data_as(_dp), params.ctypes.data_as(_dp), flags,
-                       forces.ctypes.data_as(_dp) if includeForces else None, C.byref(energy),
-                       self.sliceEnergies.ctypes.data_as(_dp), derivs.ctypes.data_as(_dp)))
+        self._check(fn(self._handle, pos.ctypes.data, box.ctypes.data, params.ctypes.data, flags,
+                       forces.ctypes.data if includeForces else None, C.byref(energy),
+                       self.sliceEnergies.ctypes.data, derivs.ctypes.data))
         for k, name in enumerate(self.derivativeNames):
             context._energyParameterDerivatives[name] = context._energyParameterDerivatives.get(name, 0.0)+derivs[k]
         return energy.value
