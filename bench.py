@@ -48,6 +48,16 @@ def load_peaks():
     return {}
 
 
+def load_traffic(workload):
+    """DRAM bytes per launch of k_direct from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)[workload]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -240,7 +250,7 @@ class Runner:
                            "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved/FP32_PEAK_TFLOPS,
                            "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz (FP32 FMA, non-tensor; MEASURED_PEAKS.json carries no FP32 entry)",
                            "interacting_pairs": kernel_pairs, "interacting_pairs_all_ranks": int(sum(r[1] for r in rows)),
-                           "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": kernel_ms, "rank": slow, "traffic": None}
+                           "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": kernel_ms, "rank": slow, "traffic": load_traffic(self.w.name)}
         # the memory-bound kernels against the measured HBM peak (algorithmic bytes)
         f = self.w.force
         _, nx, ny, nz = f.getPMEParameters()
