@@ -141,7 +141,7 @@ def config_of(w, world=1):
             "evaluation": "forces+energy+derivatives, direct+reciprocal, tile list rebuilt every step",
             "parallelism": "1 GPU" if world == 1 else
                            "%d ranks share each evaluation: tile list + exceptions partitioned, reciprocal space on rank 0, "
-                           "ncclBroadcast(positions) + ncclReduce(fixed-point forces) + ncclAllReduce(slice energies)" % world,
+                           "positions replicated by the caller, one ncclAllReduce(int64) of fixed-point forces + slice energies per evaluation" % world,
             "l2": "256 MiB flush write between timed steps; every step rewrites the force/grid/list buffers",
             "timing": "host wall-clock around each synchronised step, max over ranks (CUDA-event time reported as device_ms_per_step)",
             "precision": "mixed (FP32 pair arithmetic, FP64 / 2^32 fixed-point accumulation)"}
@@ -168,6 +168,7 @@ class Runner:
             ident = [kernel.ncclUniqueId() if rank == 0 else None]
             dist.broadcast_object_list(ident, src=0)
             kernel.commInit(ident[0], rank, world)
+            kernel.setCommOptions(broadcast_positions=False)    # every rank already holds the same positions (config says so)
         self.params = np.array([ctx.getParameter(name) for name in kernel.globalNames], dtype=np.float64)
         self.box = np.ascontiguousarray(w.box, dtype=np.float64).reshape(9)
         self.flags = _abi.EXECUTE_ALL

@@ -172,15 +172,18 @@ int snb_get_ljpme_parameters(const snb_handle* h, double* alpha, int* nx, int* n
  * on rank 0 -- the split of the reference's multi-device kernel
  * (platforms/cuda/src/CudaParallelOpenMMLabKernels.cpp:19-53;
  * CudaOpenMMLabKernels.cpp:379,405,466,680-683,762-765).  Every rank calls snb_execute* with
- * the same box, global parameters and flags; rank 0's positions are broadcast (ncclBroadcast),
- * the 2^32 fixed-point forces are summed onto rank 0 (ncclReduce, exact: the result is
- * bit-identical to the single-GPU one) and the slice energies / derivatives are all-reduced,
- * so forces are returned on rank 0 only and energies on every rank. */
+ * the same box, global parameters and flags; rank 0's positions are broadcast (ncclBroadcast;
+ * skipped when the caller declares them identical everywhere, snb_set_comm_options) and ONE
+ * ncclAllReduce(sum, int64) per evaluation carries the 2^32 fixed-point forces, the slice
+ * energies and the bookkeeping flags -- integer sums are exact, so the forces are bit-identical
+ * to the single-GPU ones -- and leaves forces, energies and derivatives on every rank. */
 int snb_nccl_unique_id(void* id128);             /* rank 0: fills a 128-byte ncclUniqueId; ship it to the other ranks */
 int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size);
 /* rank 0's share of the tile list relative to 1.0 for every other rank (it also runs reciprocal
  * space); negative = built-in cost model */
 int snb_set_rank0_share(snb_handle* h, double share);
+/* broadcast_positions = 0: every rank is given identical positions by its caller, no broadcast is needed */
+int snb_set_comm_options(snb_handle* h, int broadcast_positions);
 /* the partition rule itself (host only, no GPU): contiguous range [lo, hi) of n units for `rank` */
 int snb_partition(int64_t n, int world_size, int rank, double rank0_share, int64_t* lo, int64_t* hi);
 

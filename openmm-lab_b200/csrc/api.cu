@@ -168,6 +168,7 @@ struct GraphKey {
     int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy;
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
+    double share;
 };
 
 #define SNB_ENERGY_FLAGS 32
@@ -232,7 +233,10 @@ struct snb_handle {
     int rank = 0, world = 1;
     double rank0Share = -1;             // < 0: cost-model default
     DevBuf<long long> reduceSend, reduceRecv;
-    DevBuf<double> energyRecv;
+    PinnedBuf<long long> hEnergyFixed;  // the all-reduced energy table as it arrives (2^32 fixed point)
+    bool broadcastPositions = true;     // false: the caller guarantees identical positions on every rank
+    bool balanceFrozen = false;         // after a few measured evaluations the partition is fixed (and graphs take over)
+    int commEvals = 0;
     cudaEvent_t evDirBegin = nullptr, evDirEnd = nullptr, evRecBegin = nullptr, evRecEnd = nullptr, evReady = nullptr;
     PinnedBuf<double> loadH;            // this rank's measured times of the previous evaluation, sent with the all-reduce
     bool loadValid = false, autoBalance = true;
@@ -754,7 +758,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         CUDA_CHECK(cudaMemcpyAsync(h.posd.p, in.hostPos, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
     else
         launchConvertPositions((const float4*) in.posqDev, h.posd.p, h.N, st);
-    if (nccl)   // rank 0's positions are authoritative: every rank then builds the identical sorted order
+    if (nccl && h.broadcastPositions)   // rank 0's positions are authoritative: every rank then builds the identical sorted order
         NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, st));
     CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemsetAsync(h.zeroBlock.p, 0, h.zeroBytes, st));
@@ -827,12 +831,12 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     const bool doRecip = includeRecip && pmeFamily && h.rank == 0;
     if (doRecip && !h.timing) {
         CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.evSorted, 0));
-        if (nccl) CUDA_CHECK(cudaEventRecord(h.evRecBegin, h.pmeStream));
+        if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evRecBegin, h.pmeStream));
         reciprocal(h.pmeStream);
-        if (nccl) CUDA_CHECK(cudaEventRecord(h.evRecEnd, h.pmeStream));
+        if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evRecEnd, h.pmeStream));
         CUDA_CHECK(cudaEventRecord(h.evPmeDone, h.pmeStream));
     }
-    if (nccl && includeDirect) CUDA_CHECK(cudaEventRecord(h.evDirBegin, st));
+    if (nccl && includeDirect && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evDirBegin, st));
 
     if (includeDirect) {
         ListArgs la;
@@ -878,7 +882,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.chunkOctet = h.chunkOctet.p; da.maxChunks = (int) h.maxChunks;
         da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
         launchDirect(da, st, h.numSMs);
-        if (nccl) CUDA_CHECK(cudaEventRecord(h.evDirEnd, st));
+        if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evDirEnd, st));
         tm.mark(3);
         if (h.X > 0 && !bondedForked)
             bonded(st);
@@ -898,44 +902,40 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
 
     // ---- outputs ----
-    if (nccl) CUDA_CHECK(cudaEventRecord(h.evReady, st));
-    if (includeForces || nccl) {
-        FinishArgs fa;
-        memset(&fa, 0, sizeof(fa));
-        fa.numAtoms = h.N; fa.paddedAtoms = h.NP;
-        fa.sortedPos = includeDirect ? h.sortedPos.p : nullptr;
-        fa.forceSorted = h.forceSorted.p; fa.forceOrig = h.forceOrig.p;
-        fa.counters = h.counters.p; fa.flagsOut = h.energyBuf.p+32*2*SNB_MAX_SLICES;
-        if (nccl) {
-            // every rank contributes [3][N] fixed-point forces; the sum is exact, so the result is bit-identical
-            // to the single-GPU evaluation whatever the partition
-            fa.reduceOut = h.reduceSend.p;
-            launchFinish(fa, st);
-            if (includeForces) {
-                NCCL_CHECK(nccl, nccl->Reduce(h.reduceSend.p, h.reduceRecv.p, 3*(size_t) h.N, ncclInt64, ncclSum, 0, h.comm, st));
-                if (h.rank == 0)
-                    launchEmitReduced(h.reduceRecv.p, h.N, in.hostPositions ? h.forcesOutD.p : nullptr, (long long*) in.forcesFixedOut, st);
-            }
-        }
-        else {
-            fa.forcesOut = in.hostPositions ? h.forcesOutD.p : nullptr;
-            fa.forcesFixedOut = (long long*) in.forcesFixedOut;
-            launchFinish(fa, st);
-        }
-        if (includeForces && in.hostPositions && h.rank == 0)
-            CUDA_CHECK(cudaMemcpyAsync(h.hForces.p, h.forcesOutD.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyDeviceToHost, st));
-    }
-    tm.mark(9);
-    const double* energySrc = h.energyBuf.p;
+    if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evReady, st));
+    FinishArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.numAtoms = h.N; fa.paddedAtoms = h.NP;
+    fa.sortedPos = includeDirect ? h.sortedPos.p : nullptr;
+    fa.forceSorted = h.forceSorted.p; fa.forceOrig = h.forceOrig.p;
+    fa.counters = h.counters.p;
     if (nccl) {
-        // slice energies of all ranks, the list-overflow flags (every rank must take the same retry decision) and the
-        // times every rank measured in its PREVIOUS evaluation (every rank then derives the same new partition)
-        if (h.loadValid)
+        // ONE collective per evaluation: an int64 all-reduce of [3][N] fixed-point forces followed by the slice-energy
+        // table, the list-overflow flag (every rank must take the same retry decision) and the times every rank
+        // measured in its previous evaluation (every rank derives the same new partition), all in 2^32 fixed
+        // point.  Integer sums are exact: the forces are bit-identical to the single-GPU ones whatever the partition.
+        if (h.loadValid && !h.balanceFrozen)
             CUDA_CHECK(cudaMemcpyAsync(h.energyBuf.p+32*2*SNB_MAX_SLICES+1, h.loadH.p+1, sizeof(double)*(SNB_ENERGY_FLAGS-1), cudaMemcpyHostToDevice, st));
-        NCCL_CHECK(nccl, nccl->AllReduce(h.energyBuf.p, h.energyRecv.p, SNB_ENERGY_DOUBLES, ncclFloat64, ncclSum, h.comm, st));
-        energySrc = h.energyRecv.p;
+        fa.reduceOut = h.reduceSend.p;
+        fa.energyIn = h.energyBuf.p; fa.numEnergy = SNB_ENERGY_DOUBLES; fa.overflowSlot = 32*2*SNB_MAX_SLICES;
+        launchFinish(fa, st);
+        const size_t count = 3*(size_t) h.N+SNB_ENERGY_DOUBLES;
+        NCCL_CHECK(nccl, nccl->AllReduce(h.reduceSend.p, h.reduceRecv.p, count, ncclInt64, ncclSum, h.comm, st));
+        if (includeForces)
+            launchEmitReduced(h.reduceRecv.p, h.N, in.hostPositions ? h.forcesOutD.p : nullptr, (long long*) in.forcesFixedOut, st);
     }
-    CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, energySrc, sizeof(double)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
+    else if (includeForces) {
+        fa.forcesOut = in.hostPositions ? h.forcesOutD.p : nullptr;
+        fa.forcesFixedOut = (long long*) in.forcesFixedOut;
+        launchFinish(fa, st);
+    }
+    if (includeForces && in.hostPositions)
+        CUDA_CHECK(cudaMemcpyAsync(h.hForces.p, h.forcesOutD.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyDeviceToHost, st));
+    tm.mark(9);
+    if (nccl)
+        CUDA_CHECK(cudaMemcpyAsync(h.hEnergyFixed.p, h.reduceRecv.p+3*(size_t) h.N, sizeof(long long)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
+    else
+        CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, h.energyBuf.p, sizeof(double)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
     h.lastDirect = da;
 }
@@ -978,8 +978,9 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     key.numCells = h.numCells;
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     key.maxChunks = h.maxChunks;
+    key.share = h.comm ? rank0Share(h) : 0.0;
     key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p; key.hostPos = hostPos;
-    const bool graphable = h.useGraph && !h.timing && !h.comm;
+    const bool graphable = h.useGraph && !h.timing && (!h.comm || h.balanceFrozen);
     const bool sameKey = h.graphKeyValid && memcmp(&key, &h.graphKey, sizeof(key)) == 0;
     if (!graphable || !sameKey)
         dropGraph(h);
@@ -1018,7 +1019,10 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventElapsedTime(&h.lastDeviceMs, h.evBegin, h.evEnd));
     h.listValid = includeDirect;
-    if (h.comm && includeDirect && !h.timing) {
+    if (h.comm)
+        for (int k = 0; k < SNB_ENERGY_DOUBLES; k++)
+            h.hEnergy.p[k] = (double) h.hEnergyFixed.p[k]*(1.0/SNB_FORCE_SCALE_D);
+    if (h.comm && includeDirect && !h.timing && !h.balanceFrozen) {
         // load balance: what was measured one evaluation ago has just come back from the all-reduce, identical on every rank
         const double* got = h.hEnergy.p+32*2*SNB_MAX_SLICES;
         const int W = h.world;
@@ -1040,6 +1044,11 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
         if (h.rank == 0 && (flags&SNB_INCLUDE_RECIPROCAL) && pmeFamily && cudaEventElapsedTime(&ms, h.evRecBegin, h.evRecEnd) == cudaSuccess) h.loadH.p[1] = ms;
         h.loadValid = true;
         cudaGetLastError();     // an unrecorded event above must not poison the next evaluation's error check
+        if (++h.commEvals >= 8) {
+            // the partition has settled: freeze it (a stable launch shape), and let CUDA graphs take over
+            h.balanceFrozen = true;
+            if (h.rank0Share < 0 && h.tunedShare >= 0) h.rank0Share = h.tunedShare;
+        }
     }
     if (includeDirect) {
         const bool anyOverflow = h.comm ? h.hEnergy.p[32*2*SNB_MAX_SLICES] != 0.0 : h.hCounters.p[2] != 0;
@@ -1063,7 +1072,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     long long launches = 0;
     if (includeDirect) launches += (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
     if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 5 : 4)*(h.method == SNB_LJPME ? 2 : 1);    // spread (+finish), convolution, combine, interpolate
-    if (includeForces || h.comm) launches += 1+(h.comm && h.rank == 0 ? 1 : 0);
+    if (includeForces || h.comm) launches += 1+(h.comm && includeForces ? 1 : 0);
     if (posqDev) launches += 1;
     h.countersOut[2] = launches;
     return true;
@@ -1161,6 +1170,8 @@ void snb_destroy(snb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    // a captured evaluation holds NCCL operations: the graph must go before its communicator
+    if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
     if (h->comm) {
         if (const NcclApi* nccl = ncclApi(nullptr)) nccl->CommDestroy(h->comm);
         h->comm = nullptr;
@@ -1195,7 +1206,7 @@ int snb_execute(snb_handle* h, const double* positions, const double* box, const
     SNB_TRY
     if (!positions) throw SnbException(SNB_ERR_INVALID, "positions are null");
     evaluate(*h, positions, nullptr, box, globals, flags, nullptr);
-    if ((flags&SNB_INCLUDE_FORCES) && forces && h->rank == 0)
+    if ((flags&SNB_INCLUDE_FORCES) && forces)
         for (size_t k = 0; k < 3*(size_t) h->N; k++)
             forces[k] += h->hForces.p[k];
     return snb_read_energies(h, flags, energy, slice_energies, derivatives);
@@ -1356,14 +1367,15 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size) {
     const NcclApi* nccl = ncclApi(&why);
     if (!nccl) throw SnbException(SNB_ERR_UNSUPPORTED, std::string("NCCL is not available: ")+why);
     CUDA_CHECK(cudaSetDevice(h->device));
+    dropGraph(*h);
     if (h->comm) { nccl->CommDestroy(h->comm); h->comm = nullptr; }
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     NCCL_CHECK(nccl, nccl->CommInitRank(&h->comm, world_size, id, rank));
     h->rank = rank;
     h->world = world_size;
-    h->reduceSend.alloc(3*(size_t) h->N);
-    h->reduceRecv.alloc(3*(size_t) h->N);
+    h->reduceSend.alloc(3*(size_t) h->N+SNB_ENERGY_DOUBLES);
+    h->reduceRecv.alloc(3*(size_t) h->N+SNB_ENERGY_DOUBLES);
     h->loadH.alloc(SNB_ENERGY_FLAGS);
     if (!h->evDirBegin) {
         CUDA_CHECK(cudaEventCreate(&h->evDirBegin)); CUDA_CHECK(cudaEventCreate(&h->evDirEnd));
@@ -1371,12 +1383,15 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size) {
         CUDA_CHECK(cudaEventCreate(&h->evReady));
     }
     h->loadValid = false; h->tunedShare = -1;
-    h->energyRecv.alloc(SNB_ENERGY_DOUBLES);
+    h->hEnergyFixed.alloc(SNB_ENERGY_DOUBLES);
+    h->balanceFrozen = false; h->commEvals = 0;
     return SNB_OK;
     SNB_CATCH
 }
 
 int snb_set_rank0_share(snb_handle* h, double share) { h->rank0Share = share; return SNB_OK; }
+
+int snb_set_comm_options(snb_handle* h, int broadcast_positions) { h->broadcastPositions = broadcast_positions != 0; return SNB_OK; }
 
 int snb_partition(int64_t n, int world_size, int rank, double rank0_share, int64_t* lo, int64_t* hi) {
     if (!lo || !hi || world_size < 1 || rank < 0 || rank >= world_size || n < 0) {

@@ -5,6 +5,10 @@
 
 __global__ void k_finish(FinishArgs a) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (a.reduceOut && i < a.numEnergy) {
+        const double v = i == a.overflowSlot ? (double) a.counters[2] : a.energyIn[i];
+        a.reduceOut[3*(size_t) a.numAtoms+i] = __double2ll_rn(v*SNB_FORCE_SCALE_D);
+    }
     if (i >= a.numAtoms)
         return;
     const int k = a.sortedPos ? a.sortedPos[i] : i;
@@ -17,8 +21,6 @@ __global__ void k_finish(FinishArgs a) {
         if (a.reduceOut)
             a.reduceOut[(size_t) c*a.numAtoms+i] = f;
     }
-    if (i == 0 && a.flagsOut)
-        a.flagsOut[0] = (double) a.counters[2];
 }
 
 __global__ void k_emitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut) {
@@ -43,8 +45,9 @@ __global__ void k_convertPositions(const float4* posq, double* posd, int numAtom
 }
 
 void launchFinish(const FinishArgs& a, cudaStream_t stream) {
-    if (a.numAtoms > 0)
-        k_finish<<<(a.numAtoms+255)/256, 256, 0, stream>>>(a);
+    const int n = a.reduceOut ? (a.numAtoms > a.numEnergy ? a.numAtoms : a.numEnergy) : a.numAtoms;
+    if (n > 0)
+        k_finish<<<(n+255)/256, 256, 0, stream>>>(a);
 }
 
 void launchEmitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut, cudaStream_t stream) {

@@ -134,7 +134,8 @@ struct FinishArgs {
     long long* forcesFixedOut;      // [3][N] added to, or null
     long long* reduceOut;           // [3][N] overwritten: this rank's contribution to the NCCL force reduction, or null
     const int* counters;            // list-build counters; [2] = overflow flag
-    double* flagsOut;               // [1] overflow flag as a double, travels with the energy all-reduce (or null)
+    const double* energyIn;         // multi-GPU: the slice-energy table + flags, appended to reduceOut in 2^32 fixed point
+    int numEnergy, overflowSlot;    // entries of energyIn; which of them takes counters[2] instead
 };
 // after the force reduction (root only): reduced [3][N] fixed-point forces -> the caller's layout
 void launchEmitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut, cudaStream_t stream);

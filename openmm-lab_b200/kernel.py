@@ -209,6 +209,11 @@ class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
         self._check(fn(self._handle, unique_id, rank, world_size))
         self.rank, self.worldSize = rank, world_size
 
+    def setCommOptions(self, broadcast_positions=True):
+        fn = self._lib.snb_set_comm_options
+        fn.argtypes = [C.c_void_p, C.c_int]
+        self._check(fn(self._handle, int(bool(broadcast_positions))))
+
     def setRank0Share(self, share):
         fn = self._lib.snb_set_rank0_share
         fn.argtypes = [C.c_void_p, C.c_double]

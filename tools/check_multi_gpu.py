@@ -7,7 +7,7 @@
 Every rank takes its share of each evaluation (tile list + exceptions partitioned, reciprocal space on
 rank 0, NCCL broadcast / reduce); rank 0 then repeats the evaluation alone on a second, single-GPU
 kernel and compares: forces must be BIT-IDENTICAL in the deterministic mode (2^32 fixed-point sums do
-not depend on the partition), slice energies / derivatives equal to 1e-12 relative.
+not depend on the partition), slice energies / derivatives equal to 1e-9 (they travel in 2^32 fixed point with the forces) and identical on every rank.
 """
 import os
 import sys
@@ -43,9 +43,13 @@ def main():
             kernel.commInit(ident[0], rank, world)
             if share is not None:
                 kernel.setRank0Share(share)
-            ctx._forces = np.zeros((w.num_particles, 3))
-            ctx._energyParameterDerivatives = {}
-            e = kernel.execute(ctx, True, True, True, True)
+            # 12 evaluations: the first 8 measure and settle the partition, then it is frozen and the evaluation
+            # (NCCL all-reduce included) is replayed as a CUDA graph; the LAST one is compared
+            for it in range(12):
+                ctx._forces = np.zeros((w.num_particles, 3))
+                ctx._energyParameterDerivatives = {}
+                e = kernel.execute(ctx, True, True, True, True)
+            graphs = kernel.getCounters()[4]
             pairs = torch.tensor([kernel.countPairs()])
             dist.all_reduce(pairs)
             energies = [None]*world
@@ -65,11 +69,11 @@ def main():
                 dd = max(abs(ctx._energyParameterDerivatives[k]-solo._energyParameterDerivatives[k]) for k in solo._energyParameterDerivatives) \
                     if solo._energyParameterDerivatives else 0.0
                 same_pairs = int(pairs.item()) == k1.countPairs()
-                same_everywhere = all(abs(x[0]-e) <= 1e-12*max(abs(e), 1.0) for x in energies)
-                good = same_forces and de < 1e-12 and ds < 1e-12 and same_pairs and same_everywhere
+                same_everywhere = all(x[0] == e for x in energies)
+                good = same_forces and (share is not None or graphs == 1) and de < 1e-9 and ds < 1e-9 and same_pairs and same_everywhere
                 ok = ok and good
-                print("%-6s world=%d rank0_share=%-5s forces bit-identical=%s  pairs equal=%s  |dE|/E=%.1e  slices=%.1e  derivs=%.1e  energies on all ranks=%s  %s"
-                      % (name, world, share, same_forces, same_pairs, de, ds, dd, same_everywhere, "OK" if good else "FAIL"), flush=True)
+                print("%-6s world=%d rank0_share=%-5s forces bit-identical=%s  pairs equal=%s  |dE|/E=%.1e  slices=%.1e  derivs=%.1e  energies on all ranks=%s  graph=%d  %s"
+                      % (name, world, share, same_forces, same_pairs, de, ds, dd, same_everywhere, graphs, "OK" if good else "FAIL"), flush=True)
             del kernel, ctx
             dist.barrier()
     flag = torch.tensor([1 if ok else 0])
