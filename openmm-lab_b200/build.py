@@ -25,8 +25,10 @@ def _stale(target, deps):
 def build(verbose=False, force=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("SNB_NVCC_EXTRA", "").split()       # tuning experiments, e.g. -DDIRECT_CTAS_PER_SM=16
+    tag = os.environ.get("SNB_LIB_TAG", "")                      # experiments build next to the product: libslicednb_b200_<tag>.so
+    lib = LIB if not tag else LIB.replace(".so", "_%s.so" % tag)
     headers = [os.path.join(CSRC, h) for h in HEADERS]
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build"+("_"+tag if tag else ""))
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     for src in SOURCES:
@@ -45,9 +47,9 @@ def build(verbose=False, force=False):
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
         list(pool.map(run, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB]+objs+["-lcufft", "-ldl", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"])
-    return LIB
+    if force or jobs or _stale(lib, objs):
+        run([nvcc, "-shared", "-o", lib]+objs+["-lcufft", "-ldl", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"])
+    return lib
 
 
 if __name__ == "__main__":

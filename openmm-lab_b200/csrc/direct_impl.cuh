@@ -5,9 +5,10 @@
 // balances -- and streams through it:
 //   * the octet is held four times over in the warp (lane = 8*copy + k, atom k of the octet); copy c owns
 //     j slots 8c..8c+7 of the chunk, so a chunk is 8 steps of 32 pairs.  In step s lane (c,k) works on slot
-//     8c + (k+s)%8: every step touches 32 different pairs, the j-force accumulators travel between the 8
-//     lanes of a copy by warp shuffle and are home after 8 steps, so no reduction tree is needed; the four
-//     copies' i forces are summed by shuffle when the octet changes;
+//     8c + (k^s): every step touches 32 different pairs and the slot's address is the lane's own address
+//     XOR a constant; the j-force accumulators follow their slot between the 8 lanes of a copy by butterfly
+//     shuffles (lane masks s^(s+1), then 7) and are home after 8 steps, so no reduction tree is needed; the
+//     four copies' i forces are summed by shuffle when the octet changes;
 //   * a chunk's j atoms (position+charge, parameters, block centre) are gathered two chunks ahead: the list
 //     entry by a plain load, the atom data by cp.async straight into the other half of a double-buffered
 //     shared-memory stage, so the gather's two dependent global-memory latencies hide behind the pair
@@ -48,10 +49,14 @@ template <> struct Real<float> {
         return y*fmaf(-0.5f*r2, y*y, 1.5f);
     }
     static __device__ __forceinline__ float expNeg(float x) { return fastExp2(-1.4426950408889634f*x); }    // exp(-x)
-    // ex = exp(-alpha^2 r^2), erfcAR = erfc(alpha r): one MUFU.EX2, one MUFU.RCP, ten FMAs
-    static __device__ __forceinline__ void erfcTerms(const DirectConsts<float>& c, float r, float r2, float& ex, float& erfcAR) {
-        ex = fastExp2(r2*c.negAlpha2Log2e);
-        erfcAR = ex*erfcxPolyT(fastRcp(fmaf(r, c.halfAlpha, 1.0f)));
+    // Ewald direct-space Coulomb term (one MUFU.EX2, one MUFU.RCP, twelve FMA-pipe instructions): energy
+    // qq erfc(ar)/r and (dE/dr) r = qq/r (erfc(ar) + 2 a r/sqrt(pi) exp(-a^2 r^2)), with the common factor
+    // qq/r exp(-a^2 r^2) taken out of both (erfc = exp(-x^2) erfcx)
+    static __device__ __forceinline__ void ewaldCoulomb(const DirectConsts<float>& c, float r, float r2, float qqr, float& ec, float& fc) {
+        const float g = qqr*fastExp2(r2*c.negAlpha2Log2e);
+        const float p = erfcxPolyT(fastRcp(fmaf(r, c.halfAlpha, 1.0f)));
+        ec = g*p;
+        fc = g*fmaf(c.twoAlphaOverSqrtPi, r, p);
     }
     static __device__ __forceinline__ float rint(float x) { return rintf(x); }
     static __device__ __forceinline__ long long fixed(float f) { return toFixed(f); }
@@ -63,9 +68,10 @@ template <> struct Real<double> {
     static __device__ __forceinline__ const DirectConsts<double>& consts(const DirectArgs& a) { return a.cd; }
     static __device__ __forceinline__ double rsqrt(double r2) { return 1.0/sqrt(r2); }
     static __device__ __forceinline__ double expNeg(double x) { return exp(-x); }
-    static __device__ __forceinline__ void erfcTerms(const DirectConsts<double>& c, double r, double r2, double& ex, double& erfcAR) {
-        ex = exp(-c.alpha2*r2);
-        erfcAR = erfc(c.alpha*r);
+    static __device__ __forceinline__ void ewaldCoulomb(const DirectConsts<double>& c, double r, double r2, double qqr, double& ec, double& fc) {
+        const double erfcAR = erfc(c.alpha*r);
+        ec = qqr*erfcAR;
+        fc = qqr*fma(c.twoAlphaOverSqrtPi*r, exp(-c.alpha2*r2), erfcAR);
     }
     static __device__ __forceinline__ double rint(double x) { return ::rint(x); }
     static __device__ __forceinline__ long long fixed(double f) { return toFixedD(f); }
@@ -93,11 +99,12 @@ __device__ __forceinline__ unsigned opaque(unsigned x) {
     asm volatile("mov.u32 %0, %0;" : "+r"(x));
     return x;
 }
-// One stage buffer: pos[32] | prm[32] | ctr[32] (float4 block centres) | aux[32] (int2: j, mask); slot
-// stride = sizeof(vec4) for pos/prm, 16 for ctr, 8 for aux.
+// One stage buffer: pos[32] | prm[32] | ctr[32] (float4 block centres) | aux[32] (j, mask, -, -); slot
+// stride = sizeof(vec4) for pos/prm, 16 for ctr and aux (in single precision every section of a slot then
+// sits at a constant offset from the slot's position: one address per step).
 template <typename R> struct Stage;
 template <> struct Stage<float> {
-    enum { STRIDE = 16, PRM = 512, CTR = 1024, AUX = 1536, BYTES = 1792 };
+    enum { STRIDE = 16, PRM = 512, CTR = 1024, AUX = 1536, AUXS = 16, BYTES = 2048 };
     static __device__ __forceinline__ float4 ld4(unsigned ad) {
         float4 v;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ad) : "memory");
@@ -108,7 +115,7 @@ template <> struct Stage<float> {
     }
 };
 template <> struct Stage<double> {
-    enum { STRIDE = 32, PRM = 1024, CTR = 2048, AUX = 2560, BYTES = 2816 };
+    enum { STRIDE = 32, PRM = 1024, CTR = 2048, AUX = 2560, AUXS = 16, BYTES = 3072 };
     static __device__ __forceinline__ double4 ld4(unsigned ad) {
         double4 v;
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ad) : "memory");
@@ -148,13 +155,8 @@ __device__ __forceinline__ void pairMath(const DirectConsts<R>& c, R r2, R qq, R
     const R invR = Real<R>::rsqrt(r2);
     invR2 = invR*invR;
     const R r = r2*invR;
-    if (KIND == KIND_EWALD || KIND == KIND_LJPME) {
-        R ex, erfcAR;
-        Real<R>::erfcTerms(c, r, r2, ex, erfcAR);
-        const R qqr = qq*invR;
-        ec = qqr*erfcAR;
-        fc = qqr*fma(c.twoAlphaOverSqrtPi*r, ex, erfcAR);
-    }
+    if (KIND == KIND_EWALD || KIND == KIND_LJPME)
+        Real<R>::ewaldCoulomb(c, r, r2, qq*invR, ec, fc);
     else if (KIND == KIND_RF) {
         ec = qq*(invR+c.krf*r2-c.crf);
         fc = qq*(invR-c.twoKrf*r2);
@@ -168,8 +170,9 @@ __device__ __forceinline__ void pairMath(const DirectConsts<R>& c, R r2, R qq, R
     R s2 = sig*invR;
     s2 *= s2;
     const R s6 = s2*s2*s2;
-    fv = eps*(12*s6-6)*s6;
-    ev = eps*(s6-1)*s6;
+    const R es6 = eps*s6;
+    fv = es6*fma((R) 12, s6, (R) -6);      // eps (12 s^12 - 6 s^6)
+    ev = fma(es6, s6, -es6);               // eps (s^12 - s^6)
     if (KIND == KIND_LJPME) {
         const R c6 = c6I*c6J;
         const R dar2 = c.dalpha2*r2, dar4 = dar2*dar2;
@@ -217,10 +220,10 @@ static __device__ __noinline__ void bandPairs(DirectOut o, DirectConsts<R> c, un
     while (bandMask) {
         const int s = __ffs(bandMask)-1;
         bandMask &= bandMask-1;
-        const int slot = (copy<<3)|((k+s)&7);
+        const int slot = (copy<<3)|(k^s);
         const vec4 q = *(const vec4*) (stage+slot*Stage<R>::STRIDE);
         const vec4 prm = *(const vec4*) (stage+Stage<R>::PRM+slot*Stage<R>::STRIDE);
-        const int j = *(const int*) (stage+Stage<R>::AUX+slot*8);
+        const int j = *(const int*) (stage+Stage<R>::AUX+slot*Stage<R>::AUXS);
         const int origJ = o.sortedAtom[j];
         if (!exactInRange(o.posd, origI, origJ, &o.sp->exact))
             continue;
@@ -264,6 +267,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     constexpr bool TWO = NSUB == 2;         // subsets 0/1 travel as the floats 0.0/1.0: lambdas and energies by FMA
     constexpr int STEP_UNROLL = DIRECT_UNROLL;
     constexpr bool BRANCHY = sizeof(R) == 8 || NSUB == 0;   // double precision: skip the arithmetic of masked lanes
+    // Ewald/PME without switching: a masked lane computes on r^2 = 1e10 nm^2, where exp(-a^2 r^2) = 0 kills the
+    // Coulomb term exactly and the Lennard-Jones force is ~1e-43 of a real one -- nothing to select away
+    constexpr bool SELF_MASKING = !BRANCHY && KIND == KIND_EWALD && !SWITCH;
     typedef typename Real<R>::vec4 vec4;
     typedef Stage<R> St;
     // one warp per CTA: the two stage buffers are addressed by the slot alone
@@ -284,10 +290,10 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     const R bAx = (R) boxd.ax, bBy = (R) boxd.by, bCz = (R) boxd.cz;
     const R iAx = (R) (1.0/boxd.ax), iBy = (R) (1.0/boxd.by), iCz = (R) (1.0/boxd.cz);
     const unsigned kBit = opaque(1u<<k);
-    const int srcLane = (int) opaque((unsigned) ((copy<<3)|((k+1)&7)));     // the j accumulators move one lane down inside the copy
     const unsigned stageBase = opaque((unsigned) __cvta_generic_to_shared(&sStage[0][0]));
-    // slot of step s = 8*copy + (k+s)%8: address = copyBase | ((kOff + s*STRIDE) & (7*STRIDE)), two instructions
-    const unsigned copyOff = opaque((copy<<3)*St::STRIDE), kOff = opaque(k*St::STRIDE);
+    // slot of step s = 8*copy + (k^s): address = (buffer + own slot) ^ (s*STRIDE), one instruction (the buffers
+    // are aligned to 8 slots, so the XOR never carries out of the copy's eight slots)
+    const unsigned ownOff = opaque((unsigned) lane*St::STRIDE);
     // slice energies of this thread over all its chunks, keyed by (own subset, j subset), kept in shared
     // memory (touched once per octet; registers are worth more in the pair loop); reduced over the warp once
     constexpr int NA = NS > 4 ? 1 : NS;
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             cpAsync16(dst+St::PRM+lane*St::STRIDE+b, qs+b);
         }
         cpAsync16(dst+St::CTR+lane*16, a.blockCenter+(j>>5));
-        stSharedV2U32(dst+St::AUX+lane*8, (unsigned) ent.x, (unsigned) ent.y);
+        stSharedV2U32(dst+St::AUX+lane*St::AUXS, (unsigned) ent.x, (unsigned) ent.y);
         cpAsyncCommit();
     };
 
@@ -431,17 +437,16 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
 #pragma unroll
         for (int s = 0; s < NS; s++)
             t.eC[s] = t.eV[s] = 0;
-        const unsigned copyBase = sb+copyOff;
+        const unsigned own = sb+ownOff;
         // ---- 8 steps of 32 pairs: straight-line code (the rare per-pair-wrapping octets take their own copy) ----
         auto steps = [&](auto perPairTag) {
         constexpr bool PERPAIR = decltype(perPairTag)::value;
 #pragma unroll STEP_UNROLL
         for (int s = 0; s < 8; s++) {
-            const unsigned so = (kOff+s*St::STRIDE)&(7*St::STRIDE);
-            const unsigned ad = copyBase+so;
-            const unsigned slot = (copyOff+so)/St::STRIDE;
+            const unsigned ad = own^(unsigned) (s*St::STRIDE);
+            const unsigned aux = St::STRIDE == St::AUXS ? ad+St::AUX : sb+St::AUX+(unsigned) (lane^s)*St::AUXS;
             const vec4 q = St::ld4(ad);
-            const unsigned mj = ldSharedU32(sb+St::AUX+slot*8+4);
+            const unsigned mj = ldSharedU32(aux+4);
             R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
             if (PBC == PBC_SHIFT && PERPAIR) {
                 dx -= bAx*Real<R>::rint(dx*iAx);
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 const vec4 prm = St::ld4(ad+St::PRM);
                 R fc, fv, ec, ev, invR2;
                 // masked lanes compute on r^2 = 1 (self pairs have r = 0, excluded neighbours overflow r^-12)
-                pairMath<R, KIND, SWITCH>(c, BRANCHY ? r2 : (in ? r2 : (R) 1), pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
+                pairMath<R, KIND, SWITCH>(c, BRANCHY ? r2 : (in ? r2 : (R) (SELF_MASKING ? 1e10 : 1)), pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
                 R lc, lv;
                 if (NSUB == 1) {
                     lc = t.lamC[0]; lv = t.lamV[0];
@@ -494,7 +499,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                     lc = (R) a.sp->lambdaC[sl]; lv = (R) a.sp->lambdaV[sl];
                 }
                 R f = (lv*fv+lc*fc)*invR2;
-                if (!BRANCHY) {
+                if (!BRANCHY && !SELF_MASKING) {
                     f = in ? f : (R) 0;
                     ec = in ? ec : (R) 0;
                     ev = in ? ev : (R) 0;
@@ -521,15 +526,17 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                     }
                 }
                 if (DUMP && in) {
-                    const int origJ = a.sortedAtom[(int) ldSharedU32(sb+St::AUX+slot*8)];
+                    const int origJ = a.sortedAtom[(int) ldSharedU32(aux)];
                     unsigned long long idx = atomicAdd(a.pairDumpCount, 1ull);
                     if ((long long) idx < a.pairDumpCapacity)
                         a.pairDump[idx] = make_int2(min(origI, origJ), max(origI, origJ));
                 }
             }
-            fjx = __shfl_sync(full, fjx, srcLane);
-            fjy = __shfl_sync(full, fjy, srcLane);
-            fjz = __shfl_sync(full, fjz, srcLane);
+            // the accumulators follow their slot: to the lane that takes it in the next step (home after the last)
+            const int hop = s == 7 ? 7 : s^(s+1);
+            fjx = __shfl_xor_sync(full, fjx, hop);
+            fjy = __shfl_xor_sync(full, fjy, hop);
+            fjz = __shfl_xor_sync(full, fjz, hop);
         }
         };
         if (PBC == PBC_SHIFT && perPair)

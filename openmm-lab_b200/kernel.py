@@ -132,7 +132,8 @@ class CalcSlicedNonbondedForceKernel:
 
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libslicednb_b200.so")
+# SNB_B200_LIB: another build of the same CUDA core (kernel-tuning experiments, see build.py SNB_LIB_TAG)
+LIB_PATH = os.environ.get("SNB_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libslicednb_b200.so")
 
 
 def load_library():

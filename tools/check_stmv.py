@@ -38,6 +38,11 @@ def main():
             failures.append(str(e))
     ref = evaluate("Reference", w)
     t_ref = time.time()-t0
+    # the oracle's neighbour list of that evaluation: its size (oracle/harness.cpp snb_oracle_count_pairs)
+    import ctypes
+    count = ref["kernel"]._lib.snb_oracle_count_pairs
+    count.restype, count.argtypes = ctypes.c_longlong, [ctypes.c_void_p]
+    pairs_ref = int(count(ref["kernel"]._handle))
     dF = ref["forces"]-got["forces"]
     rmsF = np.sqrt((ref["forces"]**2).sum(axis=1).mean())
     gross = np.abs(ref["slices"]).sum()
