@@ -731,6 +731,7 @@ PmeArgs pmeArgs(snb_handle& h, int term, bool sorted) {
 
 template <typename R> void fillConsts(DirectConsts<R>& c, const DirectParams& p) {
     c.cutoffHi = (R) (p.cutoff2d+p.bandTol); c.cutoffLo = (R) (p.cutoff2d-p.bandTol);
+    c.cutoffHiWide = (R) (p.cutoff2d+p.bandTolWide); c.cutoffLoWide = (R) (p.cutoff2d-p.bandTolWide);
     c.alpha = (R) p.alphad; c.alpha2 = (R) (p.alphad*p.alphad); c.halfAlpha = (R) (0.5*p.alphad);
     c.negAlpha2Log2e = (R) (-p.alphad*p.alphad*1.4426950408889634);
     c.twoAlphaOverSqrtPi = (R) (2.0*p.alphad/1.772453850905516);
@@ -862,7 +863,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         DirectParams& p = da.p;
         p.numAtoms = h.N; p.numBlocks = h.NB; p.pbcMode = in.pbcMode; p.periodic = periodic;
         p.cutoff2d = h.cutoff*h.cutoff;
-        p.bandTol = (float) (4e-5*h.cutoff*h.cutoff);
+        p.bandTolWide = (float) (4e-5*h.cutoff*h.cutoff);
+        p.bandTol = (float) fmin((double) p.bandTolWide, 2.0e-6*h.cutoff+1.0e-6*h.cutoff*h.cutoff);    // ~4x the error bound
         p.alphad = h.alpha;
         p.krfd = pow(h.cutoff, -3.0)*(h.rfDielectric-1.0)/(2.0*h.rfDielectric+1.0);
         p.crfd = (1.0/h.cutoff)*(3.0*h.rfDielectric)/(2.0*h.rfDielectric+1.0);

@@ -136,6 +136,12 @@ __device__ __forceinline__ float4 ldSharedF4(unsigned ad) {
 __device__ __forceinline__ void cpAsync16(unsigned dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cpAsync8(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpAsync4(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ unsigned ldSharedU32(unsigned ad) {
@@ -193,6 +199,81 @@ __device__ __forceinline__ void pairMath(const DirectConsts<R>& c, R r2, R qq, R
         fv = sw*fv-ev*dsw*r;
         ev *= sw;
     }
+}
+
+// Box lengths (and, for triclinic boxes, the off-diagonal components) the wrapping needs, in registers.  The image
+// shift of the fix-up pass uses every length as hi + lo: hi on the block centres' 2^-10 nm lattice, lo the remainder.
+template <typename R> struct WrapBox {
+    R ax, by, cz, iax, iby, icz, bx, cx, cy;
+    R axHi, byHi, czHi, axLo, byLo, czLo;
+};
+template <typename R> __device__ __forceinline__ WrapBox<R> makeWrapBox(const BoxD& b) {
+    WrapBox<R> w;
+    w.ax = (R) b.ax; w.by = (R) b.by; w.cz = (R) b.cz;
+    w.iax = (R) (1.0/b.ax); w.iby = (R) (1.0/b.by); w.icz = (R) (1.0/b.cz);
+    w.bx = (R) b.bx; w.cx = (R) b.cx; w.cy = (R) b.cy;
+    const double hx = rint(b.ax*1024.0)*(1.0/1024.0), hy = rint(b.by*1024.0)*(1.0/1024.0), hz = rint(b.cz*1024.0)*(1.0/1024.0);
+    w.axHi = (R) hx; w.byHi = (R) hy; w.czHi = (R) hz;
+    w.axLo = (R) (b.ax-hx); w.byLo = (R) (b.by-hy); w.czLo = (R) (b.cz-hz);
+    return w;
+}
+// Displacement j -> i of one pair and its squared length.  Every rounding is pinned (explicit intrinsics are never
+// re-contracted), because the pair loop and the band path both classify a pair from this r^2 and must agree
+// bit for bit.  WRAP: 0 none (the staged j atom already is the right image), 1 orthorhombic per pair, 2 triclinic.
+template <int WRAP> __device__ __forceinline__ float pairDelta(const float4& pi, const float4& q, const WrapBox<float>& w, float& dx, float& dy, float& dz) {
+    dx = __fsub_rn(pi.x, q.x); dy = __fsub_rn(pi.y, q.y); dz = __fsub_rn(pi.z, q.z);
+    if (WRAP == 1) {
+        dx = __fmaf_rn(-w.ax, rintf(__fmul_rn(dx, w.iax)), dx);
+        dy = __fmaf_rn(-w.by, rintf(__fmul_rn(dy, w.iby)), dy);
+        dz = __fmaf_rn(-w.cz, rintf(__fmul_rn(dz, w.icz)), dz);
+    }
+    else if (WRAP == 2) {
+        float m = rintf(__fmul_rn(dz, w.icz));
+        dx = __fmaf_rn(-m, w.cx, dx); dy = __fmaf_rn(-m, w.cy, dy); dz = __fmaf_rn(-m, w.cz, dz);
+        m = rintf(__fmul_rn(dy, w.iby));
+        dx = __fmaf_rn(-m, w.bx, dx); dy = __fmaf_rn(-m, w.by, dy);
+        m = rintf(__fmul_rn(dx, w.iax));
+        dx = __fmaf_rn(-m, w.ax, dx);
+    }
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+template <int WRAP> __device__ __forceinline__ double pairDelta(const double4& pi, const double4& q, const WrapBox<double>& w, double& dx, double& dy, double& dz) {
+    dx = __dsub_rn(pi.x, q.x); dy = __dsub_rn(pi.y, q.y); dz = __dsub_rn(pi.z, q.z);
+    if (WRAP == 1) {
+        dx = __fma_rn(-w.ax, rint(__dmul_rn(dx, w.iax)), dx);
+        dy = __fma_rn(-w.by, rint(__dmul_rn(dy, w.iby)), dy);
+        dz = __fma_rn(-w.cz, rint(__dmul_rn(dz, w.icz)), dz);
+    }
+    else if (WRAP == 2) {
+        double m = rint(__dmul_rn(dz, w.icz));
+        dx = __fma_rn(-m, w.cx, dx); dy = __fma_rn(-m, w.cy, dy); dz = __fma_rn(-m, w.cz, dz);
+        m = rint(__dmul_rn(dy, w.iby));
+        dx = __fma_rn(-m, w.bx, dx); dy = __fma_rn(-m, w.by, dy);
+        m = rint(__dmul_rn(dx, w.iax));
+        dx = __fma_rn(-m, w.ax, dx);
+    }
+    return __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+}
+
+// Fix-up of one staged j atom: from its own block's frame into the i block's, and -- `image` -- onto the periodic
+// image nearest the octet's centre (valid while halfBox - cutoff exceeds the octet's half extent; the list build
+// flags the other octets for per-pair wrapping).  Block centres sit on a 2^-10 nm lattice, and so does the hi part
+// of every box length: centre difference - m*hi is EXACT in float (an integer below 2^24 over 1024), a few nm at most
+// for any pair near the cutoff, so adding it to the local coordinate rounds at that magnitude only; m*lo (below
+// 2^-11 nm per image) follows by FMA.  r^2 thus keeps an absolute error of ~5e-7 nm^2 whatever the box size, which
+// is what the narrow cutoff band relies on.
+template <typename R> __device__ __forceinline__ void fixupShift(typename Real<R>::vec4& pj, const float4& cJ, const float4& cI, const float4& oc,
+                                                                 bool image, const WrapBox<R>& wb) {
+    const R sx = (R) (cJ.x-cI.x), sy = (R) (cJ.y-cI.y), sz = (R) (cJ.z-cI.z);
+    if (!image) {
+        pj.x += sx; pj.y += sy; pj.z += sz;
+        return;
+    }
+    const R mx = Real<R>::rint((pj.x+sx-(R) oc.x)*wb.iax), my = Real<R>::rint((pj.y+sy-(R) oc.y)*wb.iby),
+            mz = Real<R>::rint((pj.z+sz-(R) oc.z)*wb.icz);
+    pj.x = fma(-mx, wb.axLo, pj.x+fma(-mx, wb.axHi, sx));
+    pj.y = fma(-my, wb.byLo, pj.y+fma(-my, wb.byHi, sy));
+    pj.z = fma(-mz, wb.czLo, pj.z+fma(-mz, wb.czHi, sz));
 }
 
 // what the rare out-of-line paths need, by value (taking the address of the kernel's parameter block
@@ -261,6 +342,49 @@ static __device__ __noinline__ void bandPairs(DirectOut o, DirectConsts<R> c, un
     }
 }
 
+// (packed kernel, direct_packed.cu)  The pairs of one chunk that fell inside the band around the cutoff: the pair loop only
+// notes that there is one; here the lane finds them again (same r^2, bit for bit: pairDelta), decides each exactly,
+// evaluates it and adds it with atomics, so that the pair loop itself carries neither a call nor a per-step flag.
+template <typename R, int KIND, int PBC, bool ENERGY, bool DUMP, bool SWITCH>
+static __device__ __noinline__ void bandRescan(DirectOut o, DirectConsts<R> c, int lane, int ki, int origI, R cutLo, R cutHi,
+                                              typename Real<R>::vec4 pi, typename Real<R>::vec4 si4, int perPair, const unsigned char* stage) {
+    typedef typename Real<R>::vec4 vec4;
+    const int copy = lane>>3, k = lane&7;
+    const WrapBox<R> wb = makeWrapBox<R>(o.sp->exact.boxd);
+    for (int s = 0; s < 8; s++) {
+        const int slot = (copy<<3)|(k^s);
+        const vec4 q = *(const vec4*) (stage+slot*Stage<R>::STRIDE);
+        const int2 aux = *(const int2*) (stage+Stage<R>::AUX+slot*Stage<R>::AUXS);
+        R dx, dy, dz, r2;
+        if (PBC == PBC_PAIR_TRICLINIC) r2 = pairDelta<2>(pi, q, wb, dx, dy, dz);
+        else if (PBC == PBC_SHIFT && perPair) r2 = pairDelta<1>(pi, q, wb, dx, dy, dz);
+        else r2 = pairDelta<0>(pi, q, wb, dx, dy, dz);
+        if (((unsigned) aux.y>>k)&1u || r2 < cutLo || !(r2 < cutHi))
+            continue;
+        const vec4 prm = *(const vec4*) (stage+Stage<R>::PRM+slot*Stage<R>::STRIDE);
+        const int j = aux.x;
+        const int origJ = o.sortedAtom[j];
+        if (!exactInRange(o.posd, origI, origJ, &o.sp->exact))
+            continue;
+        R fc, fv, ec, ev, invR2;
+        pairMath<R, KIND, SWITCH>(c, r2, pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
+        const int slice = sliceOf((int) si4.z, (int) prm.z);
+        const R f = ((R) o.sp->lambdaV[slice]*fv+(R) o.sp->lambdaC[slice]*fc)*invR2;
+        const long long fx = Real<R>::fixed(f*dx), fy = Real<R>::fixed(f*dy), fz = Real<R>::fixed(f*dz);
+        addFixed(&o.forceSorted[ki], fx); addFixed(&o.forceSorted[o.paddedAtoms+ki], fy); addFixed(&o.forceSorted[2*o.paddedAtoms+ki], fz);
+        addFixed(&o.forceSorted[j], -fx); addFixed(&o.forceSorted[o.paddedAtoms+j], -fy); addFixed(&o.forceSorted[2*o.paddedAtoms+j], -fz);
+        if (ENERGY) {
+            atomicAdd(&o.energyTable[2*slice], (double) ec);
+            atomicAdd(&o.energyTable[2*slice+1], (double) ev);
+        }
+        if (DUMP) {
+            unsigned long long idx = atomicAdd(o.pairDumpCount, 1ull);
+            if ((long long) idx < o.pairDumpCapacity)
+                o.pairDump[idx] = make_int2(min(origI, origJ), max(origI, origJ));
+        }
+    }
+}
+
 template <typename R, int KIND, int PBC, int NSUB, bool ENERGY, bool DUMP, bool SWITCH>
 __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? DIRECT_CTAS_PER_SM/2 : DIRECT_CTAS_PER_SM) : 8) k_direct(DirectArgs a) {
     constexpr int NS = NSUB > 0 ? NSUB : SNB_MAX_SUBSETS;
@@ -289,6 +413,11 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     const BoxD boxd = a.sp->exact.boxd;
     const R bAx = (R) boxd.ax, bBy = (R) boxd.by, bCz = (R) boxd.cz;
     const R iAx = (R) (1.0/boxd.ax), iBy = (R) (1.0/boxd.by), iCz = (R) (1.0/boxd.cz);
+    const WrapBox<R> wb = makeWrapBox<R>(boxd);
+    // cutoff band (snb_core.cuh DirectParams): narrow where the j atoms reach the octet's frame through the exact image
+    // shift of the fix-up pass, wide for per-pair wrapping and when some block of this evaluation is large
+    const bool narrowOk = PBC != PBC_PAIR_TRICLINIC && !(__int_as_float(a.counters[SNB_COUNTER_MAX_EXTENT]) > SNB_NARROW_MAX_EXTENT);
+    const R bandHi = narrowOk ? c.cutoffHi : c.cutoffHiWide, bandLo = narrowOk ? c.cutoffLo : c.cutoffLoWide;
     const unsigned kBit = opaque(1u<<k);
     const unsigned stageBase = opaque((unsigned) __cvta_generic_to_shared(&sStage[0][0]));
     // slot of step s = 8*copy + (k^s): address = (buffer + own slot) ^ (s*STRIDE), one instruction (the buffers
@@ -405,8 +534,6 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             origI = a.sortedAtom[ki];
             cI = a.blockCenter[O>>2];
             oc = a.octetCenter[O];
-            // a padding lane can never be "in range": its bounds are negative
-            myCutHi = iValid ? c.cutoffHi : (R) -1; myCutLo = iValid ? c.cutoffLo : (R) -1;
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 const int sl = sliceOf(max(subI, 0), s);
@@ -416,18 +543,14 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             if (TWO) { dLamC = t.lamC[1]-t.lamC[0]; dLamV = t.lamV[1]-t.lamV[0]; }
         }
         perPair = PBC == PBC_SHIFT && (octCur&0x40000000) != 0;     // octet too wide for one image per j atom
+        // a padding lane can never be "in range": its bounds are negative
+        myCutHi = iValid ? (perPair ? c.cutoffHiWide : bandHi) : (R) -1;
+        myCutLo = iValid ? (perPair ? c.cutoffLoWide : bandLo) : (R) -1;
         // ---- fix-up: the staged j atom of this lane moves into the octet's block frame
         {
             vec4 pj = St::ld4(sb+lane*St::STRIDE);
             const float4 cJ = ldSharedF4(sb+St::CTR+lane*16);
-            pj.x += (R) (cJ.x-cI.x); pj.y += (R) (cJ.y-cI.y); pj.z += (R) (cJ.z-cI.z);
-            if (PBC == PBC_SHIFT && !perPair) {
-                // one image per j atom, chosen relative to the octet's centre (valid while
-                // halfBox - cutoff exceeds the octet's half extent; the list build flags the rest)
-                pj.x -= bAx*Real<R>::rint((pj.x-(R) oc.x)*iAx);
-                pj.y -= bBy*Real<R>::rint((pj.y-(R) oc.y)*iBy);
-                pj.z -= bCz*Real<R>::rint((pj.z-(R) oc.z)*iCz);
-            }
+            fixupShift<R>(pj, cJ, cI, oc, PBC == PBC_SHIFT && !perPair, wb);
             St::st4(sb+lane*St::STRIDE, pj);
         }
         __syncwarp();

@@ -27,6 +27,8 @@
 #define SNB_BLOCK 32
 #define SNB_FORCE_SCALE 4294967296.0f       /* 2^32, as the reference's fixed-point forces (realToFixedPoint.cu:1-2) */
 #define SNB_FORCE_SCALE_D 4294967296.0
+#define SNB_NARROW_MAX_EXTENT 1.0f         /* nm: largest block half extent for which the narrow cutoff band is valid */
+#define SNB_COUNTER_MAX_EXTENT 5            /* counters[]: float bits of the largest block half extent of this evaluation */
 
 enum { PBC_NONE = 0, PBC_SHIFT = 1, PBC_PAIR_ORTHO = 2, PBC_PAIR_TRICLINIC = 3 };
 enum { KIND_PLAIN = 0, KIND_RF = 1, KIND_EWALD = 2, KIND_LJPME = 3 };
@@ -42,7 +44,11 @@ struct BoxD {
 
 struct DirectParams {
     int numAtoms, numBlocks, pbcMode, periodic;
-    float bandTol;                      // |r2 - cutoff2| < bandTol -> exact double predicate
+    // |r2 - cutoff2| < band -> the exact double predicate decides.  Narrow band: j atoms brought into the octet's frame
+    // with the periodic image taken in double (fix-up pass), every coordinate < ~2 nm: |error(r2)| < 5.2e-7 rc + 1.5e-7 rc^2.
+    // Wide band: per-pair wrapping in single precision (triclinic boxes, octets wider than halfBox - cutoff) or blocks
+    // wider than SNB_NARROW_MAX_EXTENT, where the error grows with the box / block size.
+    float bandTol, bandTolWide;
     double cutoff2d;
     double alphad, krfd, crfd, switchDistd, invSwitchWidthd;
     double dalphad, dispShiftExpd, invCut6d;   // LJPME: alpha_d, [1-exp(-d_c^2)(1+d_c^2+d_c^4/2)], rc^-6
@@ -52,6 +58,7 @@ struct DirectParams {
 // kernel-parameter constant bank and are used as instruction operands (no in-loop conversions).
 template <typename R> struct DirectConsts {
     R cutoffHi, cutoffLo;               // cutoff^2 +- band: inside the band the exact double predicate decides
+    R cutoffHiWide, cutoffLoWide;       // the wider band of chunks whose r^2 carries box-sized rounding errors (see bandTol)
     R alpha, alpha2, halfAlpha, negAlpha2Log2e, twoAlphaOverSqrtPi;
     R krf, crf, twoKrf;
     R switchDist, invSwitchWidth;

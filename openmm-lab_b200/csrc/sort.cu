@@ -246,8 +246,13 @@ __global__ void k_blockBounds(SortArgs a) {
     if (lane == 0) {
         a.blockCenter[warp] = make_float4((float) c[0], (float) c[1], (float) c[2], 0.f);
         // half extents, rounded up so the box is conservative in single precision
-        a.blockExt[warp] = make_float4(__double2float_ru(0.5*(hi[0]-lo[0])), __double2float_ru(0.5*(hi[1]-lo[1])),
+        const float4 ext = make_float4(__double2float_ru(0.5*(hi[0]-lo[0])), __double2float_ru(0.5*(hi[1]-lo[1])),
                                        __double2float_ru(0.5*(hi[2]-lo[2])), 0.f);
+        a.blockExt[warp] = ext;
+        // the direct-space kernels widen their cutoff band when some block is large (block-local coordinates lose bits)
+        const float widest = fmaxf(ext.x, fmaxf(ext.y, ext.z));
+        if (widest > SNB_NARROW_MAX_EXTENT)
+            atomicMax(&a.counters[SNB_COUNTER_MAX_EXTENT], __float_as_int(widest));
     }
     // bounding boxes of the four octets (8 consecutive atoms) of the block, in block-local coordinates:
     // the i side of the tile list works on octets (a tighter box => fewer out-of-range pairs per tile)
