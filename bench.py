@@ -16,10 +16,17 @@ reference kernel does (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:193
   roofline  direct-space tile kernel: algorithmic flop (67 per interacting pair)
             / its CUDA-event duration, against the FP32 FMA peak (non-tensor path); the
             memory-bound PME kernels are listed against the measured HBM peak in "kernels"
-  N > 1     ONE evaluation is shared by all ranks: tile list and exceptions partitioned,
-            reciprocal space on rank 0, positions broadcast and fixed-point forces reduced by
-            NCCL ("scaling": "strong")
-  stmv      the same measurement on the STMV-size workload (BASELINE.json configs[4]), a few steps
+  N > 1     --multi partition: ONE evaluation is shared by all ranks -- tile list and exceptions
+            partitioned, reciprocal space on rank 0, fixed-point forces + slice energies all-reduced
+            by NCCL ("scaling": "strong"); the path BASELINE.json asks for on LARGE systems (STMV).
+            --multi replicas: every rank evaluates its own copy of the workload (the lambda windows
+            of an alchemical calculation, one per GPU), no collective ("scaling": "weak").
+            --multi auto (default): partition at >= 200 000 atoms, replicas below -- a 23 558-atom
+            evaluation is launch/latency bound (145 us) and sharing it between GPUs makes it SLOWER
+            (measured 0.86x at N=2); the line then also carries the partitioned number
+            ("partitioned") so that both are on record.
+  stmv      the same measurement on the STMV-size workload (BASELINE.json configs[4]), a few steps,
+            always partitioned for N > 1
   cpu_baseline / --impl reference: the reference's own Reference-platform sources (oracle/_ref,
             compiled unchanged) timed on the host cores -- the one place bench.py executes oracle/.
 """
@@ -117,22 +124,58 @@ def cpu_reference(w, seconds_budget=20.0, max_evals=3):
                       % (len(times), w.name), "seconds_per_eval": med, "host_cores_available": os.cpu_count()}
 
 
+def _reference_worker(name, evals, queue):
+    w = make_workload(name)
+    base = cpu_reference(w, seconds_budget=1e9, max_evals=evals)
+    queue.put((base["seconds_per_eval"], base["kind"]))
+
+
+def cpu_reference_all_cores(name, evals):
+    """The Reference platform is serial; a host with C cores can still run C independent evaluations at once (the
+    lambda windows of an alchemical calculation).  C worker processes, `evals` evaluations each, aggregate rate."""
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    ctx = mp.get_context("fork")
+    queue = ctx.Queue()
+    t0 = time.time()
+    procs = [ctx.Process(target=_reference_worker, args=(name, evals, queue)) for _ in range(cores)]
+    for p in procs:
+        p.start()
+    got = [queue.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.time()-t0
+    med = sorted(g[0] for g in got)[len(got)//2]
+    # the rate while all workers evaluate (workload construction excluded: each worker's own median time per evaluation)
+    return {"value": cores/med, "unit": "evals/s", "cores": cores, "kind": got[0][1],
+            "sample": "%d worker processes x %d full evaluation(s) of %s each (neighbour list + direct + PME + exceptions), one per core; "
+                      "rate = workers / median seconds per evaluation under that load" % (cores, evals, name),
+            "seconds_per_eval": med, "wall_seconds": wall, "host_cores_available": os.cpu_count()}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = make_workload(args.workload)
-    base = cpu_reference(w, seconds_budget=60.0, max_evals=max(1, min(args.steps, 5)))
+    partition = args.gpus > 1 and (args.multi == "partition" or (args.multi == "auto" and w.num_particles >= PARTITION_MIN_ATOMS))
+    if w.num_particles >= PARTITION_MIN_ATOMS:
+        base = cpu_reference(w, seconds_budget=60.0, max_evals=max(1, min(args.steps, 2)))      # one evaluation takes most of a minute
+    else:
+        base = cpu_reference_all_cores(args.workload, max(1, min(args.steps, 3)))
     line = {"impl": "reference", "metric": "sliced-PME force evaluations/s", "value": base["value"], "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3*base["seconds_per_eval"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_of(w), "cpu_baseline": base,
+            "higher_is_better": True, "scaling": "strong" if partition else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(w, args.gpus, partition), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ns_per_day_2fs": base["value"]*0.1728}
     print(json.dumps(line))
 
 
-def config_of(w, world=1):
+PARTITION_MIN_ATOMS = 200000
+
+
+def config_of(w, world=1, partition=True):
     f = w.force
     alpha, nx, ny, nz = f.getPMEParameters()
     return {"workload": w.name, "atoms": w.num_particles, "subsets": f.getNumSubsets(), "slices": f.getNumSlices(),
@@ -140,8 +183,11 @@ def config_of(w, world=1):
             "scaling_parameters": f.getNumScalingParameters(), "derivatives": f.getNumScalingParameterDerivatives(),
             "evaluation": "forces+energy+derivatives, direct+reciprocal, tile list rebuilt every step",
             "parallelism": "1 GPU" if world == 1 else
-                           "%d ranks share each evaluation: tile list + exceptions partitioned, reciprocal space on rank 0, "
-                           "positions replicated by the caller, one ncclAllReduce(int64) of fixed-point forces + slice energies per evaluation" % world,
+                           ("%d ranks share each evaluation: tile list + exceptions partitioned, reciprocal space on rank 0, "
+                            "positions replicated by the caller, one ncclAllReduce(int64) of fixed-point forces + slice energies per evaluation" % world
+                            if partition else
+                            "%d replicas: every rank evaluates its own copy of the workload, no collective (a %d-atom evaluation is "
+                            "latency bound and does not shard profitably; the partitioned number is reported beside it)" % (world, w.num_particles)),
             "l2": "256 MiB flush write between timed steps; every step rewrites the force/grid/list buffers",
             "timing": "host wall-clock around each synchronised step, max over ranks (CUDA-event time reported as device_ms_per_step)",
             "precision": "mixed (FP32 pair arithmetic, FP64 / 2^32 fixed-point accumulation)"}
@@ -150,7 +196,7 @@ def config_of(w, world=1):
 class Runner:
     """One workload on this rank's GPU (and, for world > 1, its share of every evaluation)."""
 
-    def __init__(self, name, local, rank, world, dist):
+    def __init__(self, name, local, rank, world, dist, partition=True):
         import torch
         import openmmlab_b200 as mm
         from openmmlab_b200 import _abi
@@ -164,7 +210,8 @@ class Runner:
         for k, v in w.parameters.items():
             ctx.setParameter(k, v)
         self.kernel = kernel = ctx._kernels[0][1]
-        if world > 1:
+        self.partition = partition and world > 1
+        if self.partition:
             ident = [kernel.ncclUniqueId() if rank == 0 else None]
             dist.broadcast_object_list(ident, src=0)
             kernel.commInit(ident[0], rank, world)
@@ -229,12 +276,14 @@ class Runner:
         torch, dist = self.torch, self.dist
         t_dev, t_evt = self.timed(self.step_device, steps, warmup, flush)
         acc = self.phases(min(steps, 10), flush)
-        out = {"value": steps/t_dev, "ms_per_step": 1e3*t_dev/steps, "device_ms_per_step": 1e3*t_evt/steps}
+        # evaluations finished per step of the job: one when the ranks share it, one per rank when they run replicas
+        units = 1 if (self.partition or self.world == 1) else self.world
+        out = {"value": units*steps/t_dev, "ms_per_step": 1e3*t_dev/steps, "device_ms_per_step": 1e3*t_evt/steps}
         if e2e:
             t_e2e, _ = self.timed(self.step_host, steps, max(3, warmup), flush)
             n = self.n
-            out["e2e"] = {"value": steps/t_e2e, "unit": "evals/s", "h2d_bytes_per_step": int(n*24), "d2h_bytes_per_step": int(n*24+8*72+32),
-                          "ms_per_step": 1e3*t_e2e/steps}
+            out["e2e"] = {"value": units*steps/t_e2e, "unit": "evals/s", "h2d_bytes_per_step": int(units*n*24),
+                          "d2h_bytes_per_step": int(units*(n*24+8*72+32)), "ms_per_step": 1e3*t_e2e/steps}
         # roofline of the dominant kernel on the slowest rank: its own pairs / its own kernel time
         pairs = self.kernel.countPairs()
         mine = torch.tensor([acc["direct"], float(pairs)], dtype=torch.float64, device="cuda")
@@ -262,7 +311,7 @@ class Runner:
                               "frac_of_hbm_peak": (b/(acc[k]*1e-3)/1e9/hbm) if (hbm and acc[k] > 0) else None}
                           for k, b in bytes_of.items()}
         out["phases_ms"] = acc
-        out["gpu_launches"] = int(self.kernel.getCounters()[2])*steps
+        out["gpu_launches"] = int(self.kernel.getCounters()[2])*steps*units
         return out
 
 
@@ -280,10 +329,22 @@ def run_b200(args):
     flush = torch.empty(256*1024*1024//4, dtype=torch.float32, device="cuda")
     sampler = ClockSampler(local)
     sampler.start()
-    main = Runner(args.workload, local, rank, world, dist)
+    from openmmlab_b200 import systems
+    natoms = systems.WORKLOAD_ATOMS.get(args.workload, 0)
+    partition = world > 1 and (args.multi == "partition" or (args.multi == "auto" and natoms >= PARTITION_MIN_ATOMS))
+    main = Runner(args.workload, local, rank, world, dist, partition=partition)
     res = main.measure(args.steps, args.warmup, flush, peaks)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    shared = None
+    if world > 1 and not partition:
+        # on record beside the replicas: the same evaluation shared by all ranks
+        del main
+        main = Runner(args.workload, local, rank, world, dist, partition=True)
+        shared = main.measure(args.steps, args.warmup, flush, peaks)
+        shared = {k: shared[k] for k in ("value", "ms_per_step", "device_ms_per_step", "e2e", "phases_ms")}
+        shared["scaling"] = "strong"
+        shared["parallelism"] = config_of(main.w, world, True)["parallelism"]
     extra = None
     if not args.no_stmv and args.workload != "stmv":
         w = main.w
@@ -300,12 +361,15 @@ def run_b200(args):
         line = {"metric": "sliced-PME force evaluations/s", "value": value, "unit": "evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
                 "device_ms_per_step": res["device_ms_per_step"], "higher_is_better": True,
-                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_of(main_w, world), "ns_per_day_2fs": value*0.1728, "ns_per_day_4fs": value*0.3456,
+                "scaling": "strong" if partition else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_of(main_w, world, partition), "ns_per_day_2fs": value*0.1728, "ns_per_day_4fs": value*0.3456,
                 "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "kernels": res["kernels"],
                 "phases_ms": res["phases_ms"], "clocks": sampler.summary()}
+        if shared is not None:
+            line["partitioned"] = shared
         if extra is not None:
             extra["ns_per_day_2fs"] = extra["value"]*0.1728
+            extra["scaling"] = "strong" if world > 1 else "weak"
             line["stmv"] = extra
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference(main_w)
@@ -324,6 +388,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stmv", action="store_true")
+    ap.add_argument("--multi", default="auto", choices=["auto", "replicas", "partition"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,7 +12,7 @@
 //   1. marks, in a shared bitmap over the j blocks, the blocks owning atoms of the cells that overlap the
 //      i block's box dilated by the cutoff (cells farther than the cutoff pruned; periodic wrap in
 //      fractional coordinates, so triclinic boxes need nothing special) -- all 128 threads;
-//   2. walks the set bits in ascending order; the candidates are split between the four warps, each of
+//   2. walks the set bits in ascending order; the candidates are split evenly between the four warps, each of
 //      which loads a candidate block's 32 atoms ONCE (four candidates in flight) and tests them against
 //      all four octet boxes (one ballot -> one 32-bit word of interaction flags per octet);
 //   3. every warp then gathers its own octet's non-empty words, prefix-sums the popcounts, takes a
@@ -332,9 +332,12 @@ __global__ void __launch_bounds__(LIST_WARPS*32) k_buildList(ListArgs a) {
         const int Jbase = w0*32;
         __syncthreads();                    // everyone has read sNc before warp 0 may rewrite it
         for (int c0 = 0; c0 < nc; c0 += TEST_BATCH) {
-            // warp w tests candidates c0 + 32 w .. +31 against all four octet boxes
-            const int kEnd = min(nc, c0+32*w+32);
-            for (int k0 = c0+32*w; k0 < kEnd; k0 += 4) {
+            // the batch is split evenly between the four warps (whole groups of four candidates: four loads in flight);
+            // each tests its candidates against all four octet boxes.  An even split matters: the warps meet at a
+            // barrier after the batch, and most windows hold far fewer than 128 candidates
+            const int nbAll = min(TEST_BATCH, nc-c0), perWarp = ((nbAll+15)>>4)<<2;
+            const int kBeg = c0+w*perWarp, kEnd = min(c0+nbAll, kBeg+perWarp);
+            for (int k0 = kBeg; k0 < kEnd; k0 += 4) {
                 int J[4];
                 float4 pj[4], bc[4];
 #pragma unroll

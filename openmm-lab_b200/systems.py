@@ -264,3 +264,5 @@ def small_mixed(n_side=6, solute_sites=12, method=SlicedNonbondedForce.PME, seed
 
 
 WORKLOADS = {"water": water_box, "dhfr": dhfr_like, "apoa1": apoa1_like, "fep": fep_ligand, "stmv": stmv_like}
+# atom counts, known without building the workload (bench.py picks the multi-GPU mode from them)
+WORKLOAD_ATOMS = {"water": 648, "dhfr": 23558, "apoa1": 92224, "fep": 3000, "stmv": 1066628}
