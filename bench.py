@@ -169,7 +169,7 @@ def run_reference(args):
             "config": config_of(w, args.gpus, partition), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ns_per_day_2fs": base["value"]*0.1728}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 PARTITION_MIN_ATOMS = 200000
@@ -232,7 +232,11 @@ class Runner:
         return self.kernel.readEnergies(self.flags)
 
     def step_host(self):
-        self.ctx._forces = np.zeros((self.n, 3))
+        # the caller's force vector: kept and zeroed every step, as OpenMM's ContextImpl does with its own (the kernel adds into it)
+        if getattr(self, "_forces_host", None) is None:
+            self._forces_host = np.zeros((self.n, 3))
+        self._forces_host.fill(0.0)
+        self.ctx._forces = self._forces_host
         self.ctx._energyParameterDerivatives = {}
         return self.kernel.execute(self.ctx, True, True, True, True)
 
@@ -373,13 +377,18 @@ def run_b200(args):
             line["stmv"] = extra
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference(main_w)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print there (NCCL's version banner, ...)
+    # goes to stderr instead -- file descriptor 1 is pointed at stderr, the JSON line is written to the saved descriptor
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

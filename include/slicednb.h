@@ -73,8 +73,14 @@ enum {
  * Precision = mixed (default) | double, and DeterministicForces. */
 enum {
     SNB_FLAG_DETERMINISTIC = 1,     /* PME spreading in 64-bit fixed point: bit-reproducible forces      */
-    SNB_FLAG_DOUBLE_PRECISION = 2   /* all pair / grid arithmetic in FP64 (implies deterministic)        */
+    SNB_FLAG_DOUBLE_PRECISION = 2,  /* all pair / grid arithmetic in FP64 (implies deterministic)        */
+    /* which direct-space kernel runs the PME path in an orthorhombic box with <= 2 subsets (both give the same pair
+     * set and the same mixed-precision results; every other case has one kernel).  Neither bit: by system size --
+     * the packed-FP32 kernel from SNB_PACKED_MIN_ATOMS atoms on, the general one below (platform property DirectKernel) */
+    SNB_FLAG_DIRECT_PACKED = 4,
+    SNB_FLAG_DIRECT_GENERAL = 8
 };
+#define SNB_PACKED_MIN_ATOMS 65536
 
 typedef struct snb_desc {
     int32_t struct_size;               /* = sizeof(snb_desc); guards against ABI drift */

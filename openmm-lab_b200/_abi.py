@@ -14,7 +14,7 @@ import numpy as np
 NoCutoff, CutoffNonPeriodic, CutoffPeriodic, Ewald, PME, LJPME = range(6)
 
 INCLUDE_FORCES, INCLUDE_ENERGY, INCLUDE_DIRECT, INCLUDE_RECIPROCAL = 1, 2, 4, 8
-FLAG_DETERMINISTIC, FLAG_DOUBLE_PRECISION = 1, 2
+FLAG_DETERMINISTIC, FLAG_DOUBLE_PRECISION, FLAG_DIRECT_PACKED, FLAG_DIRECT_GENERAL = 1, 2, 4, 8
 EXECUTE_ALL = 15
 
 OK, ERR_INVALID, ERR_BOX_TOO_SMALL, ERR_PARTICLE_COUNT, ERR_EXCEPTION_SET, \

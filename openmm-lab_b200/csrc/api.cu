@@ -23,6 +23,7 @@
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -182,6 +183,7 @@ struct snb_handle {
     double cutoff = 1, switchDist = 0, rfDielectric = 78.3, alpha = 0, dalpha = 0;
     bool useSwitch = false, exceptionsPeriodic = false, useDispersion = false;
     bool doublePrecision = false, deterministic = false;
+    int directKernelFlags = 0;          // SNB_FLAG_DIRECT_PACKED / _GENERAL, 0 = by system size
     int grid[3] = {0, 0, 0}, dgrid[3] = {0, 0, 0};
     std::vector<int> subsets;
     std::vector<std::array<double, 3>> baseParticle;          // q, sigma, eps
@@ -388,6 +390,7 @@ snb_handle* createHandle(const snb_desc& d) {
         h.device = d.device_index;
         h.doublePrecision = (d.flags&SNB_FLAG_DOUBLE_PRECISION) != 0;
         h.deterministic = h.doublePrecision || (d.flags&SNB_FLAG_DETERMINISTIC) != 0;
+        h.directKernelFlags = d.flags&(SNB_FLAG_DIRECT_PACKED|SNB_FLAG_DIRECT_GENERAL);
         CUDA_CHECK(cudaSetDevice(h.device));
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, h.device));
@@ -879,6 +882,9 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         da.sp = h.stepD.p;
         da.kind = h.method == SNB_NO_CUTOFF ? KIND_PLAIN : h.method <= SNB_CUTOFF_PERIODIC ? KIND_RF : h.method == SNB_LJPME ? KIND_LJPME : KIND_EWALD;
         da.useSwitch = h.useSwitch; da.numSubsets = h.S; da.needEnergy = needEnergy; da.doublePrecision = h.doublePrecision;
+        // small systems keep the general kernel: an evaluation of a few ten thousand atoms is latency bound, and sixteen
+        // resident warps per SM finish a short chunk list sooner than the packed kernel's twelve (DHFR size: 43 vs 52 us)
+        da.usePacked = (h.directKernelFlags&SNB_FLAG_DIRECT_PACKED) ? 1 : (h.directKernelFlags&SNB_FLAG_DIRECT_GENERAL) ? 0 : h.N >= SNB_PACKED_MIN_ATOMS;
         da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
         da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
         da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.chunkOctet = h.chunkOctet.p; da.maxChunks = (int) h.maxChunks;
@@ -1203,14 +1209,35 @@ int snb_update_parameters(snb_handle* h, const snb_desc* desc) {
     SNB_CATCH
 }
 
+// forces[k] += result[k] on the host (the reference kernel ADDS into the platform's force vector,
+// ReferenceOpenMMLabKernels.cpp:35-58).  Memory bound: large systems split the range over a few threads.
+static void addForces(double* forces, const double* result, size_t n) {
+    auto span = [=](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++)
+            forces[k] += result[k];
+    };
+    const size_t perThread = 1u<<19;      // 4 MiB of doubles per thread at least: below that a thread start costs more than it saves
+    unsigned threads = (unsigned) std::min<size_t>(std::min<size_t>(n/perThread, 8), std::max(1u, std::thread::hardware_concurrency()));
+    if (threads <= 1) {
+        span(0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t chunk = (n+threads-1)/threads;
+    for (unsigned t = 1; t < threads; t++)
+        pool.emplace_back(span, std::min(n, t*chunk), std::min(n, (t+1)*chunk));
+    span(0, std::min(n, chunk));
+    for (auto& th : pool)
+        th.join();
+}
+
 int snb_execute(snb_handle* h, const double* positions, const double* box, const double* globals, int flags,
                 double* forces, double* energy, double* slice_energies, double* derivatives) {
     SNB_TRY
     if (!positions) throw SnbException(SNB_ERR_INVALID, "positions are null");
     evaluate(*h, positions, nullptr, box, globals, flags, nullptr);
     if ((flags&SNB_INCLUDE_FORCES) && forces)
-        for (size_t k = 0; k < 3*(size_t) h->N; k++)
-            forces[k] += h->hForces.p[k];
+        addForces(forces, h->hForces.p, 3*(size_t) h->N);
     return snb_read_energies(h, flags, energy, slice_energies, derivatives);
     SNB_CATCH
 }

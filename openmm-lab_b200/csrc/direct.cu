@@ -8,10 +8,9 @@ bool launchDirectPacked(const DirectArgs& a, cudaStream_t st, int grid);    // d
 
 void launchDirect(const DirectArgs& a, cudaStream_t st, int numSMs) {
     int grid = numSMs*DIRECT_CTAS_PER_SM;       // one-warp CTAs, all resident, equal contiguous shares of the chunk list
-    // PME direct space in an orthorhombic box with <= 2 subsets: the packed-FP32 pair loop (SNB_NO_PACKED=1 keeps
-    // k_direct for that case too -- A/B measurements and the parity tests of the general kernel)
-    static const bool noPacked = getenv("SNB_NO_PACKED") != nullptr && getenv("SNB_NO_PACKED")[0] == '1';
-    if (!noPacked && launchDirectPacked(a, st, grid))
+    // PME direct space in an orthorhombic box with <= 2 subsets has two kernels: the packed-FP32 pair loop (large
+    // systems) and the general one (api.cu decides: SNB_FLAG_DIRECT_*, else by size)
+    if (a.usePacked && launchDirectPacked(a, st, grid))
         return;
     switch (a.kind) {
         case KIND_PLAIN: launchDirectKind<KIND_PLAIN>(a, st, grid); break;

@@ -64,6 +64,7 @@ struct DirectArgs {
     DirectConsts<double> cd;
     const StepParams* sp;          // box, lambdas, exact-predicate parameters
     int kind, useSwitch, numSubsets, needEnergy, doublePrecision;
+    int usePacked;                 // the packed-FP32 kernel takes the launch where it applies (direct_packed.cu)
     const int* sortedAtom;
     const float4* posqLocal;
     const float4* sparams;

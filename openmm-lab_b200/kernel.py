@@ -150,8 +150,9 @@ def load_library():
 class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
     """The sm_100a implementation, registered on platform "B200" (platform.py)."""
 
-    def __init__(self, device_index=0, precision="mixed", deterministic=False):
-        flags = (_abi.FLAG_DOUBLE_PRECISION if precision == "double" else 0) | (_abi.FLAG_DETERMINISTIC if deterministic else 0)
+    def __init__(self, device_index=0, precision="mixed", deterministic=False, direct_kernel="auto"):
+        flags = (_abi.FLAG_DOUBLE_PRECISION if precision == "double" else 0) | (_abi.FLAG_DETERMINISTIC if deterministic else 0) | \
+                {"auto": 0, "packed": _abi.FLAG_DIRECT_PACKED, "general": _abi.FLAG_DIRECT_GENERAL}[direct_kernel]
         super().__init__(load_library(), "snb_", device_index, flags)
         self.precision = precision
 

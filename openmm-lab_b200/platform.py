@@ -5,7 +5,8 @@ Mirrors the reference's plugin entry points
 registers a factory for the kernel name "CalcSlicedNonbondedForce"; the factory throws for
 any other name (:56).  Platform properties follow the reference's CUDA platform
 (CudaOpenMMLabKernels.cpp:483,496; platforms/cuda/tests/CudaOpenMMLabTests.h:26-31):
-``Precision`` (mixed | double), ``DeterministicForces``, ``DeviceIndex``.
+``Precision`` (mixed | double), ``DeterministicForces``, ``DeviceIndex``; plus ``DirectKernel``
+(auto | packed | general: include/slicednb.h SNB_FLAG_DIRECT_*).
 """
 from .context import Platform
 from .force import OpenMMException
@@ -19,7 +20,10 @@ def _createKernelImpl(name, platform, context):
         if precision not in ("mixed", "double"):
             raise OpenMMException("Illegal value for Precision: %s (this platform offers mixed and double)" % precision)
         deterministic = str(props.get("DeterministicForces", "false")).lower() in ("true", "1")
-        return B200CalcSlicedNonbondedForceKernel(int(props.get("DeviceIndex", 0)), precision, deterministic)
+        direct_kernel = str(props.get("DirectKernel", "auto")).lower()
+        if direct_kernel not in ("auto", "packed", "general"):
+            raise OpenMMException("Illegal value for DirectKernel: %s (auto, packed or general)" % direct_kernel)
+        return B200CalcSlicedNonbondedForceKernel(int(props.get("DeviceIndex", 0)), precision, deterministic, direct_kernel)
     raise OpenMMException("Tried to create kernel with illegal kernel name '%s'" % name)
 
 

@@ -216,6 +216,11 @@ KernelImpl* B200OpenMMLabKernelFactory::createKernelImpl(std::string name, const
             flags |= SNB_FLAG_DOUBLE_PRECISION;
         if (deterministic != NULL && string(deterministic) != "0" && string(deterministic) != "false")
             flags |= SNB_FLAG_DETERMINISTIC;
+        const char* directKernel = getenv("SNB_DIRECT_KERNEL");     /* auto (by system size) | packed | general */
+        if (directKernel != NULL && string(directKernel) == "packed")
+            flags |= SNB_FLAG_DIRECT_PACKED;
+        else if (directKernel != NULL && string(directKernel) == "general")
+            flags |= SNB_FLAG_DIRECT_GENERAL;
         return new B200CalcSlicedNonbondedForceKernel(name, platform, device != NULL ? atoi(device) : 0, flags);
     }
     throw OpenMMException((std::string("Tried to create kernel with illegal kernel name '")+name+"'").c_str());

@@ -48,13 +48,17 @@ def _check(w, pairs=True, mixed=True, energy_tol=1e-4, **kw):
             _check_pairs(ref, got)
         assert_parity(ref, got, TOL, "%s %s [double]" % (w.name, name))
         if mixed:
-            got = evaluate("B200", w, pairs=pairs and name == "direct", **flags, **kw)
-            if "pairs" in ref:
-                _check_pairs(ref, got)
-            if name == "total":
-                assert_parity_mixed(ref, got, refs["direct"], refs["recip"], what="%s total [mixed]" % w.name, energy_tol=energy_tol)
-            else:
-                assert_parity_mixed(ref, got, what="%s %s [mixed]" % (w.name, name), energy_tol=energy_tol)
+            # both direct-space kernels of the PME path (DirectKernel; elsewhere the property changes nothing, so once is enough)
+            two = direct and method == F.PME and name != "recip"
+            for kernel in (("general", "packed") if two else ("auto",)):
+                got = evaluate("B200", w, pairs=pairs and name == "direct", properties={"DirectKernel": kernel}, **flags, **kw)
+                if "pairs" in ref:
+                    _check_pairs(ref, got)
+                what = "%s %s [mixed, DirectKernel=%s]" % (w.name, name, kernel)
+                if name == "total":
+                    assert_parity_mixed(ref, got, refs["direct"], refs["recip"], what=what, energy_tol=energy_tol)
+                else:
+                    assert_parity_mixed(ref, got, what=what, energy_tol=energy_tol)
 
 
 @pytest.mark.parametrize("method", [F.CutoffPeriodic, F.PME])
