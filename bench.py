@@ -45,6 +45,16 @@ import numpy as np  # noqa: E402
 
 FLOP_PER_PAIR = 67.0          # forces + energy + slice accumulators
 FP32_PEAK_TFLOPS = 148*128*2*1.965e9/1e12   # 74.4: SMs x lanes x 2 x max SM clock (MEASURED_PEAKS.json has no FP32 entry)
+PACKED_MIN_ATOMS = 65536                    # include/slicednb.h SNB_PACKED_MIN_ATOMS: the packed-FP32 kernel takes over from here
+
+
+def measured_fp32_peak():
+    """FFMA throughput measured on a B200 of this pool with scratch/ubench/fp32peak.cu (profiles/r1_fp32_peak.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_fp32_peak.json")) as f:
+            return json.load(f)["ffma_tflops"]
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -300,9 +310,12 @@ class Runner:
         slow = max(range(len(rows)), key=lambda r: rows[r][0])
         kernel_ms, kernel_pairs = float(rows[slow][0]), int(rows[slow][1])
         achieved = kernel_pairs*FLOP_PER_PAIR/(kernel_ms*1e-3)/1e12 if kernel_ms > 0 else 0.0
-        out["roofline"] = {"bound": "fp32", "kernel": "k_direct (direct-space tile kernel)", "achieved": achieved,
+        name = "k_directPacked (direct-space tile kernel, packed FP32)" if self.n >= PACKED_MIN_ATOMS else "k_direct (direct-space tile kernel)"
+        measured = measured_fp32_peak()
+        out["roofline"] = {"bound": "fp32", "kernel": name, "achieved": achieved,
                            "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved/FP32_PEAK_TFLOPS,
                            "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz (FP32 FMA, non-tensor; MEASURED_PEAKS.json carries no FP32 entry)",
+                           "peak_measured_ffma": measured, "frac_of_measured": (achieved/measured if measured else None),
                            "interacting_pairs": kernel_pairs, "interacting_pairs_all_ranks": int(sum(r[1] for r in rows)),
                            "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": kernel_ms, "rank": slow, "traffic": load_traffic(self.w.name)}
         # the memory-bound kernels against the measured HBM peak (algorithmic bytes)
