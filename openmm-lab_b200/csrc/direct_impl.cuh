@@ -433,10 +433,25 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             sAccC[s][lane] = sAccV[s][lane] = 0.0;
     }
 
-    // gather of chunk `ch` into stage buffer `buf`: list entry -> aux, atom data by cp.async
-    auto gather = [&](const int2 ent, unsigned buf) {
-        const int j = max(ent.x, 0);        // padding entries copy atom 0: never in range (mask 0xff)
-        const unsigned dst = stageBase+buf*BUF;
+    // Everything the steady-state loop reads from global memory arrives through cp.async: a plain prefetch load holds a
+    // register scoreboard for a DRAM round trip, and with six scoreboards per warp some unrelated instruction of the
+    // pair loop ends up waiting on it (ncu on the packed kernel: 26% of the warp time in long-scoreboard stalls).
+    //   fetchEntries(c): list entry of every lane + the octet of chunk c  -> ring slot c&3           (two chunks ahead)
+    //   gather(c):       the 32 j atoms of chunk c (entries already in the ring) -> stage buffer c&1  (one chunk ahead)
+    __shared__ __align__(16) int2 sEnt[4][32];
+    __shared__ int sOct[4];
+    const unsigned entBase = opaque((unsigned) __cvta_generic_to_shared(&sEnt[0][0])+(unsigned) lane*8u);
+    const unsigned octBase = opaque((unsigned) __cvta_generic_to_shared(&sOct[0]));
+    auto fetchEntries = [&](int chunk) {
+        cpAsync8(entBase+(unsigned) (chunk&3)*256u, a.jList+(size_t) chunk*32+lane);
+        if (lane == 0)
+            cpAsync4(octBase+(unsigned) (chunk&3)*4u, a.chunkOctet+chunk);
+    };
+    auto gather = [&](int chunk) {
+        const unsigned ent = entBase+(unsigned) (chunk&3)*256u;
+        const int jRaw = (int) ldSharedU32(ent);
+        const int j = max(jRaw, 0);         // padding entries copy atom 0: never in range (mask 0xff)
+        const unsigned dst = stageBase+(unsigned) (chunk&1)*BUF;
         const char* ps = (const char*) (Real<R>::pos(a)+j);
         const char* qs = (const char*) (Real<R>::prm(a)+j);
 #pragma unroll
@@ -445,8 +460,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             cpAsync16(dst+St::PRM+lane*St::STRIDE+b, qs+b);
         }
         cpAsync16(dst+St::CTR+lane*16, a.blockCenter+(j>>5));
-        stSharedV2U32(dst+St::AUX+lane*St::AUXS, (unsigned) ent.x, (unsigned) ent.y);
-        cpAsyncCommit();
+        stSharedV2U32(dst+St::AUX+lane*St::AUXS, (unsigned) jRaw, ldSharedU32(ent+4));
     };
 
     // ---- the octet in flight
@@ -490,36 +504,30 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             t.EC[s] = t.EV[s] = 0.0;
     };
 
-    // ---- prologue: chunk cBegin is gathered, the entry of cBegin+1 is on its way
-    int2 entNext = make_int2(-1, 0xff);
-    int jCur = -1, octCur = 0, octNext = 0;
+    // ---- prologue: entries of the first two chunks, then the atoms of the first
     if (cBegin < cEnd) {
-        const int2 e0 = a.jList[(size_t) cBegin*32+lane];
-        octCur = __shfl_sync(full, a.chunkOctet[cBegin], 0);
-        jCur = e0.x;
-        gather(e0, 0);
-        if (cBegin+1 < cEnd) {
-            entNext = a.jList[(size_t) (cBegin+1)*32+lane];
-            octNext = __shfl_sync(full, a.chunkOctet[cBegin+1], 0);
-        }
+        fetchEntries(cBegin);
+        if (cBegin+1 < cEnd)
+            fetchEntries(cBegin+1);
+        cpAsyncCommit();
+        cpAsyncWait<0>();
+        __syncwarp();
+        gather(cBegin);
+        cpAsyncCommit();
     }
     for (int ch = cBegin; ch < cEnd; ch++) {
-        const unsigned buf = (unsigned) (ch-cBegin)&1u;
+        const unsigned buf = (unsigned) ch&1u;
         const unsigned sb = stageBase+buf*BUF;
-        __syncwarp();                       // every lane is done reading the other buffer (chunk ch-1)
-        // ---- keep the pipeline full: gather chunk ch+1, fetch the entry of chunk ch+2
-        const int jNext = entNext.x;
-        const int octNext1 = octNext;
+        // the atoms of chunk ch and the entries of chunk ch+1 were requested a whole chunk ago
+        cpAsyncWait<0>();
+        __syncwarp();                       // ... by every lane; and every lane is done with chunk ch-1
         if (ch+1 < cEnd) {
-            gather(entNext, buf^1u);
-            if (ch+2 < cEnd) {
-                entNext = a.jList[(size_t) (ch+2)*32+lane];
-                octNext = __shfl_sync(full, a.chunkOctet[ch+2], 0);
-            }
-            cpAsyncWait<1>();               // chunk ch has landed (all but the newest group)
+            gather(ch+1);
+            if (ch+2 < cEnd)
+                fetchEntries(ch+2);
+            cpAsyncCommit();
         }
-        else
-            cpAsyncWait<0>();
+        const int octCur = __shfl_sync(full, (int) ldSharedU32(octBase+(unsigned) (ch&3)*4u), 0);
         // ---- octet switch
         const int O = octCur&0x3fffffff;
         if (O != curO) {
@@ -675,6 +683,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 bandPairs<R, KIND, PBC, ENERGY, DUMP, SWITCH>(o, c, bandMask, lane, ki, origI, pi, si4, perPair ? 1 : 0, &sStage[buf][0]);
             }
         }
+        const int jCur = (int) ldSharedU32(entBase+(unsigned) (ch&3)*256u);
         if (jCur >= 0) {
             addFixed(&a.forceSorted[jCur], Real<R>::fixed(fjx));
             addFixed(&a.forceSorted[a.paddedAtoms+jCur], Real<R>::fixed(fjy));
@@ -692,8 +701,6 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 t.EV[u] += t.eV[u];
             }
         }
-        jCur = jNext;
-        octCur = octNext1;
     }
     if (curO >= 0)
         flushOctet();
