@@ -22,8 +22,8 @@ reference kernel does (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:193
             --multi replicas: every rank evaluates its own copy of the workload (the lambda windows
             of an alchemical calculation, one per GPU), no collective ("scaling": "weak").
             --multi auto (default): partition at >= 200 000 atoms, replicas below -- a 23 558-atom
-            evaluation is launch/latency bound (145 us) and sharing it between GPUs makes it SLOWER
-            (measured 0.86x at N=2); the line then also carries the partitioned number
+            evaluation is launch/latency bound (145 us) and sharing it between GPUs gains nothing
+            (measured 1.01x at N=2); the line then also carries the partitioned number
             ("partitioned") so that both are on record.
   stmv      the same measurement on the STMV-size workload (BASELINE.json configs[4]), a few steps,
             always partitioned for N > 1
