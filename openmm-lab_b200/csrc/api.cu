@@ -183,6 +183,9 @@ struct snb_handle {
     double cutoff = 1, switchDist = 0, rfDielectric = 78.3, alpha = 0, dalpha = 0;
     bool useSwitch = false, exceptionsPeriodic = false, useDispersion = false;
     bool doublePrecision = false, deterministic = false;
+    int kmax[3] = {0, 0, 0}, numK = 0;  // classic Ewald: reciprocal vectors per axis, size of the half space
+    DevBuf<int3> ewaldK;
+    DevBuf<double2> ewaldS;
     int directKernelFlags = 0;          // SNB_FLAG_DIRECT_PACKED / _GENERAL, 0 = by system size
     int grid[3] = {0, 0, 0}, dgrid[3] = {0, 0, 0};
     std::vector<int> subsets;
@@ -268,8 +271,8 @@ void validateDesc(const snb_desc& d) {
         throw SnbException(SNB_ERR_UNSUPPORTED, "more than 8 subsets are not supported by this build");
     if (d.method < SNB_NO_CUTOFF || d.method > SNB_LJPME)
         throw SnbException(SNB_ERR_INVALID, "unknown nonbonded method");
-    if (d.method == SNB_EWALD)
-        throw SnbException(SNB_ERR_UNSUPPORTED, "classic Ewald summation is not implemented on the B200 platform; use PME");
+    if (d.method == SNB_EWALD && (d.default_box[3] != 0.0 || d.default_box[6] != 0.0 || d.default_box[7] != 0.0))
+        throw SnbException(SNB_ERR_INVALID, "SlicedNonbondedForce: Ewald is not supported with non-rectangular boxes.  Use PME instead.");
     for (int i = 0; i < d.num_particles; i++)
         if (d.subset[i] < 0 || d.subset[i] >= d.num_subsets)
             throw SnbException(SNB_ERR_INVALID, "particle subset out of range");
@@ -342,6 +345,31 @@ void calcPMEParameters(const snb_desc& d, bool lj, double& alpha, int grid[3]) {
             int n = lj ? (int) ceil(alpha*len/(3*pow(tol, 0.2))) : (int) ceil(2*alpha*len/(3*pow(tol, 0.2)));
             grid[k] = std::max(n, 6);
         }
+    }
+}
+
+// OpenMM NonbondedForceImpl::calcEwaldParameters (third party, OpenMM 8.1; call site ReferenceOpenMMLabKernels.cpp:169-173):
+// alpha from the tolerance, kmax per axis = smallest odd-rounded k with 0.05 sqrt(L alpha) k exp(-(pi k/(L alpha))^2) < tol
+void calcEwaldParameters(const snb_desc& d, double& alpha, int kmax[3]) {
+    const double tol = d.ewald_error_tolerance;
+    alpha = (1.0/d.cutoff)*std::sqrt(-log(2.0*tol));
+    for (int k = 0; k < 3; k++) {
+        const double width = d.default_box[4*k];
+        auto err = [&](int km) {
+            const double t = km*M_PI/(width*alpha);
+            return tol-0.05*sqrt(width*alpha)*km*exp(-t*t);
+        };
+        int arg = 10;
+        double value = err(arg);
+        if (value > 0.0) {
+            while (value > 0.0 && arg > 0)
+                value = err(--arg);
+            arg++;
+        }
+        else
+            while (value < 0.0)
+                value = err(++arg);
+        kmax[k] = arg%2 == 0 ? arg+1 : arg;
     }
 }
 
@@ -448,6 +476,25 @@ snb_handle* createHandle(const snb_desc& d) {
         }
         if (h.method == SNB_PME || h.method == SNB_LJPME)
             calcPMEParameters(d, false, h.alpha, h.grid);
+        if (h.method == SNB_EWALD) {
+            calcEwaldParameters(d, h.alpha, h.kmax);
+            // the half space of reciprocal vectors the reference visits (ReferenceSlicedLJCoulombIxn.cpp:279-296)
+            std::vector<int3> kv;
+            int lowry = 0, lowrz = 1;
+            for (int rx = 0; rx < h.kmax[0]; rx++) {
+                for (int ry = lowry; ry < h.kmax[1]; ry++) {
+                    for (int rz = lowrz; rz < h.kmax[2]; rz++)
+                        kv.push_back(make_int3(rx, ry, rz));
+                    lowrz = 1-h.kmax[2];
+                }
+                lowry = 1-h.kmax[1];
+            }
+            h.numK = (int) kv.size();
+            h.ewaldK.alloc(std::max<size_t>(kv.size(), 1));
+            if (!kv.empty())
+                CUDA_CHECK(cudaMemcpy(h.ewaldK.p, kv.data(), sizeof(int3)*kv.size(), cudaMemcpyHostToDevice));
+            h.ewaldS.alloc(std::max<size_t>(kv.size()*(size_t) h.S, 1));
+        }
         if (h.method == SNB_LJPME) {
             calcPMEParameters(d, true, h.dalpha, h.dgrid);
             h.useSwitch = false;
@@ -752,6 +799,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
                includeRecip = flags&SNB_INCLUDE_RECIPROCAL;
     const bool periodic = h.method >= SNB_CUTOFF_PERIODIC;
     const bool pmeFamily = h.method == SNB_PME || h.method == SNB_LJPME;
+    const bool ewaldFamily = pmeFamily || h.method == SNB_EWALD;
     const bool needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     cudaStream_t st = h.stream;
     const NcclApi* nccl = h.comm ? ncclApi(nullptr) : nullptr;
@@ -776,7 +824,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         int64_t xlo = 0, xhi = h.X;
         partitionRange(h.X, h.world, h.rank, 1.0, &xlo, &xhi);
         ba.firstException = (int) xlo;
-        ba.numExceptions = (int) (xhi-xlo); ba.periodicExceptions = h.exceptionsPeriodic; ba.ewald = pmeFamily; ba.ljpme = h.method == SNB_LJPME;
+        ba.numExceptions = (int) (xhi-xlo); ba.periodicExceptions = h.exceptionsPeriodic; ba.ewald = ewaldFamily; ba.ljpme = h.method == SNB_LJPME;
         ba.includeForces = 1;
         ba.alpha = h.alpha; ba.dalpha = h.dalpha; ba.sp = h.stepD.p;
         ba.posd = h.posd.p; ba.paramsD = h.paramsD.p; ba.subset = h.subsetD.p; ba.exceptionAtoms = h.exceptionAtomsD.p;
@@ -814,6 +862,17 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
 
     // ---- reciprocal space (rank 0): its own stream, beside the tile list / direct-space kernels ----
     auto reciprocal = [&](cudaStream_t ps) {
+        if (h.method == SNB_EWALD) {
+            EwaldArgs ea;
+            memset(&ea, 0, sizeof(ea));
+            ea.numAtoms = h.N; ea.numSubsets = h.S; ea.numK = h.numK; ea.paddedAtoms = h.NP; ea.alpha = h.alpha;
+            ea.sp = h.stepD.p; ea.posd = h.posd.p; ea.paramsD = h.paramsD.p; ea.subset = h.subsetD.p;
+            ea.kvec = h.ewaldK.p; ea.structure = h.ewaldS.p; ea.forceOrig = h.forceOrig.p;
+            ea.energyBuf = needEnergy ? h.energyBuf.p : nullptr;
+            launchEwaldReciprocal(ea, includeForces, ps);
+            tm.mark(5); tm.mark(6); tm.mark(7); tm.mark(8);
+            return;
+        }
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
             PmeGrid& g = term == 0 ? h.pme : h.dpme;
             PmeArgs pa = pmeArgs(h, term, includeDirect);
@@ -832,7 +891,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             if (term == 0) tm.mark(8);
         }
     };
-    const bool doRecip = includeRecip && pmeFamily && h.rank == 0;
+    const bool doRecip = includeRecip && ewaldFamily && h.rank == 0;
     if (doRecip && !h.timing) {
         CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.evSorted, 0));
         if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evRecBegin, h.pmeStream));
@@ -1079,6 +1138,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
     if (includeDirect) launches += (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
+    if (includeRecip && h.method == SNB_EWALD && h.rank == 0) launches += 2;    // structure factors, forces
     if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 5 : 4)*(h.method == SNB_LJPME ? 2 : 1);    // spread (+finish), convolution, combine, interpolate
     if (includeForces || h.comm) launches += 1+(h.comm && includeForces ? 1 : 0);
     if (posqDev) launches += 1;
@@ -1096,7 +1156,7 @@ void finishEnergies(snb_handle& h, const double* box, int flags) {
     }
     // (multi-GPU: the all-reduce gave every rank the summed slice energies; the host-side terms below are
     // added identically everywhere, so every rank returns the same energies.  Forces land on rank 0.)
-    if (includeRecip && (h.method == SNB_PME || h.method == SNB_LJPME))
+    if (includeRecip && (h.method == SNB_EWALD || h.method == SNB_PME || h.method == SNB_LJPME))
         for (int s = 0; s < h.S; s++) {
             h.sliceEnergies[2*(s*(s+3)/2)] += h.selfC[s];
             h.sliceEnergies[2*(s*(s+3)/2)+1] += h.selfV[s];

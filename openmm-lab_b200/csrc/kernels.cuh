@@ -126,6 +126,20 @@ void launchPmeSpread(const PmeArgs& a, cudaStream_t stream);
 void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);
 
+struct EwaldArgs {
+    int numAtoms, numSubsets, numK, paddedAtoms;
+    double alpha;
+    const StepParams* sp;           // box, Coulomb lambdas
+    const double* posd;
+    const double* paramsD;          // [N][3] sigma/2, 2 sqrt(eps), q
+    const int* subset;
+    const int3* kvec;               // [numK] the half space of reciprocal vectors, in units of 2 pi / box length
+    double2* structure;             // [numK][numSubsets] structure factors
+    long long* forceOrig;
+    double* energyBuf;              // or null: no energies wanted
+};
+void launchEwaldReciprocal(const EwaldArgs& a, bool includeForces, cudaStream_t stream);
+
 struct FinishArgs {
     int numAtoms, paddedAtoms;
     const int* sortedPos;

@@ -31,7 +31,7 @@ def _check(w, pairs=True, mixed=True, energy_tol=1e-4, **kw):
     """
     method = w.force.getNonbondedMethod()
     direct, reciprocal = kw.pop("direct", True), kw.pop("reciprocal", True)
-    ewald_family = method in (F.PME, F.LJPME)
+    ewald_family = method in (F.Ewald, F.PME, F.LJPME)
     want_pairs = pairs and method != F.NoCutoff
     combos = []
     if direct:
@@ -72,7 +72,7 @@ def test_water_box_direct_reciprocal_split(direct, reciprocal):
     _check(systems.water_box(), direct=direct, reciprocal=reciprocal, energy_tol=1e-5)
 
 
-@pytest.mark.parametrize("method", [F.CutoffPeriodic, F.PME, F.LJPME])
+@pytest.mark.parametrize("method", [F.CutoffPeriodic, F.Ewald, F.PME, F.LJPME])
 @pytest.mark.parametrize("groups", [1, 2, 3])
 def test_small_mixed(method, groups):
     kw = {}
