@@ -386,7 +386,7 @@ static __device__ __noinline__ void bandRescan(DirectOut o, DirectConsts<R> c, i
 }
 
 template <typename R, int KIND, int PBC, int NSUB, bool ENERGY, bool DUMP, bool SWITCH>
-__global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? DIRECT_CTAS_PER_SM/2 : DIRECT_CTAS_PER_SM) : 8) k_direct(DirectArgs a) {
+__global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? DIRECT_WIDE_CTAS_PER_SM : DIRECT_CTAS_PER_SM) : 8) k_direct(DirectArgs a) {
     constexpr int NS = NSUB > 0 ? NSUB : SNB_MAX_SUBSETS;
     constexpr bool TWO = NSUB == 2;         // subsets 0/1 travel as the floats 0.0/1.0: lambdas and energies by FMA
     constexpr int STEP_UNROLL = DIRECT_UNROLL;
@@ -725,6 +725,9 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
 
 template <int KIND, int PBC, int NSUB, bool SWITCH>
 static void launch5(const DirectArgs& a, cudaStream_t st, int grid) {
+    // every CTA resident at once (equal contiguous shares of the chunk list): more than two subsets take more registers
+    if (NSUB > 2 || NSUB == 0)
+        grid = grid/DIRECT_CTAS_PER_SM*DIRECT_WIDE_CTAS_PER_SM;
     if (a.doublePrecision) {
         // the double-precision mode is a correctness mode: one instantiation (energies always on)
         if (a.pairDump) k_direct<double, KIND, PBC, NSUB, true, true, SWITCH><<<grid/2, 32, 0, st>>>(a);

@@ -54,6 +54,10 @@ void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 #define DIRECT_CTAS_PER_SM 16       /* one-warp CTAs of the direct-space kernel resident per SM (register budget 65536/32/this) */
 #endif
 
+#ifndef DIRECT_WIDE_CTAS_PER_SM
+#define DIRECT_WIDE_CTAS_PER_SM 12  /* the same for more than two subsets (per-subset lambda / energy tables: 168 registers) */
+#endif
+
 #ifndef DIRECT_UNROLL
 #define DIRECT_UNROLL 8
 #endif
