@@ -190,6 +190,14 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size);
 int snb_set_rank0_share(snb_handle* h, double share);
 /* broadcast_positions = 0: every rank is given identical positions by its caller, no broadcast is needed */
 int snb_set_comm_options(snb_handle* h, int broadcast_positions);
+/* What snb_create derives from a descriptor on the host, without touching a GPU (tests compare it with the CPU oracle):
+ * Ewald / PME separation parameter and grid (NonbondedForceImpl::calcPMEParameters, call sites
+ * ReferenceOpenMMLabKernels.cpp:171,176,178), the LJPME pair, the classic-Ewald reciprocal vectors per axis
+ * (calcEwaldParameters, :169-173) and the dispersion-correction coefficient of every slice
+ * (SlicedNonbondedForceImpl::calcDispersionCorrections, SlicedNonbondedForceImpl.cpp:263-354).  Entries that do not
+ * apply to desc->method come back 0; any output pointer may be null.  dispersion has num_subsets (num_subsets+1)/2 entries. */
+int snb_host_parameters(const snb_desc* desc, double* alpha, int32_t grid[3], double* dispersion_alpha, int32_t dispersion_grid[3],
+                        int32_t kmax[3], double* dispersion);
 /* the partition rule itself (host only, no GPU): contiguous range [lo, hi) of n units for `rank` */
 int snb_partition(int64_t n, int world_size, int rank, double rank0_share, int64_t* lo, int64_t* hi);
 

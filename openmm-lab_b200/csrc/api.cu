@@ -1482,6 +1482,36 @@ int snb_set_rank0_share(snb_handle* h, double share) { h->rank0Share = share; re
 
 int snb_set_comm_options(snb_handle* h, int broadcast_positions) { h->broadcastPositions = broadcast_positions != 0; return SNB_OK; }
 
+int snb_host_parameters(const snb_desc* desc, double* alpha, int32_t grid[3], double* dispersion_alpha, int32_t dispersion_grid[3],
+                        int32_t kmax[3], double* dispersion) {
+    SNB_TRY
+    if (!desc) throw SnbException(SNB_ERR_INVALID, "descriptor is null");
+    const snb_desc& d = *desc;
+    validateDesc(d);
+    double a = 0.0, da = 0.0;
+    int g[3] = {0, 0, 0}, dg[3] = {0, 0, 0}, km[3] = {0, 0, 0};
+    if (d.method == SNB_PME || d.method == SNB_LJPME)
+        calcPMEParameters(d, false, a, g);
+    if (d.method == SNB_LJPME)
+        calcPMEParameters(d, true, da, dg);
+    if (d.method == SNB_EWALD)
+        calcEwaldParameters(d, a, km);
+    if (alpha) *alpha = a;
+    if (dispersion_alpha) *dispersion_alpha = da;
+    for (int k = 0; k < 3; k++) {
+        if (grid) grid[k] = g[k];
+        if (dispersion_grid) dispersion_grid[k] = dg[k];
+        if (kmax) kmax[k] = km[k];
+    }
+    if (dispersion) {
+        const int L = d.num_subsets*(d.num_subsets+1)/2;
+        const std::vector<double> coef = d.use_dispersion_correction ? calcDispersionCorrections(d) : std::vector<double>(L, 0.0);
+        std::copy(coef.begin(), coef.end(), dispersion);
+    }
+    return SNB_OK;
+    SNB_CATCH
+}
+
 int snb_partition(int64_t n, int world_size, int rank, double rank0_share, int64_t* lo, int64_t* hi) {
     if (!lo || !hi || world_size < 1 || rank < 0 || rank >= world_size || n < 0) {
         g_lastError = "bad partition arguments";
