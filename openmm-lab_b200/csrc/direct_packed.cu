@@ -235,6 +235,14 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
             const float2 ex = make_float2(fastExp2(e.x), fastExp2(e.y));
             const float2 w = fma2(r, bc(c.halfAlpha), bc(1.f));
             const float2 u = fma2(make_float2(fastRcp(w.x), fastRcp(w.y)), bc(3.f), bc(-2.f));
+#ifdef PACKED_ESTRIN
+            // tuning variant (not the default; unmeasured): Estrin's scheme, 12 operations in a chain of 4 instead of 9 in a chain of 9
+            const float2 u2 = mul2(u, u), u4 = mul2(u2, u2), u8 = mul2(u4, u4);
+            const float2 q01 = fma2(bc(4.0981802125e-01f), u, bc(4.2758357745e-01f)), q23 = fma2(bc(2.2509531568e-02f), u, bc(1.4242693719e-01f));
+            const float2 q45 = fma2(bc(-8.6138957608e-04f), u, bc(-1.6015017984e-03f)), q67 = fma2(bc(3.4861879002e-05f), u, bc(9.8919924926e-05f));
+            const float2 q89 = fma2(bc(-7.5385177448e-07f), u, bc(-8.2052179778e-06f));
+            const float2 p = fma2(q89, u8, fma2(fma2(q67, u2, q45), u4, fma2(q23, u2, q01)));
+#else
             float2 p = fma2(bc(-7.5385177448e-07f), u, bc(-8.2052179778e-06f));
             p = fma2(p, u, bc(3.4861879002e-05f));
             p = fma2(p, u, bc(9.8919924926e-05f));
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
             p = fma2(p, u, bc(1.4242693719e-01f));
             p = fma2(p, u, bc(4.0981802125e-01f));
             p = fma2(p, u, bc(4.2758357745e-01f));
+#endif
             const float2 g = mul2(mul2(mul2(make_float2(zq.z, zq.w), bc(pi.w)), invR), ex);
             const float2 ec = mul2(g, p);
             const float2 fc = mul2(g, fma2(bc(c.twoAlphaOverSqrtPi), r, p));
