@@ -210,6 +210,9 @@ int snb_dump_pairs(snb_handle* h, int32_t** pairs, int64_t* num_pairs);
 /* number of interacting pairs of the last execute on this handle (this rank's share), without the list */
 int snb_count_pairs(snb_handle* h, int64_t* num_pairs);
 void snb_free(void* p);
+/* test hook: set the capacity of the tile list (chunks of 32 entries).  A value that is too small makes the next
+ * evaluation overflow, grow the buffers and repeat -- the path a locally dense system takes on its first evaluation. */
+int snb_set_list_capacity(snb_handle* h, int64_t chunks);
 
 /* per-phase device times (ms) of the last execute, when timing is enabled */
 enum { SNB_PHASE_SORT = 0, SNB_PHASE_LIST, SNB_PHASE_DIRECT, SNB_PHASE_BONDED,
@@ -220,7 +223,10 @@ int snb_get_phase_times(snb_handle* h, float* ms /*[SNB_NUM_PHASES]*/);
 /* CUDA-event time (ms) of the last execute on the handle's stream: first memset .. last read-back copy
  * (excludes the host->device copy of the positions, which precedes it) */
 int snb_get_last_device_ms(snb_handle* h, float* ms);
-/* counters of the last execute: [0]=interacting pairs, [1]=tile entries, [2]=kernel launches */
+/* counters of the last execute: [0] unused (the interacting pairs are counted on request: snb_count_pairs),
+ * [1] chunks of 32 tile-list entries, [2] kernel launches of this library, [3] k_computeParameters launches since
+ * creation, [4] 1 when the evaluation was replayed from a captured CUDA graph, [5] 1 when the packed-FP32 direct-space
+ * kernel (k_directPacked) took the launch, 0 for the general one (k_direct) */
 int snb_get_counters(snb_handle* h, int64_t* out /*[8]*/);
 
 const char* snb_last_error(void);

@@ -11,6 +11,7 @@
 #include "comm.cuh"
 
 #include <cufft.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <array>
@@ -43,6 +44,12 @@ struct SnbException : public std::exception {
     throw SnbException(SNB_ERR_CUDA, std::string(#call)+": "+(api)->GetErrorString(r_)); } while (0)
 #define CUFFT_CHECK(call) do { cufftResult r_ = (call); if (r_ != CUFFT_SUCCESS) \
     throw SnbException(SNB_ERR_CUDA, std::string(#call)+": cuFFT error "+std::to_string((int) r_)); } while (0)
+
+// NVTX range over the host-side enqueue of one phase (shows up in Nsight timelines; a no-op without a tool attached)
+struct Range {
+    explicit Range(const char* name) { nvtxRangePushA(name); }
+    ~Range() { nvtxRangePop(); }
+};
 
 template <typename T> struct DevBuf {
     T* p = nullptr;
@@ -166,7 +173,7 @@ struct PmeGrid {
 // same nodes with the same arguments (the box and the lambdas travel through StepParams in device
 // memory), so the second one onwards replays a captured CUDA graph.
 struct GraphKey {
-    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy;
+    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast;
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
     double share;
@@ -204,7 +211,12 @@ struct snb_handle {
     // ---- derived host state ----
     bool paramsDirty = true;
     std::vector<double> lastOffsetValues;
-    std::vector<double> selfC, selfV;                          // per subset
+    // computeParameters runs on the device (params.cu): base parameters and the offset CSRs live in HBM
+    DevBuf<double> baseParticleD, baseExceptionD, globalsD, selfD, selfPartial;
+    DevBuf<int> particleOffsetStart, exceptionOffsetStart;
+    DevBuf<double4> particleOffsetsD, exceptionOffsetsD;
+    DevBuf<unsigned> paramTicket;
+    PinnedBuf<double> hGlobals, hSelf;                         // hSelf: [subset][Coulomb, dispersion] self energies
     double lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
     int cellDim[3] = {0, 0, 0}, numCells = 0;
     int pbcModeOverride = -1;
@@ -238,7 +250,11 @@ struct snb_handle {
     int rank = 0, world = 1;
     double rank0Share = -1;             // < 0: cost-model default
     DevBuf<long long> reduceSend, reduceRecv;
+    DevBuf<long long> forcePme;         // rank 0: reciprocal-space forces, kept apart from what is reduced ([3][NP], original order)
+    DevBuf<double> energyPme;           // rank 0: reciprocal-space slice energies, likewise
+    PinnedBuf<double> hEnergyPme;
     PinnedBuf<long long> hEnergyFixed;  // the all-reduced energy table as it arrives (2^32 fixed point)
+    cudaEvent_t evPacked = nullptr;     // this rank's contribution is packed (timing; load balance)
     bool broadcastPositions = true;     // false: the caller guarantees identical positions on every rank
     bool balanceFrozen = false;         // after a few measured evaluations the partition is fixed (and graphs take over)
     int commEvals = 0;
@@ -258,6 +274,8 @@ struct snb_handle {
     bool evCreated = false;
     float phaseMs[SNB_NUM_PHASES];
     long long countersOut[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool packedLaunched = false;        // which direct-space kernel the last enqueue chose
+    long long paramLaunches = 0;        // k_computeParameters launches so far
 };
 
 namespace {
@@ -276,6 +294,29 @@ void validateDesc(const snb_desc& d) {
     for (int i = 0; i < d.num_particles; i++)
         if (d.subset[i] < 0 || d.subset[i] >= d.num_subsets)
             throw SnbException(SNB_ERR_INVALID, "particle subset out of range");
+    if (d.num_exceptions < 0 || d.num_global_parameters < 0 || d.num_particle_offsets < 0 || d.num_exception_offsets < 0 ||
+        d.num_scaling_parameters < 0 || d.num_derivatives < 0)
+        throw SnbException(SNB_ERR_INVALID, "negative count in the descriptor");
+    // every index the host and device loops will use
+    for (int k = 0; k < d.num_particle_offsets; k++)
+        if (d.particle_offset_index[2*k] < 0 || d.particle_offset_index[2*k] >= d.num_global_parameters ||
+            d.particle_offset_index[2*k+1] < 0 || d.particle_offset_index[2*k+1] >= d.num_particles)
+            throw SnbException(SNB_ERR_INVALID, "particle parameter offset: parameter or particle index out of range");
+    for (int k = 0; k < d.num_exception_offsets; k++)
+        if (d.exception_offset_index[2*k] < 0 || d.exception_offset_index[2*k] >= d.num_global_parameters ||
+            d.exception_offset_index[2*k+1] < 0 || d.exception_offset_index[2*k+1] >= d.num_exceptions)
+            throw SnbException(SNB_ERR_INVALID, "exception parameter offset: parameter or exception index out of range");
+    for (int k = 0; k < d.num_derivatives; k++)
+        if (d.derivative_parameters[k] < 0 || d.derivative_parameters[k] >= d.num_global_parameters)
+            throw SnbException(SNB_ERR_INVALID, "derivative parameter index out of range");
+    // user-supplied PME grids: the spreading / interpolation stencils wrap once, which needs at least ORDER points per axis
+    if (d.method == SNB_PME || d.method == SNB_LJPME) {
+        if (d.ewald_alpha != 0.0 && (d.pme_grid[0] < SNB_PME_ORDER || d.pme_grid[1] < SNB_PME_ORDER || d.pme_grid[2] < SNB_PME_ORDER))
+            throw SnbException(SNB_ERR_INVALID, "PME grid dimensions must be at least the spline order (5)");
+        if (d.method == SNB_LJPME && d.dispersion_alpha != 0.0 &&
+            (d.dispersion_grid[0] < SNB_PME_ORDER || d.dispersion_grid[1] < SNB_PME_ORDER || d.dispersion_grid[2] < SNB_PME_ORDER))
+            throw SnbException(SNB_ERR_INVALID, "LJPME grid dimensions must be at least the spline order (5)");
+    }
 }
 
 std::vector<int> find14s(const snb_desc& d) {
@@ -385,6 +426,63 @@ void loadParameters(snb_handle& h, const snb_desc& d) {
         h.exceptionAtoms[e] = make_int2(d.exception_particles[2*e], d.exception_particles[2*e+1]);
     }
     h.paramsDirty = true;
+}
+
+// CSR over `count` items of the offsets given as (parameter, item) pairs; map semantics of the reference (one entry per
+// key, a repeated key keeps its last scale; entries of an item ordered by parameter index)
+void buildOffsetCsr(int count, const std::vector<std::array<int, 2>>& idx, const std::vector<std::array<double, 3>>& scale,
+                    std::vector<int>& start, std::vector<double4>& entries) {
+    std::map<std::pair<int, int>, std::array<double, 3>> byKey;     // (item, parameter) -> scale
+    for (size_t k = 0; k < idx.size(); k++)
+        byKey[{idx[k][1], idx[k][0]}] = scale[k];
+    start.assign(count+1, 0);
+    entries.clear();
+    for (auto& o : byKey)
+        start[o.first.first+1]++;
+    for (int i = 0; i < count; i++)
+        start[i+1] += start[i];
+    for (auto& o : byKey)
+        entries.push_back(make_double4(o.second[0], o.second[1], o.second[2], (double) o.first.second));
+}
+
+// The inputs of the device-side computeParameters (params.cu): base parameters, subsets, offset CSRs.  Called at
+// creation and by updateParametersInContext; synchronous (the staging vectors die here).
+void uploadBaseParameters(snb_handle& h) {
+    std::vector<double> bp(3*(size_t) h.N), be(3*(size_t) h.X);
+    for (int i = 0; i < h.N; i++)
+        for (int c = 0; c < 3; c++)
+            bp[3*(size_t) i+c] = h.baseParticle[i][c];
+    for (int e = 0; e < h.X; e++)
+        for (int c = 0; c < 3; c++)
+            be[3*(size_t) e+c] = h.baseException[e][c];
+    h.baseParticleD.upload(bp.data(), bp.size(), h.stream);
+    h.baseExceptionD.upload(be.data(), be.size(), h.stream);
+    h.subsetD.upload(h.subsets.data(), h.N, h.stream);
+    std::vector<int> start;
+    std::vector<double4> entries;
+    if (!h.particleOffsetIdx.empty()) {
+        buildOffsetCsr(h.N, h.particleOffsetIdx, h.particleOffsetScale, start, entries);
+        h.particleOffsetStart.upload(start.data(), start.size(), h.stream);
+        h.particleOffsetsD.upload(entries.data(), entries.size(), h.stream);
+        CUDA_CHECK(cudaStreamSynchronize(h.stream));
+    }
+    if (!h.exceptionOffsetIdx.empty()) {
+        buildOffsetCsr(h.X, h.exceptionOffsetIdx, h.exceptionOffsetScale, start, entries);
+        h.exceptionOffsetStart.upload(start.data(), start.size(), h.stream);
+        h.exceptionOffsetsD.upload(entries.data(), entries.size(), h.stream);
+        CUDA_CHECK(cudaStreamSynchronize(h.stream));
+    }
+    h.globalsD.alloc(std::max(h.G, 1));
+    h.hGlobals.alloc(std::max(h.G, 1));
+    h.selfD.alloc(2*SNB_MAX_SUBSETS);
+    h.hSelf.alloc(2*SNB_MAX_SUBSETS);
+    std::fill(h.hSelf.p, h.hSelf.p+2*SNB_MAX_SUBSETS, 0.0);
+    if (!h.selfPartial.p) {
+        h.selfPartial.alloc((size_t) SNB_PARAM_MAX_BLOCKS*2*SNB_MAX_SUBSETS);
+        h.paramTicket.alloc(1);
+        CUDA_CHECK(cudaMemsetAsync(h.paramTicket.p, 0, sizeof(unsigned), h.stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(h.stream));
 }
 
 void setupPme(snb_handle& h, PmeGrid& g, const int n[3], double alpha) {
@@ -529,6 +627,7 @@ snb_handle* createHandle(const snb_desc& d) {
         h.params4.alloc(h.N);
         h.subsetD.alloc(h.N);
         h.exception14.alloc(3*(size_t) h.X);
+        uploadBaseParameters(h);
         h.atomCell.alloc(h.N); h.atomSlot.alloc(h.N); h.cellScratch.alloc(h.N);
         h.sortedAtom.alloc(h.NP); h.sortedPos.alloc(h.N);
         h.posqLocal.alloc(h.NP); h.sparams.alloc(h.NP);
@@ -572,17 +671,25 @@ void updateHandle(snb_handle& h, const snb_desc& d) {
     std::vector<int> is14 = find14s(d);
     if ((int) std::count(is14.begin(), is14.end(), 1) != h.num14 || d.num_exceptions != h.X)
         throw SnbException(SNB_ERR_EXCEPTION_SET, "updateParametersInContext: The number of non-excluded exceptions has changed");
+    // the exclusion structure was built from the exception pairs at creation: they must not move
+    // (as the reference's CUDA platform insists, CudaOpenMMLabKernels.cpp:1175-1176)
+    for (int e = 0; e < h.X; e++)
+        if (d.exception_particles[2*e] != h.exceptionAtoms[e].x || d.exception_particles[2*e+1] != h.exceptionAtoms[e].y)
+            throw SnbException(SNB_ERR_EXCEPTION_SET, "updateParametersInContext: The set of non-excluded exceptions has changed");
     CUDA_CHECK(cudaSetDevice(h.device));
     h.is14 = is14;
     h.is14D.upload(h.is14.data(), h.X, h.stream);
     loadParameters(h, d);
-    h.exceptionAtomsD.upload(h.exceptionAtoms.data(), h.X, h.stream);
     CUDA_CHECK(cudaStreamSynchronize(h.stream));
+    uploadBaseParameters(h);
     if (d.use_dispersion_correction && (d.method == SNB_CUTOFF_PERIODIC || d.method == SNB_EWALD || d.method == SNB_PME))
         h.dispersionCoef = calcDispersionCorrections(d);
 }
 
-// computeParameters (:332-385): lambdas, particle and exception parameters with offsets
+// computeParameters (:332-385): the slice lambdas on the host (L values); particle and exception parameters with their
+// offsets and the self energies on the device (params.cu), only when something they depend on changed, with no
+// synchronisation: the kernel is ordered before the evaluation on the handle's stream, the self energies come back with
+// an asynchronous copy that the evaluation's final synchronisation covers.
 void computeParameters(snb_handle& h, const double* globals) {
     for (int s = 0; s < h.L; s++) {
         h.lambdaC[s] = h.sliceParam[s][0] < 0 ? 1.0 : globals[h.sliceParam[s][0]];
@@ -595,42 +702,30 @@ void computeParameters(snb_handle& h, const double* globals) {
         return;
     h.lastOffsetValues = offsetValues;
     h.paramsDirty = false;
-    std::vector<std::array<double, 3>> part = h.baseParticle, exc = h.baseException;
-    // map semantics of the reference: one entry per (parameter, index); a repeated key keeps the last scale
-    std::map<std::pair<int, int>, std::array<double, 3>> pOff, eOff;
-    for (size_t k = 0; k < h.particleOffsetIdx.size(); k++)
-        pOff[{h.particleOffsetIdx[k][0], h.particleOffsetIdx[k][1]}] = h.particleOffsetScale[k];
-    for (size_t k = 0; k < h.exceptionOffsetIdx.size(); k++)
-        eOff[{h.exceptionOffsetIdx[k][0], h.exceptionOffsetIdx[k][1]}] = h.exceptionOffsetScale[k];
-    for (auto& o : pOff)
-        for (int c = 0; c < 3; c++)
-            part[o.first.second][c] += globals[o.first.first]*o.second[c];
-    for (auto& o : eOff)
-        for (int c = 0; c < 3; c++)
-            exc[o.first.second][c] += globals[o.first.first]*o.second[c];
-    std::vector<double> pd(3*(size_t) h.N), e14(3*(size_t) h.X);
-    std::vector<float4> p4(h.N);
-    h.selfC.assign(h.S, 0.0);
-    h.selfV.assign(h.S, 0.0);
-    for (int i = 0; i < h.N; i++) {
-        double q = part[i][0], sig = 0.5*part[i][1], eps = 2.0*sqrt(part[i][2]);
-        pd[3*i] = sig; pd[3*i+1] = eps; pd[3*i+2] = q;
-        p4[i] = make_float4((float) q, (float) sig, (float) eps, 0.f);
-        int sub = h.subsets[i];
-        memcpy(&p4[i].w, &sub, 4);
-        // self energies (ReferenceSlicedLJCoulombIxn.cpp:198-206)
-        h.selfC[sub] -= SNB_ONE_4PI_EPS0*q*q*h.alpha/sqrt(M_PI);
-        if (h.method == SNB_LJPME)
-            h.selfV[sub] += pow(h.dalpha, 6.0)*64.0*pow(sig, 6.0)*pow(eps, 2.0)/12.0;
-    }
-    for (int e = 0; e < h.X; e++) {
-        e14[3*e] = exc[e][1]; e14[3*e+1] = 4.0*exc[e][2]; e14[3*e+2] = exc[e][0];
-    }
-    h.paramsD.upload(pd.data(), pd.size(), h.stream);
-    h.params4.upload(p4.data(), p4.size(), h.stream);
-    h.subsetD.upload(h.subsets.data(), h.N, h.stream);
-    h.exception14.upload(e14.data(), e14.size(), h.stream);
-    CUDA_CHECK(cudaStreamSynchronize(h.stream));    // the staging vectors die with this scope
+    Range range("snb computeParameters");
+    for (int g = 0; g < h.G; g++)
+        h.hGlobals.p[g] = globals[g];
+    if (h.G > 0)
+        CUDA_CHECK(cudaMemcpyAsync(h.globalsD.p, h.hGlobals.p, sizeof(double)*h.G, cudaMemcpyHostToDevice, h.stream));
+    ParamArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.numAtoms = h.N; pa.numExceptions = h.X;
+    const bool ewaldFamily = h.method == SNB_EWALD || h.method == SNB_PME || h.method == SNB_LJPME;
+    pa.selfScaleC = ewaldFamily ? SNB_ONE_4PI_EPS0*h.alpha/sqrt(M_PI) : 0.0;
+    pa.selfScaleV = h.method == SNB_LJPME ? pow(h.dalpha, 6.0)*64.0/12.0 : 0.0;
+    pa.globals = h.globalsD.p;
+    pa.baseParticle = h.baseParticleD.p;
+    pa.particleOffsetStart = h.particleOffsetIdx.empty() ? nullptr : h.particleOffsetStart.p;
+    pa.particleOffsets = h.particleOffsetsD.p;
+    pa.baseException = h.baseExceptionD.p;
+    pa.exceptionOffsetStart = h.exceptionOffsetIdx.empty() ? nullptr : h.exceptionOffsetStart.p;
+    pa.exceptionOffsets = h.exceptionOffsetsD.p;
+    pa.subset = h.subsetD.p;
+    pa.paramsD = h.paramsD.p; pa.params4 = h.params4.p; pa.exception14 = h.exception14.p;
+    pa.selfPartial = h.selfPartial.p; pa.selfOut = h.selfD.p; pa.ticket = h.paramTicket.p;
+    launchComputeParameters(pa, h.stream);
+    CUDA_CHECK(cudaMemcpyAsync(h.hSelf.p, h.selfD.p, sizeof(double)*2*SNB_MAX_SUBSETS, cudaMemcpyDeviceToHost, h.stream));
+    h.paramLaunches++;
 }
 
 void makeBox(const double* box, BoxD& bd, BoxF& bf) {
@@ -806,14 +901,31 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     Timer tm(h);
 
     // ---- inputs ----
-    if (in.hostPositions)
-        CUDA_CHECK(cudaMemcpyAsync(h.posd.p, in.hostPos, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
-    else
+    // multi-GPU with the position broadcast on: rank 0's positions are authoritative -- ONE host->device copy on rank 0,
+    // the other ranks receive them over NVLink -- and every rank then builds the identical sorted order
+    const bool root = h.rank == 0;
+    const bool receivePositions = nccl && h.broadcastPositions && !root;
+    Range* range = new Range("snb inputs");
+    if (in.hostPositions) {
+        if (!receivePositions)
+            CUDA_CHECK(cudaMemcpyAsync(h.posd.p, in.hostPos, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
+    }
+    else if (!receivePositions)
         launchConvertPositions((const float4*) in.posqDev, h.posd.p, h.N, st);
-    if (nccl && h.broadcastPositions)   // rank 0's positions are authoritative: every rank then builds the identical sorted order
+    if (nccl && h.broadcastPositions)
         NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, st));
     CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemsetAsync(h.zeroBlock.p, 0, h.zeroBytes, st));
+    // multi-GPU, rank 0: reciprocal space accumulates into buffers of its own, so that the other terms can be reduced
+    // between the ranks WHILE it runs; its forces and energies are added after the reduction
+    const bool splitRecip = nccl && root;
+    if (splitRecip) {
+        CUDA_CHECK(cudaMemsetAsync(h.forcePme.p, 0, sizeof(long long)*3*(size_t) h.NP, st));
+        CUDA_CHECK(cudaMemsetAsync(h.energyPme.p, 0, sizeof(double)*2*SNB_MAX_SLICES, st));
+    }
+    long long* recipForce = splitRecip ? h.forcePme.p : h.forceOrig.p;
+    double* recipEnergy = splitRecip ? h.energyPme.p : h.energyBuf.p;
+    delete range;
     tm.mark(0);
 
     // ---- exceptions / exclusion corrections: need the inputs only, so they run beside the sort ----
@@ -843,6 +955,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     DirectArgs da;
     memset(&da, 0, sizeof(da));
     if (includeDirect) {
+        Range sortRange("snb sort");
         SortArgs sa;
         memset(&sa, 0, sizeof(sa));
         sa.numAtoms = h.N; sa.paddedAtoms = h.NP; sa.numBlocks = h.NB; sa.numCells = h.numCells; sa.periodic = periodic;
@@ -862,13 +975,14 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
 
     // ---- reciprocal space (rank 0): its own stream, beside the tile list / direct-space kernels ----
     auto reciprocal = [&](cudaStream_t ps) {
+        Range recipRange("snb reciprocal space");
         if (h.method == SNB_EWALD) {
             EwaldArgs ea;
             memset(&ea, 0, sizeof(ea));
             ea.numAtoms = h.N; ea.numSubsets = h.S; ea.numK = h.numK; ea.paddedAtoms = h.NP; ea.alpha = h.alpha;
             ea.sp = h.stepD.p; ea.posd = h.posd.p; ea.paramsD = h.paramsD.p; ea.subset = h.subsetD.p;
-            ea.kvec = h.ewaldK.p; ea.structure = h.ewaldS.p; ea.forceOrig = h.forceOrig.p;
-            ea.energyBuf = needEnergy ? h.energyBuf.p : nullptr;
+            ea.kvec = h.ewaldK.p; ea.structure = h.ewaldS.p; ea.forceOrig = recipForce;
+            ea.energyBuf = needEnergy ? recipEnergy : nullptr;
             launchEwaldReciprocal(ea, includeForces, ps);
             tm.mark(5); tm.mark(6); tm.mark(7); tm.mark(8);
             return;
@@ -876,6 +990,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
             PmeGrid& g = term == 0 ? h.pme : h.dpme;
             PmeArgs pa = pmeArgs(h, term, includeDirect);
+            pa.forceOrig = recipForce; pa.energyBuf = recipEnergy;
             CUFFT_CHECK(cufftSetStream(g.fwd, ps));
             CUFFT_CHECK(cufftSetStream(g.inv, ps));
             launchPmeSpread(pa, ps);
@@ -902,6 +1017,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     if (nccl && includeDirect && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evDirBegin, st));
 
     if (includeDirect) {
+        Range directRange("snb list + direct + exceptions");
         ListArgs la;
         memset(&la, 0, sizeof(la));
         la.numAtoms = h.N; la.numBlocks = h.NB; la.pbcMode = in.pbcMode; la.periodic = periodic;
@@ -919,7 +1035,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         partitionRange(h.NB, h.world, h.rank, rank0Share(h), &lo, &hi);
         la.blockLo = (int) lo; la.blockHi = (int) hi;
         la.bitmapWords = (h.NB+31)/32;
-        launchBuildList(la, st, h.numSMs);
+        CUDA_CHECK(launchBuildList(la, st, h.numSMs));
         tm.mark(2);
 
         DirectParams& p = da.p;
@@ -948,7 +1064,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
         da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.chunkOctet = h.chunkOctet.p; da.maxChunks = (int) h.maxChunks;
         da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
-        launchDirect(da, st, h.numSMs);
+        h.packedLaunched = launchDirect(da, st, h.numSMs);
         if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evDirEnd, st));
         tm.mark(3);
         if (h.X > 0 && !bondedForked)
@@ -965,11 +1081,9 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     }
     if (bondedForked)
         CUDA_CHECK(cudaStreamWaitEvent(st, h.evBondedDone, 0));
-    if (doRecip && !h.timing)
-        CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
+    Range outRange("snb reduce + outputs");
 
     // ---- outputs ----
-    if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evReady, st));
     FinishArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.numAtoms = h.N; fa.paddedAtoms = h.NP;
@@ -977,30 +1091,47 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     fa.forceSorted = h.forceSorted.p; fa.forceOrig = h.forceOrig.p;
     fa.counters = h.counters.p;
     if (nccl) {
-        // ONE collective per evaluation: an int64 all-reduce of [3][N] fixed-point forces followed by the slice-energy
-        // table, the list-overflow flag (every rank must take the same retry decision) and the times every rank
-        // measured in its previous evaluation (every rank derives the same new partition), all in 2^32 fixed
-        // point.  Integer sums are exact: the forces are bit-identical to the single-GPU ones whatever the partition.
+        // Direct space + exceptions of every rank -> rank 0: ncclReduce(sum, int64) of the [3][N] fixed-point forces, grouped
+        // with a small all-reduce of the slice-energy table, the list-overflow flag (every rank must take the same retry
+        // decision) and the times every rank measured in its previous evaluation (every rank derives the same new partition),
+        // all in 2^32 fixed point.  Integer sums are exact: the forces are bit-identical to the single-GPU ones whatever the
+        // partition.  Rank 0's reciprocal space is NOT waited for first: it runs on its own stream while the collective is in
+        // flight, and its forces / energies are added afterwards (reciprocal space stays on rank 0, as in the reference:
+        // platforms/cuda/src/CudaOpenMMLabKernels.cpp:379,405,466).
+        if (!h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evReady, st));
         if (h.loadValid && !h.balanceFrozen)
             CUDA_CHECK(cudaMemcpyAsync(h.energyBuf.p+32*2*SNB_MAX_SLICES+1, h.loadH.p+1, sizeof(double)*(SNB_ENERGY_FLAGS-1), cudaMemcpyHostToDevice, st));
         fa.reduceOut = h.reduceSend.p;
         fa.energyIn = h.energyBuf.p; fa.numEnergy = SNB_ENERGY_DOUBLES; fa.overflowSlot = 32*2*SNB_MAX_SLICES;
         launchFinish(fa, st);
-        const size_t count = 3*(size_t) h.N+SNB_ENERGY_DOUBLES;
-        NCCL_CHECK(nccl, nccl->AllReduce(h.reduceSend.p, h.reduceRecv.p, count, ncclInt64, ncclSum, h.comm, st));
-        if (includeForces)
-            launchEmitReduced(h.reduceRecv.p, h.N, in.hostPositions ? h.forcesOutD.p : nullptr, (long long*) in.forcesFixedOut, st);
+        const size_t nf = 3*(size_t) h.N;
+        NCCL_CHECK(nccl, nccl->GroupStart());
+        NCCL_CHECK(nccl, nccl->Reduce(h.reduceSend.p, h.reduceRecv.p, nf, ncclInt64, ncclSum, 0, h.comm, st));
+        NCCL_CHECK(nccl, nccl->AllReduce(h.reduceSend.p+nf, h.reduceRecv.p+nf, SNB_ENERGY_DOUBLES, ncclInt64, ncclSum, h.comm, st));
+        NCCL_CHECK(nccl, nccl->GroupEnd());
+        if (doRecip && !h.timing)
+            CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
+        if (includeForces && root)
+            launchEmitReduced(h.reduceRecv.p, h.N, h.NP, splitRecip ? h.forcePme.p : nullptr, in.hostPositions ? h.forcesOutD.p : nullptr,
+                              (long long*) in.forcesFixedOut, h.reduceRecv.p+nf+32*2*SNB_MAX_SLICES, st);
     }
-    else if (includeForces) {
-        fa.forcesOut = in.hostPositions ? h.forcesOutD.p : nullptr;
-        fa.forcesFixedOut = (long long*) in.forcesFixedOut;
-        launchFinish(fa, st);
+    else {
+        if (doRecip && !h.timing)
+            CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
+        if (includeForces) {
+            fa.forcesOut = in.hostPositions ? h.forcesOutD.p : nullptr;
+            fa.forcesFixedOut = (long long*) in.forcesFixedOut;
+            launchFinish(fa, st);
+        }
     }
-    if (includeForces && in.hostPositions)
+    if (includeForces && in.hostPositions && (!nccl || root))
         CUDA_CHECK(cudaMemcpyAsync(h.hForces.p, h.forcesOutD.p, sizeof(double)*3*(size_t) h.N, cudaMemcpyDeviceToHost, st));
     tm.mark(9);
-    if (nccl)
+    if (nccl) {
         CUDA_CHECK(cudaMemcpyAsync(h.hEnergyFixed.p, h.reduceRecv.p+3*(size_t) h.N, sizeof(long long)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
+        if (splitRecip)
+            CUDA_CHECK(cudaMemcpyAsync(h.hEnergyPme.p, h.energyPme.p, sizeof(double)*2*SNB_MAX_SLICES, cudaMemcpyDeviceToHost, st));
+    }
     else
         CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, h.energyBuf.p, sizeof(double)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
@@ -1046,6 +1177,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     key.maxChunks = h.maxChunks;
     key.share = h.comm ? rank0Share(h) : 0.0;
+    key.broadcast = h.comm && h.broadcastPositions;
     key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p; key.hostPos = hostPos;
     const bool graphable = h.useGraph && !h.timing && (!h.comm || h.balanceFrozen);
     const bool sameKey = h.graphKeyValid && memcmp(&key, &h.graphKey, sizeof(key)) == 0;
@@ -1086,9 +1218,18 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventElapsedTime(&h.lastDeviceMs, h.evBegin, h.evEnd));
     h.listValid = includeDirect;
-    if (h.comm)
+    if (h.comm) {
+        const NcclApi* nccl = ncclApi(nullptr);
+        ncclResult_t asyncErr = ncclSuccess;
+        if (nccl && nccl->CommGetAsyncError && nccl->CommGetAsyncError(h.comm, &asyncErr) == ncclSuccess && asyncErr != ncclSuccess)
+            throw SnbException(SNB_ERR_CUDA, std::string("NCCL asynchronous error: ")+nccl->GetErrorString(asyncErr));
         for (int k = 0; k < SNB_ENERGY_DOUBLES; k++)
             h.hEnergy.p[k] = (double) h.hEnergyFixed.p[k]*(1.0/SNB_FORCE_SCALE_D);
+        // rank 0: its reciprocal-space energies were kept out of the reduction (they were still being computed)
+        if (h.rank == 0 && includeRecip)
+            for (int k = 0; k < 2*SNB_MAX_SLICES; k++)
+                h.hEnergy.p[k] += h.hEnergyPme.p[k];
+    }
     if (h.comm && includeDirect && !h.timing && !h.balanceFrozen) {
         // load balance: what was measured one evaluation ago has just come back from the all-reduce, identical on every rank
         const double* got = h.hEnergy.p+32*2*SNB_MAX_SLICES;
@@ -1109,6 +1250,9 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
         if (h.rank < 8 && cudaEventElapsedTime(&ms, h.evDirBegin, h.evDirEnd) == cudaSuccess) h.loadH.p[2+h.rank] = ms;
         if (h.rank < 8 && cudaEventElapsedTime(&ms, h.evBegin, h.evReady) == cudaSuccess) h.loadH.p[10+h.rank] = ms;
         if (h.rank == 0 && (flags&SNB_INCLUDE_RECIPROCAL) && pmeFamily && cudaEventElapsedTime(&ms, h.evRecBegin, h.evRecEnd) == cudaSuccess) h.loadH.p[1] = ms;
+        // rank 0 is ready when BOTH its share of direct space and its reciprocal space (own stream, overlapping the reduction) are
+        if (h.rank == 0 && (flags&SNB_INCLUDE_RECIPROCAL) && pmeFamily && cudaEventElapsedTime(&ms, h.evBegin, h.evRecEnd) == cudaSuccess)
+            h.loadH.p[10] = std::max(h.loadH.p[10], (double) ms);
         h.loadValid = true;
         cudaGetLastError();     // an unrecorded event above must not poison the next evaluation's error check
         if (++h.commEvals >= 8) {
@@ -1134,7 +1278,9 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
         CUDA_CHECK(cudaEventElapsedTime(&h.phaseMs[SNB_PHASE_TOTAL], h.ev[0], h.ev[9]));
     }
     h.countersOut[1] = h.hCounters.p[0];
+    h.countersOut[3] = h.paramLaunches;
     h.countersOut[4] = h.graphExec ? 1 : 0;
+    h.countersOut[5] = includeDirect && h.packedLaunched ? 1 : 0;
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
     if (includeDirect) launches += (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
@@ -1158,8 +1304,8 @@ void finishEnergies(snb_handle& h, const double* box, int flags) {
     // added identically everywhere, so every rank returns the same energies.  Forces land on rank 0.)
     if (includeRecip && (h.method == SNB_EWALD || h.method == SNB_PME || h.method == SNB_LJPME))
         for (int s = 0; s < h.S; s++) {
-            h.sliceEnergies[2*(s*(s+3)/2)] += h.selfC[s];
-            h.sliceEnergies[2*(s*(s+3)/2)+1] += h.selfV[s];
+            h.sliceEnergies[2*(s*(s+3)/2)] += h.hSelf.p[2*s];
+            h.sliceEnergies[2*(s*(s+3)/2)+1] += h.hSelf.p[2*s+1];
         }
     if (includeDirect && (h.method == SNB_CUTOFF_PERIODIC || h.method == SNB_EWALD || h.method == SNB_PME)) {
         double volume = box[0]*box[4]*box[8];
@@ -1191,7 +1337,9 @@ void evaluate(snb_handle& h, const double* positions, const void* posqDev, const
         return;
     }
     const double* hostPos = nullptr;
-    if (positions) {
+    if (positions && h.comm && h.broadcastPositions && h.rank != 0)
+        hostPos = h.hPos.p;         // not read: rank 0's positions arrive by broadcast
+    else if (positions) {
         // a page-locked caller buffer is read by the copy engine directly; anything else is staged through the pinned mirror
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, positions) == cudaSuccess && attr.type == cudaMemoryTypeHost)
@@ -1296,7 +1444,8 @@ int snb_execute(snb_handle* h, const double* positions, const double* box, const
     SNB_TRY
     if (!positions) throw SnbException(SNB_ERR_INVALID, "positions are null");
     evaluate(*h, positions, nullptr, box, globals, flags, nullptr);
-    if ((flags&SNB_INCLUDE_FORCES) && forces)
+    // (multi-GPU: the reduced forces are delivered on rank 0)
+    if ((flags&SNB_INCLUDE_FORCES) && forces && (!h->comm || h->rank == 0))
         addForces(forces, h->hForces.p, 3*(size_t) h->N);
     return snb_read_energies(h, flags, energy, slice_energies, derivatives);
     SNB_CATCH
@@ -1399,26 +1548,18 @@ int snb_count_pairs(snb_handle* h, int64_t* num_pairs) {
 
 void snb_free(void* p) { free(p); }
 
-/* debugging aid: print the sorted order and the tile list of the last execute (small systems) */
-int snb_debug_dump(snb_handle* h) {
+/* test hook: capacity of the tile list in chunks (the next evaluation re-allocates; too small a value exercises the
+ * overflow -> grow -> repeat path) */
+int snb_set_list_capacity(snb_handle* h, int64_t chunks) {
     SNB_TRY
-    std::vector<int> sa(h->NP), cnt(8);
-    std::vector<float4> sp(h->NP), pq(h->NP);
-    CUDA_CHECK(cudaMemcpy(sa.data(), h->sortedAtom.p, sizeof(int)*h->NP, cudaMemcpyDeviceToHost));
-    CUDA_CHECK(cudaMemcpy(sp.data(), h->sparams.p, sizeof(float4)*h->NP, cudaMemcpyDeviceToHost));
-    CUDA_CHECK(cudaMemcpy(pq.data(), h->posqLocal.p, sizeof(float4)*h->NP, cudaMemcpyDeviceToHost));
-    CUDA_CHECK(cudaMemcpy(cnt.data(), h->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost));
-    printf("counters:"); for (int k = 0; k < 8; k++) printf(" %d", cnt[k]); printf("\n");
-    for (int k = 0; k < std::min(h->NP, 64); k++) {
-        int sub; memcpy(&sub, &sp[k].z, 4);
-        printf("k=%d atom=%d local=(%g %g %g) q=%g sig=%g eps=%g subset=%d\n", k, sa[k], pq[k].x, pq[k].y, pq[k].z, pq[k].w, sp[k].x, sp[k].y, sub);
-    }
-    int nch = std::min(cnt[0], 4);
-    std::vector<int2> jl(32*(size_t) std::max(nch, 1));
-    CUDA_CHECK(cudaMemcpy(jl.data(), h->jList.p, sizeof(int2)*32*nch, cudaMemcpyDeviceToHost));
-    for (int c = 0; c < nch; c++)
-        for (int l = 0; l < 32; l++)
-            printf("chunk %d slot %d j=%d mask=%08x\n", c, l, jl[32*c+l].x, (unsigned) jl[32*c+l].y);
+    if (!h || chunks < 1) throw SnbException(SNB_ERR_INVALID, "bad list capacity");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    dropGraph(*h);
+    h->jList.release(); h->chunkOctet.release();
+    h->maxChunks = (size_t) chunks;
+    h->jList.alloc(h->maxChunks*32);
+    h->chunkOctet.alloc(h->maxChunks);
     return SNB_OK;
     SNB_CATCH
 }
@@ -1473,6 +1614,12 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size) {
     }
     h->loadValid = false; h->tunedShare = -1;
     h->hEnergyFixed.alloc(SNB_ENERGY_DOUBLES);
+    if (rank == 0) {
+        h->forcePme.alloc(3*(size_t) h->NP);
+        h->energyPme.alloc(2*SNB_MAX_SLICES);
+        h->hEnergyPme.alloc(2*SNB_MAX_SLICES);
+        std::fill(h->hEnergyPme.p, h->hEnergyPme.p+2*SNB_MAX_SLICES, 0.0);
+    }
     h->balanceFrozen = false; h->commEvals = 0;
     return SNB_OK;
     SNB_CATCH

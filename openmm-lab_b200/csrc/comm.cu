@@ -34,6 +34,7 @@ void loadNccl() {
     SNB_SYM(GroupEnd, "ncclGroupEnd")
     SNB_SYM(GetErrorString, "ncclGetErrorString")
 #undef SNB_SYM
+    g_api.CommGetAsyncError = (decltype(g_api.CommGetAsyncError)) dlsym(g_api.lib, "ncclCommGetAsyncError");
 }
 }  // namespace
 

@@ -6,16 +6,18 @@
 template <int KIND> void launchDirectKind(const DirectArgs& a, cudaStream_t st, int grid);
 bool launchDirectPacked(const DirectArgs& a, cudaStream_t st, int grid);    // direct_packed.cu
 
-void launchDirect(const DirectArgs& a, cudaStream_t st, int numSMs) {
+// returns true when the packed-FP32 kernel took the launch (reported through snb_get_counters)
+bool launchDirect(const DirectArgs& a, cudaStream_t st, int numSMs) {
     int grid = numSMs*DIRECT_CTAS_PER_SM;       // one-warp CTAs, all resident, equal contiguous shares of the chunk list
     // PME direct space in an orthorhombic box with <= 2 subsets has two kernels: the packed-FP32 pair loop (large
     // systems) and the general one (api.cu decides: SNB_FLAG_DIRECT_*, else by size)
     if (a.usePacked && launchDirectPacked(a, st, grid))
-        return;
+        return true;
     switch (a.kind) {
         case KIND_PLAIN: launchDirectKind<KIND_PLAIN>(a, st, grid); break;
         case KIND_RF: launchDirectKind<KIND_RF>(a, st, grid); break;
         case KIND_EWALD: launchDirectKind<KIND_EWALD>(a, st, grid); break;
         default: launchDirectKind<KIND_LJPME>(a, st, grid); break;
     }
+    return false;
 }

@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     // Ewald/PME without switching: a masked lane computes on r^2 = 1e10 nm^2, where exp(-a^2 r^2) = 0 kills the
     // Coulomb term exactly and the Lennard-Jones force is ~1e-43 of a real one -- nothing to select away
     constexpr bool SELF_MASKING = !BRANCHY && KIND == KIND_EWALD && !SWITCH;
+    constexpr bool CLEANABLE = !BRANCHY && NSUB > 0 && KIND != KIND_PLAIN;      // the lean copy of the pair loop exists (see `clean`)
     typedef typename Real<R>::vec4 vec4;
     typedef Stage<R> St;
     // one warp per CTA: the two stage buffers are addressed by the slot alone
@@ -407,7 +408,8 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     // this warp's contiguous share of the chunks
     // (values loaded from a uniform address are broadcast through a shuffle so that the compiler KNOWS they are
     // warp-uniform: the loops and branches they steer then carry no divergence bookkeeping)
-    const int numChunks = __shfl_sync(full, min(a.counters[0], a.maxChunks), 0);
+    // (a list that overflowed its buffers holds unwritten chunks: the host discards this pass and repeats it)
+    const int numChunks = __shfl_sync(full, a.counters[2] ? 0 : min(a.counters[0], a.maxChunks), 0);
     const int per = (numChunks+(int) gridDim.x-1)/(int) gridDim.x;
     const int cBegin = min(numChunks, (int) blockIdx.x*per), cEnd = min(numChunks, cBegin+per);
     const BoxD boxd = a.sp->exact.boxd;
@@ -555,11 +557,21 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
         myCutHi = iValid ? (perPair ? c.cutoffHiWide : bandHi) : (R) -1;
         myCutLo = iValid ? (perPair ? c.cutoffLoWide : bandLo) : (R) -1;
         // ---- fix-up: the staged j atom of this lane moves into the octet's block frame
+        // A CLEAN chunk -- no exclusion bit, no padding entry (mask 0xff), every j atom in the same subset -- takes the lean
+        // copy of the pair loop: no mask loads, one lambda pair and one energy pair for the whole chunk (most chunks are)
+        bool clean = false;
+        R subJ0 = 0;
         {
             vec4 pj = St::ld4(sb+lane*St::STRIDE);
             const float4 cJ = ldSharedF4(sb+St::CTR+lane*16);
             fixupShift<R>(pj, cJ, cI, oc, PBC == PBC_SHIFT && !perPair, wb);
             St::st4(sb+lane*St::STRIDE, pj);
+            if (CLEANABLE) {
+                const unsigned mask = ldSharedU32(entBase+(unsigned) (ch&3)*256u+4u);
+                const R subJ = *(const R*) (&sStage[buf][0]+St::PRM+lane*St::STRIDE+2*sizeof(R));
+                subJ0 = __shfl_sync(full, subJ, 0);
+                clean = !__any_sync(full, mask != 0u || subJ != subJ0);
+            }
         }
         __syncwarp();
         R fix = 0, fiy = 0, fiz = 0, fjx = 0, fjy = 0, fjz = 0;
@@ -570,14 +582,24 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
             t.eC[s] = t.eV[s] = 0;
         const unsigned own = sb+ownOff;
         // ---- 8 steps of 32 pairs: straight-line code (the rare per-pair-wrapping octets take their own copy) ----
-        auto steps = [&](auto perPairTag) {
+        auto steps = [&](auto perPairTag, auto cleanTag) {
         constexpr bool PERPAIR = decltype(perPairTag)::value;
+        constexpr bool CLEAN = decltype(cleanTag)::value;
+        // CLEAN: the lambdas of the chunk's one j subset
+        R lcC = t.lamC[0], lvC = t.lamV[0];
+        if (CLEAN && NSUB > 1) {
+#pragma unroll
+            for (int u = 1; u < NS; u++) {
+                lcC = subJ0 == (R) u ? t.lamC[u] : lcC;
+                lvC = subJ0 == (R) u ? t.lamV[u] : lvC;
+            }
+        }
 #pragma unroll STEP_UNROLL
         for (int s = 0; s < 8; s++) {
             const unsigned ad = own^(unsigned) (s*St::STRIDE);
             const unsigned aux = St::STRIDE == St::AUXS ? ad+St::AUX : sb+St::AUX+(unsigned) (lane^s)*St::AUXS;
             const vec4 q = St::ld4(ad);
-            const unsigned mj = ldSharedU32(aux+4);
+            const unsigned mj = CLEAN ? 0u : ldSharedU32(aux+4);
             R dx = pi.x-q.x, dy = pi.y-q.y, dz = pi.z-q.z;
             if (PBC == PBC_SHIFT && PERPAIR) {
                 dx -= bAx*Real<R>::rint(dx*iAx);
@@ -610,8 +632,8 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 // masked lanes compute on r^2 = 1 (self pairs have r = 0, excluded neighbours overflow r^-12)
                 pairMath<R, KIND, SWITCH>(c, BRANCHY ? r2 : (in ? r2 : (R) (SELF_MASKING ? 1e10 : 1)), pi.w*q.w, si4.x, si4.y, si4.w, prm.x, prm.y, prm.w, fc, fv, ec, ev, invR2);
                 R lc, lv;
-                if (NSUB == 1) {
-                    lc = t.lamC[0]; lv = t.lamV[0];
+                if (NSUB == 1 || CLEAN) {
+                    lc = lcC; lv = lvC;
                 }
                 else if (TWO) {
                     lc = fma(prm.z, dLamC, t.lamC[0]);
@@ -638,7 +660,10 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
                 fix += f*dx; fiy += f*dy; fiz += f*dz;
                 fjx -= f*dx; fjy -= f*dy; fjz -= f*dz;
                 if (ENERGY) {
-                    if (TWO) {
+                    if (CLEAN) {
+                        eCt += ec; eVt += ev;
+                    }
+                    else if (TWO) {
                         eCt += ec; eVt += ev;
                         eC1 = fma(prm.z, ec, eC1); eV1 = fma(prm.z, ev, eV1);
                     }
@@ -671,9 +696,23 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
         }
         };
         if (PBC == PBC_SHIFT && perPair)
-            steps(std::true_type());
+            steps(std::true_type(), std::false_type());     // rare (octets wider than half the box minus the cutoff): one copy
+        else if (CLEANABLE && clean)
+            steps(std::false_type(), std::integral_constant<bool, CLEANABLE>());
         else
-            steps(std::false_type());
+            steps(std::false_type(), std::false_type());
+        if (ENERGY && CLEANABLE && clean && !(PBC == PBC_SHIFT && perPair)) {
+            // the chunk's energies belong to its one j subset
+            if (TWO) { eC1 = subJ0*eCt; eV1 = subJ0*eVt; }
+            else if (NSUB == 1) { t.eC[0] = eCt; t.eV[0] = eVt; }
+            else if (NSUB > 2) {
+#pragma unroll
+                for (int u = 0; u < NS; u++) {
+                    t.eC[u] = subJ0 == (R) u ? eCt : (R) 0;
+                    t.eV[u] = subJ0 == (R) u ? eVt : (R) 0;
+                }
+            }
+        }
         if (KIND != KIND_PLAIN && __any_sync(full, bandMask != 0u)) {
             if (bandMask) {
                 DirectOut o;

@@ -5,7 +5,7 @@
 // fixed-point accumulation as k_direct.  What changes is the pair loop: sm_100 has two-wide FP32 instructions
 // (FFMA2 / FMUL2 / FADD2: two independent IEEE operations per lane per issue slot; measured on B200 the FMA pipe
 // delivers the same 70 TFLOP/s either way, but the packed form needs half the issue slots, and k_direct is
-// issue-bound: scratch/ubench/fp32peak.cu).  So every lane works on TWO j atoms at a time:
+// issue-bound: tools/ubench/fp32peak.cu).  So every lane works on TWO j atoms at a time:
 //   * after the fix-up pass the 32 staged j atoms are re-laid out as 16 slot pairs, structure-of-arrays
 //     within the pair -- (x0,x1,y0,y1) (z0,z1,q0,q1) (sig0,sig1,eps0,eps1) (sub0,sub1,mask0,mask1) -- so one
 //     LDS.128 hands the packed instructions their operands in aligned register pairs;
@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
     const int copy = lane>>3, k = lane&7;
     const unsigned full = 0xffffffffu;
     const DirectConsts<float>& c = a.cf;
-    const int numChunks = __shfl_sync(full, min(a.counters[0], a.maxChunks), 0);
+    // a list that overflowed its buffers holds unwritten chunks: the host discards this pass and repeats it
+    const int numChunks = __shfl_sync(full, a.counters[2] ? 0 : min(a.counters[0], a.maxChunks), 0);
     const int per = (numChunks+(int) gridDim.x-1)/(int) gridDim.x;
     const int cBegin = min(numChunks, (int) blockIdx.x*per), cEnd = min(numChunks, cBegin+per);
     const WrapBox<float> wb = makeWrapBox<float>(a.sp->exact.boxd);
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
     bool iValid = false;
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), si4 = pi;
     float4 cI = pi, oc = pi;
-    float myCutHi = -1.f, myCutLo = -1.f, lamC0 = 0.f, lamV0 = 0.f, dLamC = 0.f, dLamV = 0.f;
+    float myCutHi = -1.f, myCutLo = -1.f, myCutMid = -1.f, myBandTol = 0.f, lamC0 = 0.f, lamV0 = 0.f, dLamC = 0.f, dLamV = 0.f;
     double EC[NSUB], EV[NSUB];
 #pragma unroll
     for (int s = 0; s < NSUB; s++)
@@ -176,9 +177,16 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
             }
         }
         const bool perPair = (octCur&0x40000000) != 0;      // octet too wide for one image per j atom
+        bool clean = false;
+        float subJ0 = 0.f;
         // a padding lane can never be "in range": its bounds are negative
         myCutHi = iValid ? (perPair ? c.cutoffHiWide : bandHi) : -1.f;
         myCutLo = iValid ? (perPair ? c.cutoffLoWide : bandLo) : -1.f;
+        // the pair loop only has to NOTICE a band pair (bandRescan then classifies every pair of the chunk again with the
+        // exact bounds): |r^2 - mid| < tol, a superset of [lo, hi) -- the difference is exact (Sterbenz), mid carries half
+        // an ulp (3e-8 against a band of 2.6e-6 at least), the tolerance is widened by 5% + 1e-7 for it
+        myCutMid = iValid ? 0.5f*(myCutHi+myCutLo) : -1.f;
+        myBandTol = iValid ? fmaf(0.5f*(myCutHi-myCutLo), 1.05f, 1e-7f) : 0.f;
         // ---- fix-up: this lane's staged j atom moves into the octet's block frame, then into the pair planes
         {
             float4 pj = St::ld4(sb+lane*St::STRIDE);
@@ -193,19 +201,29 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
             stSharedF32(st1+PL_ZQ, swapStores ? pj.w : pj.z); stSharedF32(st2+PL_ZQ, swapStores ? pj.z : pj.w);
             stSharedF32(st1+PL_SE, swapStores ? prm.y : prm.x); stSharedF32(st2+PL_SE, swapStores ? prm.x : prm.y);
             stSharedF32(st1+PL_SM, swapStores ? maskF : prm.z); stSharedF32(st2+PL_SM, swapStores ? prm.z : maskF);
+            // a CLEAN chunk -- no exclusion bit, no padding entry (mask 0xff), every j atom in the same subset -- takes the lean
+            // copy of the pair loop: no mask plane, one lambda pair and one energy pair for the whole chunk.  Nineteen chunks in twenty.
+            subJ0 = __shfl_sync(full, prm.z, 0);
+            clean = !__any_sync(full, mask != 0u || prm.z != subJ0);
         }
         __syncwarp();
         float2 fix = bc(0.f), fiy = bc(0.f), fiz = bc(0.f), fjx = bc(0.f), fjy = bc(0.f), fjz = bc(0.f);
         float2 eCt = bc(0.f), eVt = bc(0.f), eC1 = bc(0.f), eV1 = bc(0.f);
         bool anyBand = false;
         // ---- 4 double-steps of 64 pairs ----
-        auto steps = [&](auto perPairTag) {
+        auto steps = [&](auto perPairTag, auto cleanTag) {
         constexpr bool PERPAIR = decltype(perPairTag)::value;
+        constexpr bool CLEAN = decltype(cleanTag)::value;
+        // CLEAN: the lambdas of the chunk's one j subset
+        const float lamCc = fmaf(subJ0, dLamC, lamC0), lamVc = fmaf(subJ0, dLamV, lamV0);
 #pragma unroll
         for (int d = 0; d < 4; d++) {
             const unsigned ad = ownPair^(unsigned) (d*16);
             const float4 xy = ldSharedF4(ad+PL_XY), zq = ldSharedF4(ad+PL_ZQ);
-            const float4 se = ldSharedF4(ad+PL_SE), sm = ldSharedF4(ad+PL_SM);
+            const float4 se = ldSharedF4(ad+PL_SE);
+            float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!CLEAN)
+                sm = ldSharedF4(ad+PL_SM);
             const float2 m1 = bc(-1.f);
             float2 dx = fma2(make_float2(xy.x, xy.y), m1, bc(pi.x));
             float2 dy = fma2(make_float2(xy.z, xy.w), m1, bc(pi.y));
@@ -219,9 +237,10 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
                 dz = fma2(bc(-wb.cz), make_float2(rintf(t.x), rintf(t.y)), dz);
             }
             const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-            const bool ok0 = !(__float_as_uint(sm.z)&kBit), ok1 = !(__float_as_uint(sm.w)&kBit);
+            const bool ok0 = CLEAN || !(__float_as_uint(sm.z)&kBit), ok1 = CLEAN || !(__float_as_uint(sm.w)&kBit);
             const bool in0 = ok0 && r2.x < myCutLo, in1 = ok1 && r2.y < myCutLo;
-            anyBand |= (ok0 & !(r2.x < myCutLo) & (r2.x < myCutHi)) | (ok1 & !(r2.y < myCutLo) & (r2.y < myCutHi));
+            const float2 off = add2(r2, bc(-myCutMid));
+            anyBand |= (ok0 & (fabsf(off.x) < myBandTol)) | (ok1 & (fabsf(off.y) < myBandTol));
             // a masked pair computes on r^2 = 1e10 nm^2: exp(-a^2 r^2) = 0 kills the Coulomb term exactly, the
             // Lennard-Jones force is ~1e-43 of a real one
             const float2 r2m = make_float2(in0 ? r2.x : 1e10f, in1 ? r2.y : 1e10f);
@@ -266,15 +285,17 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
             // lambda-weighted force over r
             float2 f;
             const float2 subJ = make_float2(sm.x, sm.y);
-            if (NSUB == 2)
+            if (NSUB == 2 && !CLEAN)
                 f = mul2(fma2(fma2(subJ, bc(dLamV), bc(lamV0)), fv, mul2(fma2(subJ, bc(dLamC), bc(lamC0)), fc)), invR2);
+            else if (NSUB == 2)
+                f = mul2(fma2(bc(lamVc), fv, mul2(bc(lamCc), fc)), invR2);
             else
                 f = mul2(fma2(bc(lamV0), fv, mul2(bc(lamC0), fc)), invR2);
             fix = fma2(f, dx, fix); fiy = fma2(f, dy, fiy); fiz = fma2(f, dz, fiz);
             fjx = fma2(f, dx, fjx); fjy = fma2(f, dy, fjy); fjz = fma2(f, dz, fjz);     // sign applied once, at the end
             if (ENERGY) {
                 eCt = add2(eCt, ec); eVt = add2(eVt, ev);
-                if (NSUB == 2) {
+                if (NSUB == 2 && !CLEAN) {
                     eC1 = fma2(subJ, ec, eC1); eV1 = fma2(subJ, ev, eV1);
                 }
             }
@@ -297,9 +318,15 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
         }
         };
         if (perPair)
-            steps(std::true_type());
+            steps(std::true_type(), std::false_type());     // rare (octets wider than half the box minus the cutoff): one copy
+        else if (clean)
+            steps(std::false_type(), std::true_type());
         else
-            steps(std::false_type());
+            steps(std::false_type(), std::false_type());
+        if (ENERGY && NSUB == 2 && clean && !perPair) {
+            // the chunk's energies belong to its one j subset
+            eC1 = mul2(eCt, bc(subJ0)); eV1 = mul2(eVt, bc(subJ0));
+        }
         if (__any_sync(full, anyBand)) {
             if (anyBand) {
                 DirectOut o;

@@ -12,26 +12,31 @@ __global__ void k_finish(FinishArgs a) {
     if (i >= a.numAtoms)
         return;
     const int k = a.sortedPos ? a.sortedPos[i] : i;
+    // a pass whose tile list overflowed is discarded and repeated by the host: it must leave the caller's accumulator alone
+    const bool discard = a.counters[2] != 0;
     for (int c = 0; c < 3; c++) {
         long long f = a.forceSorted[c*a.paddedAtoms+k]+a.forceOrig[c*a.paddedAtoms+i];
         if (a.forcesOut)
             a.forcesOut[3*i+c] = (double) f*(1.0/SNB_FORCE_SCALE_D);
-        if (a.forcesFixedOut)
+        if (a.forcesFixedOut && !discard)
             a.forcesFixedOut[(size_t) c*a.numAtoms+i] += f;
         if (a.reduceOut)
             a.reduceOut[(size_t) c*a.numAtoms+i] = f;
     }
 }
 
-__global__ void k_emitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut) {
+__global__ void k_emitReduced(const long long* reduced, int numAtoms, int paddedAtoms, const long long* extra, double* forcesOut, long long* forcesFixedOut, const long long* overflow) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
     if (i >= numAtoms)
         return;
+    // some rank's tile list overflowed: every rank repeats the evaluation, nothing of this pass may reach the caller's accumulator
+    const bool discard = overflow && *overflow != 0;
     for (int c = 0; c < 3; c++) {
-        const long long f = reduced[(size_t) c*numAtoms+i];
+        // extra: rank 0's reciprocal-space forces ([3][paddedAtoms], original order), computed while the reduction ran
+        const long long f = reduced[(size_t) c*numAtoms+i]+(extra ? extra[(size_t) c*paddedAtoms+i] : 0ll);
         if (forcesOut)
             forcesOut[3*i+c] = (double) f*(1.0/SNB_FORCE_SCALE_D);
-        if (forcesFixedOut)
+        if (forcesFixedOut && !discard)
             forcesFixedOut[(size_t) c*numAtoms+i] += f;
     }
 }
@@ -50,9 +55,10 @@ void launchFinish(const FinishArgs& a, cudaStream_t stream) {
         k_finish<<<(n+255)/256, 256, 0, stream>>>(a);
 }
 
-void launchEmitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut, cudaStream_t stream) {
+void launchEmitReduced(const long long* reduced, int numAtoms, int paddedAtoms, const long long* extra, double* forcesOut, long long* forcesFixedOut,
+                       const long long* overflow, cudaStream_t stream) {
     if (numAtoms > 0)
-        k_emitReduced<<<(numAtoms+255)/256, 256, 0, stream>>>(reduced, numAtoms, forcesOut, forcesFixedOut);
+        k_emitReduced<<<(numAtoms+255)/256, 256, 0, stream>>>(reduced, numAtoms, paddedAtoms, extra, forcesOut, forcesFixedOut, overflow);
 }
 
 void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream) {

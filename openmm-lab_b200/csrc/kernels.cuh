@@ -4,6 +4,29 @@
 
 #include "snb_core.cuh"
 
+// ---- computeParameters on the device (params.cu)
+#define SNB_PARAM_MAX_BLOCKS 296
+struct ParamArgs {
+    int numAtoms, numExceptions;
+    double selfScaleC;              // ONE_4PI_EPS0 alpha / sqrt(pi)   (0 outside the Ewald family)
+    double selfScaleV;              // alpha_d^6 64 / 12               (0 unless LJPME)
+    const double* globals;          // [G] current values of the Context parameters
+    const double* baseParticle;     // [N][3] charge, sigma, epsilon as given
+    const int* particleOffsetStart; // [N+1] CSR over particles, or null when the force has no particle offsets
+    const double4* particleOffsets; // (chargeScale, sigmaScale, epsilonScale, parameter index)
+    const double* baseException;    // [X][3] chargeProd, sigma, epsilon as given
+    const int* exceptionOffsetStart;
+    const double4* exceptionOffsets;
+    const int* subset;              // [N]
+    double* paramsD;                // out [N][3] sigma/2, 2 sqrt(eps), q
+    float4* params4;                // out [N]    q, sigma/2, 2 sqrt(eps), subset bits
+    double* exception14;            // out [X][3] sigma, 4 eps, chargeProd
+    double* selfPartial;            // scratch [SNB_PARAM_MAX_BLOCKS][2*SNB_MAX_SUBSETS]
+    double* selfOut;                // out [SNB_MAX_SUBSETS][2] self energies per subset (Coulomb, dispersion)
+    unsigned* ticket;               // zero between launches
+};
+void launchComputeParameters(const ParamArgs& a, cudaStream_t stream);
+
 struct SortArgs {
     int numAtoms, paddedAtoms, numBlocks, numCells, periodic;
     int cellDim[3];
@@ -48,7 +71,7 @@ struct ListArgs {
     int blockLo, blockHi;   // this rank's i blocks
     int bitmapWords;        // ceil(numBlocks/32)
 };
-void launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
+cudaError_t launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 
 #ifndef DIRECT_CTAS_PER_SM
 #define DIRECT_CTAS_PER_SM 16       /* one-warp CTAs of the direct-space kernel resident per SM (register budget 65536/32/this) */
@@ -88,7 +111,7 @@ struct DirectArgs {
     unsigned long long* pairDumpCount;
     long long pairDumpCapacity;
 };
-void launchDirect(const DirectArgs& a, cudaStream_t stream, int numSMs);
+bool launchDirect(const DirectArgs& a, cudaStream_t stream, int numSMs);      // true: the packed-FP32 kernel ran
 
 struct BondedArgs {
     int numExceptions, periodicExceptions, ewald, ljpme, includeForces;
@@ -157,7 +180,10 @@ struct FinishArgs {
     int numEnergy, overflowSlot;    // entries of energyIn; which of them takes counters[2] instead
 };
 // after the force reduction (root only): reduced [3][N] fixed-point forces -> the caller's layout
-void launchEmitReduced(const long long* reduced, int numAtoms, double* forcesOut, long long* forcesFixedOut, cudaStream_t stream);
+// overflow: the reduced list-overflow flag (device pointer, nonzero = the pass is being discarded) or null
+// extra: forces to add on top of the reduced ones ([3][paddedAtoms], original order), or null
+void launchEmitReduced(const long long* reduced, int numAtoms, int paddedAtoms, const long long* extra, double* forcesOut, long long* forcesFixedOut,
+                       const long long* overflow, cudaStream_t stream);
 void launchFinish(const FinishArgs& a, cudaStream_t stream);
 void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream);
 

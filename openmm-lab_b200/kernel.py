@@ -191,6 +191,12 @@ class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
         self._check(self._lib.snb_get_last_device_ms(self._handle, C.byref(ms)))
         return ms.value
 
+    def setListCapacity(self, chunks):
+        """Test hook (snb_set_list_capacity): too small a tile-list capacity exercises overflow -> grow -> repeat."""
+        fn = self._lib.snb_set_list_capacity
+        fn.argtypes = [C.c_void_p, C.c_int64]
+        self._check(fn(self._handle, int(chunks)))
+
     def getCounters(self):
         out = (C.c_int64*8)()
         self._check(self._lib.snb_get_counters(self._handle, out))

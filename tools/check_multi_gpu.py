@@ -5,9 +5,12 @@
         tools/check_multi_gpu.py [workload ...]
 
 Every rank takes its share of each evaluation (tile list + exceptions partitioned, reciprocal space on
-rank 0, NCCL broadcast / reduce); rank 0 then repeats the evaluation alone on a second, single-GPU
-kernel and compares: forces must be BIT-IDENTICAL in the deterministic mode (2^32 fixed-point sums do
-not depend on the partition), slice energies / derivatives equal to 1e-9 (they travel in 2^32 fixed point with the forces) and identical on every rank.
+rank 0 overlapping the reduction, NCCL broadcast / reduce to rank 0); rank 0 -- where the results are
+delivered -- then repeats the evaluation alone on a second, single-GPU kernel and compares: forces must
+be BIT-IDENTICAL in the deterministic mode (2^32 fixed-point sums do not depend on the partition), slice
+energies / derivatives equal to 1e-9 (they travel in 2^32 fixed point), and the partition must cover every
+interacting pair exactly once.  Mirrors the reference's testParallelComputation
+(platforms/cuda/tests/TestCudaSlicedNonbondedForce.cpp:17-80).
 """
 import os
 import sys
@@ -52,8 +55,6 @@ def main():
             graphs = kernel.getCounters()[4]
             pairs = torch.tensor([kernel.countPairs()])
             dist.all_reduce(pairs)
-            energies = [None]*world
-            dist.all_gather_object(energies, (e, kernel.sliceEnergies.tolist()))
             if rank == 0:
                 solo = mm.Context(w.system, "B200", props)
                 solo.setPositions(w.positions)
@@ -69,11 +70,10 @@ def main():
                 dd = max(abs(ctx._energyParameterDerivatives[k]-solo._energyParameterDerivatives[k]) for k in solo._energyParameterDerivatives) \
                     if solo._energyParameterDerivatives else 0.0
                 same_pairs = int(pairs.item()) == k1.countPairs()
-                same_everywhere = all(x[0] == e for x in energies)
-                good = same_forces and (share is not None or graphs == 1) and de < 1e-9 and ds < 1e-9 and same_pairs and same_everywhere
+                good = same_forces and (share is not None or graphs == 1) and de < 1e-9 and ds < 1e-9 and dd < 1e-9*max(1.0, abs(e1)) and same_pairs
                 ok = ok and good
-                print("%-6s world=%d rank0_share=%-5s forces bit-identical=%s  pairs equal=%s  |dE|/E=%.1e  slices=%.1e  derivs=%.1e  energies on all ranks=%s  graph=%d  %s"
-                      % (name, world, share, same_forces, same_pairs, de, ds, dd, same_everywhere, graphs, "OK" if good else "FAIL"), flush=True)
+                print("%-6s world=%d rank0_share=%-5s forces bit-identical=%s  pairs equal=%s  |dE|/E=%.1e  slices=%.1e  derivs=%.1e  graph=%d  %s"
+                      % (name, world, share, same_forces, same_pairs, de, ds, dd, graphs, "OK" if good else "FAIL"), flush=True)
             del kernel, ctx
             dist.barrier()
     flag = torch.tensor([1 if ok else 0])
