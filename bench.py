@@ -492,7 +492,7 @@ def run_b200(args):
     steps, warmup = (min(args.steps, 30), min(args.warmup, 5)) if big else (args.steps, args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
-    main = Runner(name, local, rank, world, dist, partition=partition)
+    main = Runner(name, local, rank, world, dist, partition=partition, properties={"DirectKernel": args.direct_kernel})
     res = main.measure(steps, warmup, flush, peaks)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -567,6 +567,8 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the sub-objects of the other workloads")
     ap.add_argument("--no-stmv", action="store_true", help="(kept for old command lines) same as --no-others")
     ap.add_argument("--multi", default="auto", choices=["auto", "replicas", "partition"])
+    ap.add_argument("--direct-kernel", default="auto", choices=["auto", "packed", "general"],
+                    help="platform property DirectKernel of the main workload (A/B measurements)")
     args = ap.parse_args()
     args.no_others = args.no_others or args.no_stmv
     if args.impl == "reference":

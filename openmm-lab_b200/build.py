@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libslicednb_b200.so")
 SOURCES = ["api.cu", "comm.cu", "sort.cu", "neighbor.cu", "direct.cu", "direct_plain.cu", "direct_rf.cu", "direct_ewald.cu",
-           "direct_ljpme.cu", "direct_packed.cu", "bonded.cu", "pme.cu", "ewald.cu", "finish.cu", "params.cu"]
+           "direct_ljpme.cu", "direct_packed.cu", "bonded.cu", "pme.cu", "pme_brick.cu", "ewald.cu", "finish.cu", "params.cu"]
 HEADERS = ["snb_core.cuh", "kernels.cuh", "comm.cuh", "direct_impl.cuh", "../../include/slicednb.h", "../../include/snb_constants.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true"]

@@ -161,6 +161,10 @@ struct PmeGrid {
     bool planned = false;
     DevBuf<char> real, cplx, eterm;     // float or double, by the handle's precision
     DevBuf<long long> fixed;            // deterministic spreading
+    DevBuf<float> pad;                  // brick path: padded copy of the grids addressed by the TMA bricks
+    alignas(64) CUtensorMap brickMap;
+    int nzp = 0;
+    bool brick = false;
     DevBuf<double> moduli[3];
     double etermBox[6] = {0, 0, 0, 0, 0, 0};
     bool etermValid = false;
@@ -495,6 +499,14 @@ void setupPme(snb_handle& h, PmeGrid& g, const int n[3], double alpha) {
     g.eterm.alloc(GC*rb);
     if (h.deterministic)
         g.fixed.alloc(G*h.S);
+    // shared-memory bricks + TMA (pme_brick.cu): mixed precision, float atomics allowed (not the deterministic mode),
+    // every dimension at least one brick long
+    g.brick = false;
+    if (!h.doublePrecision && !h.deterministic && n[0] >= 16 && n[1] >= 16 && n[2] >= 16 && getenv("SNB_NO_PME_BRICKS") == nullptr) {
+        g.nzp = (n[2]+4+3)&~3;
+        g.pad.alloc((size_t) h.S*(n[0]+4)*(n[1]+4)*g.nzp);
+        g.brick = makeBrickTensorMap(&g.brickMap, g.pad.p, h.S, n[0], n[1], g.nzp);
+    }
     int dims[3] = {n[0], n[1], n[2]};
     CUFFT_CHECK(cufftPlanMany(&g.fwd, 3, dims, nullptr, 1, (int) G, nullptr, 1, (int) GC, h.doublePrecision ? CUFFT_D2Z : CUFFT_R2C, h.S));
     CUFFT_CHECK(cufftPlanMany(&g.inv, 3, dims, nullptr, 1, (int) GC, nullptr, 1, (int) G, h.doublePrecision ? CUFFT_Z2D : CUFFT_C2R, h.S));
@@ -869,6 +881,7 @@ PmeArgs pmeArgs(snb_handle& h, int term, bool sorted) {
     pa.sortedAtom = sorted ? h.sortedAtom.p : nullptr;
     pa.params4 = h.params4.p; pa.paramsD = h.paramsD.p; pa.grid = g.real.p; pa.cgrid = g.cplx.p; pa.eterm = g.eterm.p;
     pa.gridFixed = h.deterministic ? g.fixed.p : nullptr;
+    pa.gridPad = g.brick ? g.pad.p : nullptr; pa.nzp = g.nzp;
     for (int k = 0; k < 3; k++) pa.moduli[k] = g.moduli[k].p;
     pa.forceOrig = h.forceOrig.p; pa.paddedAtoms = h.NP; pa.energyBuf = h.energyBuf.p;
     return pa;
@@ -993,7 +1006,11 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             pa.forceOrig = recipForce; pa.energyBuf = recipEnergy;
             CUFFT_CHECK(cufftSetStream(g.fwd, ps));
             CUFFT_CHECK(cufftSetStream(g.inv, ps));
-            launchPmeSpread(pa, ps);
+            // atoms in sorted order + mixed precision: shared-memory bricks moved by TMA; else the per-atom kernels
+            const bool bricks = g.brick && pa.sortedAtom != nullptr;
+            static const bool noBrickSpread = getenv("SNB_NO_BRICK_SPREAD") != nullptr, noBrickInterp = getenv("SNB_NO_BRICK_INTERP") != nullptr;
+            if (bricks && !noBrickSpread) launchPmeSpreadBrick(pa, g.brickMap, ps);
+            else launchPmeSpread(pa, ps);
             if (term == 0) tm.mark(5);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecD2Z(g.fwd, (double*) g.real.p, (cufftDoubleComplex*) g.cplx.p));
             else CUFFT_CHECK(cufftExecR2C(g.fwd, (float*) g.real.p, (cufftComplex*) g.cplx.p));
@@ -1002,7 +1019,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             if (term == 0) tm.mark(7);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecZ2D(g.inv, (cufftDoubleComplex*) g.cplx.p, (double*) g.real.p));
             else CUFFT_CHECK(cufftExecC2R(g.inv, (cufftComplex*) g.cplx.p, (float*) g.real.p));
-            launchPmeInterpolate(pa, ps);
+            if (bricks && !noBrickInterp) launchPmeInterpolateBrick(pa, g.brickMap, ps);
+            else launchPmeInterpolate(pa, ps);
             if (term == 0) tm.mark(8);
         }
     };
@@ -1285,7 +1303,9 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     long long launches = 0;
     if (includeDirect) launches += (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
     if (includeRecip && h.method == SNB_EWALD && h.rank == 0) launches += 2;    // structure factors, forces
-    if (includeRecip && pmeFamily && h.rank == 0) launches += (h.deterministic ? 5 : 4)*(h.method == SNB_LJPME ? 2 : 1);    // spread (+finish), convolution, combine, interpolate
+    if (includeRecip && pmeFamily && h.rank == 0)      // spread (+ finish or fold), convolution, combine, interpolate
+        for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++)
+            launches += (h.deterministic || ((term == 0 ? h.pme : h.dpme).brick && includeDirect)) ? 5 : 4;
     if (includeForces || h.comm) launches += 1+(h.comm && includeForces ? 1 : 0);
     if (posqDev) launches += 1;
     h.countersOut[2] = launches;

@@ -4,6 +4,8 @@
 
 #include "snb_core.cuh"
 
+#include <cuda.h>      /* CUtensorMap (type only: the encoder is resolved at run time through cudaGetDriverEntryPoint) */
+
 // ---- computeParameters on the device (params.cu)
 #define SNB_PARAM_MAX_BLOCKS 296
 struct ParamArgs {
@@ -140,6 +142,8 @@ struct PmeArgs {
     const float4* params4;          // q in .x ; sigma/2, 2 sqrt(eps) in .y .z (dispersion "charge" = 8 s^3 e) ; subset bits in .w
     const double* paramsD;          // [N][3] sigma/2, 2 sqrt(eps), q
     void* grid;                     // [S][nx][ny][nz] real (float or double)
+    float* gridPad;                 // brick path (pme_brick.cu): [S][nx+4][ny+4][nzp] padded copy the TMA bricks address, or null
+    int nzp;                        // its row length: nz+4 rounded up to a multiple of 4 floats
     long long* gridFixed;           // same shape, 2^40 fixed point (deterministic spreading), or null
     void* cgrid;                    // [S][nx][ny][nz/2+1] complex
     void* eterm;                    // [nx][ny][nz/2+1]
@@ -152,6 +156,10 @@ void launchPmeEterm(const PmeArgs& a, cudaStream_t stream);
 void launchPmeSpread(const PmeArgs& a, cudaStream_t stream);
 void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);
+// brick path (mixed precision, sorted atoms): shared-memory grid bricks moved by TMA
+bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numSubsets, int nx, int ny, int nzp);
+void launchPmeSpreadBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
+void launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
 
 struct EwaldArgs {
     int numAtoms, numSubsets, numK, paddedAtoms;

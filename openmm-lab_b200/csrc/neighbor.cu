@@ -2,12 +2,10 @@
 // atoms, one warp per octet.
 //
 // The sorted atoms are cut into blocks of 32 (j side) and octets of 8 (i side; 4 per block).  For
-// every octet the list holds the later atoms that come within the cutoff of AT LEAST ONE ATOM of the
-// octet -- the tile interaction flags, compacted into chunks of 32 j atoms -- each with an 8-bit
-// exclusion mask over the octet's atoms.  Candidates are found with the octet's bounding box (much
-// tighter than a 32-atom block's: ~45% of the pairs a tile visits would be in range instead of ~27%)
-// and then refined against the eight atoms themselves (~55%): every entry dropped here saves the
-// direct-space kernel eight pair slots.
+// every octet the list holds the later atoms that come within the cutoff of the octet's bounding
+// box -- the tile interaction flags, compacted into chunks of 32 j atoms -- each with an 8-bit
+// exclusion mask over the octet's atoms.  An octet's box is much tighter than a 32-atom block's, so
+// ~40% of the pairs a tile visits are in range instead of ~27%.
 //
 // Candidate search is O(N): the atoms were binned into small cells (sort.cu) whose sorted ranges
 // are known, so a CTA
@@ -17,11 +15,10 @@
 //   2. walks the set bits in ascending order; the candidates are split evenly between the four warps, each of
 //      which loads a candidate block's 32 atoms ONCE (four candidates in flight) and tests them against
 //      all four octet boxes (one ballot -> one 32-bit word of interaction flags per octet);
-//   3. every warp then gathers its own octet's non-empty words, refines them (the surviving candidates are
-//      compacted through a small ring so that all 32 lanes test one candidate each against the octet's
-//      eight atoms), prefix-sums the popcounts, takes a contiguous range of chunks from the global list
-//      with one atomicAdd, writes the entries (ascending j: the tile kernel's gathers stay coalesced)
-//      and ORs the exclusion masks in from the octet's own (short) exclusion lists.
+//   3. every warp then gathers its own octet's non-empty words, prefix-sums the popcounts, takes a
+//      contiguous range of chunks from the global list with one atomicAdd, writes the entries (ascending
+//      j: the tile kernel's gathers stay coalesced) and ORs the exclusion masks in from the octet's own
+//      (short) exclusion lists.
 // No order-dependent atomics: chunk CONTENTS are deterministic, only their location in the list varies.
 // A rank of a multi-GPU run builds the lists of its own block range [blockLo, blockHi) only.
 //
@@ -138,8 +135,7 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
     unsigned* hitWord = (unsigned*) ((int*) (tmpWord+4*TEST_BATCH)+4*HIT_CAP)+w*HIT_CAP;
     int* hitBase = (int*) (tmpWord+4*TEST_BATCH)+8*HIT_CAP+w*HIT_CAP;
     __shared__ int sNc;
-    __shared__ int sRing[LIST_WARPS][64];               // refinement: candidates waiting for a full warp of tests
-    __shared__ float4 sOctAtom[LIST_WARPS][8];          // the octet's atoms relative to its centre (w = 0, or huge for a padding slot)
+    __shared__ int sWordLo, sWordHi;            // bitmap words that got a bit: the candidate walk visits only these
     const unsigned full = 0xffffffffu;
     const int lastI = O*8+7, wFirst = I>>5;
     const float4 cI = a.blockCenter[I];
@@ -158,20 +154,30 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
         ov[o] = e.x >= 0.f;                             // false: padding octet
     }
     const float4 ext = a.octetExt[O];
-    const float4 ocMine = a.octetCenter[O];             // (oc[w] would index the register array dynamically)
     const bool mine = ext.x >= 0.f;
-    if (lane < 8) {
-        const float4 p = a.posqLocal[O*8+lane];
-        const bool real = a.sortedAtom[O*8+lane] >= 0;
-        // a padding slot sits far away from everything
-        sOctAtom[w][lane] = real ? make_float4(p.x-ocMine.x, p.y-ocMine.y, p.z-ocMine.z, 0.f) : make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    // Orthorhombic boxes: the periodic image of a candidate atom is taken ONCE, relative to the i block's centre, when that
+    // is the image every octet of the block would pick -- a box at least 2 (cutoff + block extent) + 2 block extents long;
+    // smaller boxes wrap the displacement to every octet on its own.
+    bool wrapOnce = false;
+    if (pbcMode == PBC_SHIFT) {
+        const float4 be = a.blockExt[I];
+        const float reach = a.cutoff+1e-3f;
+        wrapOnce = box.ax > 2.f*(reach+2.f*be.x) && box.by > 2.f*(reach+2.f*be.y) && box.cz > 2.f*(reach+2.f*be.z);
     }
 
     // ---- 1. candidate blocks of the whole i block (all 128 threads) -------------------------------
     for (int k = wFirst+threadIdx.x; k < a.bitmapWords; k += blockDim.x)
         bm[k] = 0u;
+    if (threadIdx.x == 0) {
+        sWordLo = a.bitmapWords;
+        sWordHi = -1;
+    }
     __syncthreads();
     if (!a.useCutoff) {
+        if (threadIdx.x == 0) {
+            sWordLo = wFirst;
+            sWordHi = a.bitmapWords-1;
+        }
         // no cutoff: every later atom interacts
         for (int k = wFirst+threadIdx.x; k < a.bitmapWords; k += blockDim.x) {
             unsigned word = full;
@@ -195,6 +201,7 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
         const float pruneCut2 = (a.cutoff+1e-5f)*(a.cutoff+1e-5f);
         const int nyz = n[1]*n[2], total = n[0]*nyz;
         const int dy = a.cellDim[1], dz = a.cellDim[2], dx = a.cellDim[0];
+        int myLo = a.bitmapWords, myHi = -1;       // bitmap words this thread touched
         for (int base = 0; base < total; base += 2*LIST_WARPS*32) {
             int2 range[2];
 #pragma unroll
@@ -225,10 +232,19 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int s0 = max(range[u].x, I*32), e0 = range[u].y;
-                if (e0 > s0)
+                if (e0 > s0) {
                     for (int b = s0>>5; b <= (e0-1)>>5; b++)
                         atomicOr(&bm[b>>5], 1u<<(b&31));
+                    myLo = min(myLo, s0>>10);
+                    myHi = max(myHi, (e0-1)>>10);
+                }
             }
+        }
+        myLo = __reduce_min_sync(0xffffffffu, myLo);
+        myHi = __reduce_max_sync(0xffffffffu, myHi);
+        if (lane == 0 && myHi >= 0) {
+            atomicMin(&sWordLo, myLo);
+            atomicMax(&sWordHi, myHi);
         }
     }
     __syncthreads();
@@ -242,55 +258,7 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
     const int atomK = mine ? a.sortedAtom[ki] : -1;     // atom k = lane&7 of the octet, on every lane
     const int atomI = lane < 8 ? atomK : -1;
 
-    // Refinement of the batch's flag words: a candidate stays only if it comes within the (padded) cutoff of one of the
-    // octet's atoms.  Valid where the direct-space kernel takes ONE periodic image per j atom (the one nearest the
-    // octet's centre): orthorhombic or no periodicity, octet not `wide`; the other octets keep the box test.
-    const bool refinable = a.useCutoff && pbcMode != PBC_PAIR_TRICLINIC && !wide;
-    auto refine = [&]() {
-        int* ring = sRing[w];
-        int head = 0, fill = 0;
-        auto testBatch = [&](int count) {
-            const int e = lane < count ? ring[(head+lane)&63] : -1;
-            if (e >= 0) {
-                const int k = e>>5, b = e&31, J = hitJ[k];
-                const float4 pj = a.posqLocal[J*32+b];
-                const float4 bcJ = a.blockCenter[J];
-                float dx = pj.x+(bcJ.x-cI.x)-ocMine.x, dy = pj.y+(bcJ.y-cI.y)-ocMine.y, dz = pj.z+(bcJ.z-cI.z)-ocMine.z;
-                if (pbcMode != PBC_NONE) {
-                    dx = wrapOrtho(dx, box.ax, box.invAx);
-                    dy = wrapOrtho(dy, box.by, box.invBy);
-                    dz = wrapOrtho(dz, box.cz, box.invCz);
-                }
-                bool keep = false;
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const float4 pi = sOctAtom[w][t];
-                    const float x = dx-pi.x, y = dy-pi.y, z = dz-pi.z;
-                    keep |= x*x+y*y+z*z < cut2;
-                }
-                if (!keep)
-                    atomicAnd(&hitWord[k], ~(1u<<b));
-            }
-            head = (head+count)&63;
-            fill -= count;
-        };
-        for (int k = 0; k < nh; k++) {
-            const unsigned word = hitWord[k];
-            if ((word>>lane)&1u)
-                ring[(head+fill+__popc(word&((1u<<lane)-1)))&63] = (k<<5)|lane;
-            fill += __popc(word);
-            __syncwarp();
-            if (fill >= 32)
-                testBatch(32);
-        }
-        if (fill > 0)
-            testBatch(fill);
-        __syncwarp();
-    };
-
     auto flush = [&]() {
-        if (refinable)
-            refine();
         // positions of the batch's entries (the octet's own atoms occupy entries 0..7 of its first batch)
         int running = first ? 8 : 0;
         for (int k0 = 0; k0 < nh; k0 += 32) {
@@ -367,7 +335,8 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
         nh = 0;
     };
 
-    for (int w0 = wFirst; w0 < a.bitmapWords; w0 += 32) {
+    const int wordLo = max(wFirst, sWordLo), wordHi = sWordHi;
+    for (int w0 = wordLo; w0 <= wordHi; w0 += 32) {
         // candidates of this window of 32 bitmap words, in ascending order (warp 0 lists them for everyone)
         {
             const unsigned probe = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
@@ -418,13 +387,19 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
                         continue;
                     const int j = J[u]*32+lane;
                     const bool atom = j < a.numAtoms;
-                    const float px = pj[u].x+(bc[u].x-cI.x), py = pj[u].y+(bc[u].y-cI.y), pz = pj[u].z+(bc[u].z-cI.z);
+                    float px = pj[u].x+(bc[u].x-cI.x), py = pj[u].y+(bc[u].y-cI.y), pz = pj[u].z+(bc[u].z-cI.z);
+                    if (wrapOnce) {
+                        px = wrapOrtho(px, box.ax, box.invAx);
+                        py = wrapOrtho(py, box.by, box.invBy);
+                        pz = wrapOrtho(pz, box.cz, box.invCz);
+                    }
                     unsigned keep = 0u;
 #pragma unroll
                     for (int o = 0; o < 4; o++) {
                         bool acc = atom && ov[o] && j > (4*I+o)*8+7;
                         if (a.useCutoff && acc)
-                            acc = imageDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o], pbcMode, box) < cut2;
+                            acc = (wrapOnce ? boxDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o])
+                                            : imageDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o], pbcMode, box)) < cut2;
                         const unsigned word = __ballot_sync(full, acc);
                         if (lane == o)
                             keep = word;
