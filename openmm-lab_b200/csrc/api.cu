@@ -505,7 +505,7 @@ void setupPme(snb_handle& h, PmeGrid& g, const int n[3], double alpha) {
     if (!h.doublePrecision && !h.deterministic && n[0] >= 16 && n[1] >= 16 && n[2] >= 16 && getenv("SNB_NO_PME_BRICKS") == nullptr) {
         g.nzp = (n[2]+4+3)&~3;
         g.pad.alloc((size_t) h.S*(n[0]+4)*(n[1]+4)*g.nzp);
-        g.brick = makeBrickTensorMap(&g.brickMap, g.pad.p, h.S, n[0], n[1], g.nzp);
+        g.brick = makeBrickTensorMap(&g.brickMap, g.pad.p, h.N, h.S, n[0], n[1], g.nzp);
     }
     int dims[3] = {n[0], n[1], n[2]};
     CUFFT_CHECK(cufftPlanMany(&g.fwd, 3, dims, nullptr, 1, (int) G, nullptr, 1, (int) GC, h.doublePrecision ? CUFFT_D2Z : CUFFT_R2C, h.S));
@@ -1009,7 +1009,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             // atoms in sorted order + mixed precision: shared-memory bricks moved by TMA; else the per-atom kernels
             const bool bricks = g.brick && pa.sortedAtom != nullptr;
             static const bool noBrickSpread = getenv("SNB_NO_BRICK_SPREAD") != nullptr, noBrickInterp = getenv("SNB_NO_BRICK_INTERP") != nullptr;
-            if (bricks && !noBrickSpread) launchPmeSpreadBrick(pa, g.brickMap, ps);
+            if (bricks && !noBrickSpread) CUDA_CHECK(launchPmeSpreadBrick(pa, g.brickMap, ps));
             else launchPmeSpread(pa, ps);
             if (term == 0) tm.mark(5);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecD2Z(g.fwd, (double*) g.real.p, (cufftDoubleComplex*) g.cplx.p));
@@ -1019,7 +1019,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             if (term == 0) tm.mark(7);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecZ2D(g.inv, (cufftDoubleComplex*) g.cplx.p, (double*) g.real.p));
             else CUFFT_CHECK(cufftExecC2R(g.inv, (cufftComplex*) g.cplx.p, (float*) g.real.p));
-            if (bricks && !noBrickInterp) launchPmeInterpolateBrick(pa, g.brickMap, ps);
+            if (bricks && !noBrickInterp) CUDA_CHECK(launchPmeInterpolateBrick(pa, g.brickMap, ps));
             else launchPmeInterpolate(pa, ps);
             if (term == 0) tm.mark(8);
         }
@@ -1305,7 +1305,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     if (includeRecip && h.method == SNB_EWALD && h.rank == 0) launches += 2;    // structure factors, forces
     if (includeRecip && pmeFamily && h.rank == 0)      // spread (+ finish or fold), convolution, combine, interpolate
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++)
-            launches += (h.deterministic || ((term == 0 ? h.pme : h.dpme).brick && includeDirect)) ? 5 : 4;
+            launches += h.deterministic ? 5 : 4;
     if (includeForces || h.comm) launches += 1+(h.comm && includeForces ? 1 : 0);
     if (posqDev) launches += 1;
     h.countersOut[2] = launches;

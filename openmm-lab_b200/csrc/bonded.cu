@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(128) k_bonded(BondedArgs a) {
         sE[k] = 0.0;
     __syncthreads();
     const int idx = blockIdx.x*blockDim.x+threadIdx.x;
+    int mySlice = -1;
+    double myC = 0.0, myV = 0.0;
     if (idx < a.numExceptions) {
         const int e = a.firstException+idx;
         const int2 atoms = a.exceptionAtoms[e];
@@ -71,13 +73,37 @@ __global__ void __launch_bounds__(128) k_bonded(BondedArgs a) {
                 addFixed(&a.forceOrig[k*a.paddedAtoms+j], -f);
             }
         }
-        if (eC != 0.0) atomicAdd(&sE[2*slice], eC);
-        if (eV != 0.0) atomicAdd(&sE[2*slice+1], eV);
+        mySlice = slice;
+        myC = eC; myV = eV;
+    }
+    // Energies: summed over the warp slice by slice (a warp's exceptions sit in one or two slices) before they touch shared
+    // memory -- a double-precision atomicAdd there is a compare-and-swap loop, and with every thread of the CTA adding to the
+    // same two words it WAS the kernel (168 us for the two million exceptions of the STMV-size system) -- then one global
+    // atomic per CTA and slice into one of the 32 replicas of the table (summed on the host)
+    {
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x&31;
+        unsigned todo = __ballot_sync(full, mySlice >= 0);
+        while (todo) {
+            const int s = __shfl_sync(full, mySlice, __ffs(todo)-1);
+            const bool mine = mySlice == s;
+            double c = mine ? myC : 0.0, v = mine ? myV : 0.0;
+            for (int o = 16; o > 0; o >>= 1) {
+                c += __shfl_xor_sync(full, c, o);
+                v += __shfl_xor_sync(full, v, o);
+            }
+            if (lane == 0) {
+                if (c != 0.0) atomicAdd(&sE[2*s], c);
+                if (v != 0.0) atomicAdd(&sE[2*s+1], v);
+            }
+            todo &= ~__ballot_sync(full, mine);
+        }
     }
     __syncthreads();
+    double* table = a.energyBuf+(size_t) (blockIdx.x%32)*2*SNB_MAX_SLICES;
     for (int k = threadIdx.x; k < 2*SNB_MAX_SLICES; k += blockDim.x)
         if (sE[k] != 0.0)
-            atomicAdd(&a.energyBuf[k], sE[k]);
+            atomicAdd(&table[k], sE[k]);
 }
 
 void launchBonded(const BondedArgs& a, cudaStream_t stream) {

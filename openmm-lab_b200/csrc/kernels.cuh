@@ -157,9 +157,9 @@ void launchPmeSpread(const PmeArgs& a, cudaStream_t stream);
 void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);
 // brick path (mixed precision, sorted atoms): shared-memory grid bricks moved by TMA
-bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numSubsets, int nx, int ny, int nzp);
-void launchPmeSpreadBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
-void launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
+bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numAtoms, int numSubsets, int nx, int ny, int nzp);
+cudaError_t launchPmeSpreadBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
+cudaError_t launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
 
 struct EwaldArgs {
     int numAtoms, numSubsets, numK, paddedAtoms;

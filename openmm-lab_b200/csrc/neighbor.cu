@@ -12,9 +12,10 @@
 //   1. marks, in a shared bitmap over the j blocks, the blocks owning atoms of the cells that overlap the
 //      i block's box dilated by the cutoff (cells farther than the cutoff pruned; periodic wrap in
 //      fractional coordinates, so triclinic boxes need nothing special) -- all 128 threads;
-//   2. walks the set bits in ascending order; the candidates are split evenly between the four warps, each of
-//      which loads a candidate block's 32 atoms ONCE (four candidates in flight) and tests them against
-//      all four octet boxes (one ballot -> one 32-bit word of interaction flags per octet);
+//   2. compacts the set bits into one ascending candidate list (all 128 threads, one prefix sum); the candidates are
+//      split evenly between the four warps, each of which loads a candidate block's 32 atoms ONCE (four candidates
+//      in flight) and tests them against all four octet boxes (one ballot -> one 32-bit word of interaction flags
+//      per octet);
 //   3. every warp then gathers its own octet's non-empty words, prefix-sums the popcounts, takes a
 //      contiguous range of chunks from the global list with one atomicAdd, writes the entries (ascending
 //      j: the tile kernel's gathers stay coalesced) and ORs the exclusion masks in from the octet's own
@@ -27,10 +28,13 @@
 // (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:104-112).
 #include "kernels.cuh"
 
+#include <type_traits>
+
 #define LIST_WARPS 4
 #define HIT_CAP 128            /* hit blocks buffered per batch; a fuller octet emits several batches */
-#define CAND_CAP 1024          /* candidate blocks of one window of 32 bitmap words (unsigned shorts) */
+#define CAND_CAP 1024          /* candidate blocks listed at a time (more: further rounds over the same bitmap) */
 #define TEST_BATCH 128         /* candidates tested between two CTA barriers: 32 per warp */
+#define LIST_GROUP 2           /* candidate blocks a warp loads together */
 
 __device__ __forceinline__ float wrapOrtho(float d, float L, float invL) { return d-L*rintf(d*invL); }
 
@@ -129,12 +133,12 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
     const int O = 4*I+w;
     // shared: bitmap | candidates of the window | flag words of the batch under test | per-octet hit lists
     unsigned* bm = sMem;
-    unsigned short* cand = (unsigned short*) (bm+a.bitmapWords);
+    int* cand = (int*) (bm+a.bitmapWords);
     unsigned* tmpWord = (unsigned*) (cand+CAND_CAP);                // [4][TEST_BATCH]
     int* hitJ = (int*) (tmpWord+4*TEST_BATCH)+w*HIT_CAP;            // this warp's rows of [4][HIT_CAP]
     unsigned* hitWord = (unsigned*) ((int*) (tmpWord+4*TEST_BATCH)+4*HIT_CAP)+w*HIT_CAP;
     int* hitBase = (int*) (tmpWord+4*TEST_BATCH)+8*HIT_CAP+w*HIT_CAP;
-    __shared__ int sNc;
+    __shared__ int sWarpTotal[LIST_WARPS];
     __shared__ int sWordLo, sWordHi;            // bitmap words that got a bit: the candidate walk visits only these
     const unsigned full = 0xffffffffu;
     const int lastI = O*8+7, wFirst = I>>5;
@@ -153,6 +157,11 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
         oe[o] = make_float3(e.x, e.y, e.z);
         ov[o] = e.x >= 0.f;                             // false: padding octet
     }
+    // a candidate atom j pairs with octet o when it comes after the octet's last atom (every pair once); never with a padding octet
+    int jMin[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++)
+        jMin[o] = ov[o] ? (4*I+o)*8+7 : 0x7fffffff;
     const float4 ext = a.octetExt[O];
     const bool mine = ext.x >= 0.f;
     // Orthorhombic boxes: the periodic image of a candidate atom is taken ONCE, relative to the i block's centre, when that
@@ -335,79 +344,106 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
         nh = 0;
     };
 
+    // ---- the candidate blocks of the whole touched window [wordLo, wordHi] of the bitmap, compacted in ascending order
+    // by all 128 threads at once (every thread owns a contiguous run of words; one CTA-wide prefix sum), then tested in
+    // batches.  (Walking the bitmap in windows of 1 024 blocks cost four barriers per window for a handful of candidates
+    // each -- the candidates of a block are scattered along the space-filling curve.)
     const int wordLo = max(wFirst, sWordLo), wordHi = sWordHi;
-    for (int w0 = wordLo; w0 <= wordHi; w0 += 32) {
-        // candidates of this window of 32 bitmap words, in ascending order (warp 0 lists them for everyone)
-        {
-            const unsigned probe = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
-            if (!__any_sync(full, probe != 0u))
-                continue;                   // same answer in every warp: no barrier is skipped by some only
+    const int nWords = max(0, wordHi-wordLo+1);
+    const int wpt = (nWords+LIST_WARPS*32-1)/(LIST_WARPS*32);
+    const int wBeg = wordLo+(int) threadIdx.x*wpt, wEnd = min(wordHi+1, wBeg+wpt);
+    int myCount = 0;
+    for (int k = wBeg; k < wEnd; k++)
+        myCount += __popc(bm[k]);
+    int myOffset, totalCand;
+    {
+        int incl = myCount;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
         }
-        if (w == 0) {
-            unsigned myWord = w0+lane < a.bitmapWords ? bm[w0+lane] : 0u;
-            const int cnt = __popc(myWord);
-            int incl = cnt;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(full, incl, o);
-                if (lane >= o) incl += t;
+        if (lane == 31)
+            sWarpTotal[w] = incl;
+        __syncthreads();
+        myOffset = incl-myCount;
+        totalCand = 0;
+        for (int k = 0; k < LIST_WARPS; k++) {
+            if (k < w) myOffset += sWarpTotal[k];
+            totalCand += sWarpTotal[k];
+        }
+    }
+    for (int base = 0; base < totalCand; base += CAND_CAP) {
+        // this round's slice [base, base+CAND_CAP) of the ascending candidate sequence
+        if (myOffset < base+CAND_CAP && myOffset+myCount > base) {
+            int pos = myOffset-base;
+            for (int k = wBeg; k < wEnd; k++) {
+                unsigned word = bm[k];
+                while (word) {
+                    if (pos >= 0 && pos < CAND_CAP)
+                        cand[pos] = k*32+__ffs(word)-1;
+                    pos++;
+                    word &= word-1;
+                }
             }
-            int pos = incl-cnt;
-            while (myWord) {
-                cand[pos++] = (unsigned short) (lane*32+__ffs(myWord)-1);
-                myWord &= myWord-1;
-            }
-            if (lane == 31)
-                sNc = incl;
         }
         __syncthreads();
-        const int nc = sNc;
-        const int Jbase = w0*32;
-        __syncthreads();                    // everyone has read sNc before warp 0 may rewrite it
+        const int nc = min(CAND_CAP, totalCand-base);
         for (int c0 = 0; c0 < nc; c0 += TEST_BATCH) {
-            // the batch is split evenly between the four warps (whole groups of four candidates: four loads in flight);
+            // the batch is split evenly between the four warps (whole groups of LIST_GROUP candidates, loaded together);
             // each tests its candidates against all four octet boxes.  An even split matters: the warps meet at a
-            // barrier after the batch, and most windows hold far fewer than 128 candidates
-            const int nbAll = min(TEST_BATCH, nc-c0), perWarp = ((nbAll+15)>>4)<<2;
+            // barrier after the batch.  The image rule of the block (wrapOnce) is a template parameter of the loop: as a run-time
+            // select BOTH rules were evaluated for every test (ncu: 225 instructions per candidate), and the loop body no
+            // longer fit the instruction cache (18 % of the warp time with no instruction to issue).
+            const int nbAll = min(TEST_BATCH, nc-c0);
+            const int perWarp = ((nbAll+LIST_WARPS*LIST_GROUP-1)/(LIST_WARPS*LIST_GROUP))*LIST_GROUP;
             const int kBeg = c0+w*perWarp, kEnd = min(c0+nbAll, kBeg+perWarp);
-            for (int k0 = kBeg; k0 < kEnd; k0 += 4) {
-                int J[4];
-                float4 pj[4], bc[4];
+            auto testCandidates = [&](auto wrapTag) {
+                constexpr bool WRAP_ONCE = decltype(wrapTag)::value;
+#pragma unroll 1
+                for (int k0 = kBeg; k0 < kEnd; k0 += LIST_GROUP) {
+                    int J[LIST_GROUP];
+                    float4 pj[LIST_GROUP], bc[LIST_GROUP];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    J[u] = k0+u < kEnd ? Jbase+cand[k0+u] : -1;
-                    pj[u] = bc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (J[u] >= 0 && a.useCutoff) {
-                        pj[u] = a.posqLocal[J[u]*32+lane];
-                        bc[u] = a.blockCenter[J[u]];
+                    for (int u = 0; u < LIST_GROUP; u++) {
+                        J[u] = k0+u < kEnd ? cand[k0+u] : -1;
+                        pj[u] = bc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (J[u] >= 0 && a.useCutoff) {
+                            pj[u] = a.posqLocal[J[u]*32+lane];
+                            bc[u] = a.blockCenter[J[u]];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < LIST_GROUP; u++) {
+                        if (J[u] < 0)
+                            continue;
+                        const int j = J[u]*32+lane;
+                        const bool atom = j < a.numAtoms;
+                        float px = pj[u].x+(bc[u].x-cI.x), py = pj[u].y+(bc[u].y-cI.y), pz = pj[u].z+(bc[u].z-cI.z);
+                        if (WRAP_ONCE) {
+                            px = wrapOrtho(px, box.ax, box.invAx);
+                            py = wrapOrtho(py, box.by, box.invBy);
+                            pz = wrapOrtho(pz, box.cz, box.invCz);
+                        }
+                        unsigned keep = 0u;
+#pragma unroll
+                        for (int o = 0; o < 4; o++) {
+                            bool acc = atom && j > jMin[o];
+                            if (a.useCutoff && acc)
+                                acc = (WRAP_ONCE ? boxDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o])
+                                                 : imageDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o], pbcMode, box)) < cut2;
+                            const unsigned word = __ballot_sync(full, acc);
+                            if (lane == o)
+                                keep = word;
+                        }
+                        if (lane < 4)
+                            tmpWord[lane*TEST_BATCH+(k0+u-c0)] = keep;
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (J[u] < 0)
-                        continue;
-                    const int j = J[u]*32+lane;
-                    const bool atom = j < a.numAtoms;
-                    float px = pj[u].x+(bc[u].x-cI.x), py = pj[u].y+(bc[u].y-cI.y), pz = pj[u].z+(bc[u].z-cI.z);
-                    if (wrapOnce) {
-                        px = wrapOrtho(px, box.ax, box.invAx);
-                        py = wrapOrtho(py, box.by, box.invBy);
-                        pz = wrapOrtho(pz, box.cz, box.invCz);
-                    }
-                    unsigned keep = 0u;
-#pragma unroll
-                    for (int o = 0; o < 4; o++) {
-                        bool acc = atom && ov[o] && j > (4*I+o)*8+7;
-                        if (a.useCutoff && acc)
-                            acc = (wrapOnce ? boxDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o])
-                                            : imageDist2(px-oc[o].x, py-oc[o].y, pz-oc[o].z, oe[o], pbcMode, box)) < cut2;
-                        const unsigned word = __ballot_sync(full, acc);
-                        if (lane == o)
-                            keep = word;
-                    }
-                    if (lane < 4)
-                        tmpWord[lane*TEST_BATCH+(k0+u-c0)] = keep;
-                }
-            }
+            };
+            if (pbcMode == PBC_SHIFT && wrapOnce)
+                testCandidates(std::true_type());
+            else
+                testCandidates(std::false_type());
             __syncthreads();
             // this warp gathers its own octet's non-empty words, in candidate (= ascending j) order
             const int nb = min(TEST_BATCH, nc-c0);
@@ -421,7 +457,7 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
                     const unsigned nz = __ballot_sync(full, word != 0u);
                     if (word) {
                         const int pos = nh+__popc(nz&((1u<<lane)-1));
-                        hitJ[pos] = Jbase+cand[c0+k0+lane];
+                        hitJ[pos] = cand[c0+k0+lane];
                         hitWord[pos] = word;
                     }
                     nh += __popc(nz);
@@ -439,7 +475,7 @@ cudaError_t launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs) 
     const int numBlocks = a.blockHi-a.blockLo;
     if (numBlocks <= 0)
         return cudaSuccess;
-    const size_t smem = sizeof(unsigned)*((size_t) a.bitmapWords+CAND_CAP/2+4*TEST_BATCH+12*HIT_CAP);
+    const size_t smem = sizeof(unsigned)*((size_t) a.bitmapWords+CAND_CAP+4*TEST_BATCH+12*HIT_CAP);
     // PBC_SHIFT and PBC_PAIR_ORTHO share the orthorhombic rule
     const int rule = a.pbcMode == PBC_NONE ? 0 : a.pbcMode == PBC_PAIR_TRICLINIC ? 2 : 1;
     // the attribute is per device and per context: set whenever it is needed (no process-wide cache), and checked

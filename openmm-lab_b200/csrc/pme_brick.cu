@@ -1,22 +1,21 @@
-// Sliced PME spreading and interpolation through shared-memory grid bricks moved by TMA (mixed precision, atoms in
-// the sorted order of the tile list; every other case keeps the kernels of pme.cu).
+// Sliced PME spreading and interpolation through shared-memory grid bricks (mixed precision, atoms in the sorted order of
+// the tile list; every other case keeps the kernels of pme.cu).
 //
-// The atoms arrive spatially sorted, so 32 consecutive atoms and their 5x5x5 stencils sit in a small brick of the
-// grid.  A one-warp CTA takes 32 atoms and
-//   spreading      accumulates their charges into a 16x16x20 brick in shared memory -- one atom at a time, lane ->
-//                  (iy, iz) of the stencil's yz face, serial over x: plain read-modify-write, no atomics, a fixed order --
-//                  and adds the brick to the grid with ONE bulk tensor reduction (cp.reduce.async.bulk.tensor.3d ... .add,
-//                  SASS UTMAREDG) instead of 125 scattered atomics per atom;
-//   interpolation  fetches the brick of the (lambda-combined) potential with ONE bulk tensor load (cp.async.bulk.tensor.3d,
-//                  SASS UTMALDG, completion on an mbarrier) and then works one THREAD per atom: 125 shared-memory loads
-//                  and ~460 FMAs with the atom's spline weights in registers, no shuffles, no reduction.
-// A set of atoms whose stencils do not fit one brick (a jump of the space-filling curve, a subset boundary: the grids are
-// per subset) is halved until it does; a single atom always fits.
+// The atoms arrive spatially sorted, so consecutive atoms and their 5x5x5 stencils sit in a small brick of the grid.
+//   spreading      a warp accumulates 32 atoms into a private 16x16x20 brick in shared memory (plain read-modify-writes,
+//                  a fixed order, no atomics) and sends the touched part to the grid as float4 reductions
+//                  (red.global.add.v4.f32): see k_pmeSpreadWarp below for what that replaces and why;
+//   interpolation  a CTA of 128 / 256 atoms fetches the 24x24x28 brick of the (lambda-combined) potential with ONE bulk tensor
+//                  load (cp.async.bulk.tensor.4d, SASS UTMALDG, completion on an mbarrier) and then works one THREAD per
+//                  atom: 125 shared-memory loads and ~460 FMAs with the atom's spline weights in registers, no shuffles,
+//                  no reduction.
+// A set of atoms whose stencils do not fit one brick (a jump of the space-filling curve, the periodic boundary, a subset
+// boundary: the grids are per subset) is halved, in sorted order, until it does; a single atom always fits.
 //
-// Bricks never wrap: they address a PADDED copy of the grids, [S][nx+4][ny+4][nzp] with nzp = nz+4 rounded up to a multiple
-// of 4 floats (TMA strides are multiples of 16 bytes).  Spreading accumulates into it and k_pmeFold folds the halo back
-// while writing the dense grid cuFFT reads (no memset of that grid, no atomics); after the inverse transform
-// k_pmeCombinePad writes phi_i = sum_j lambda[slice(i,j)] grid_j straight into the padded layout, halo included.
+// Interpolation bricks never wrap: they address a PADDED copy of the potentials, [S][nx+4][ny+4][nzp] with nzp = nz+4 rounded
+// up to a multiple of 4 floats (TMA strides are multiples of 16 bytes); a brick hanging over the padded extent is clipped by
+// the TMA unit itself (the subset is the tensor's fourth coordinate).  After the inverse transform k_pmeCombinePad writes
+// phi_i = sum_j lambda[slice(i,j)] grid_j straight into the padded layout, halo included.
 //
 // Arithmetic: platforms/reference/src/ReferencePME.cpp:196-256 (index, fraction), :264-317 (B-splines), :320-396 (spreading),
 // :598-702 (interpolation; subset stride nx, see pme.cu).  (GPU behavioural cross-reference:
@@ -26,13 +25,16 @@
 #include <climits>
 
 #define ORDER SNB_PME_ORDER
+#define MAX_WARPS 8                      /* CTAs of 128 or 256 threads */
+
 // Brick shape in grid points (x, y, z).  TMA wants the innermost coordinate of a box 16-byte aligned -- a start at z = 2
 // raises CUDA_ERROR_ILLEGAL_INSTRUCTION, measured with tools/ubench/tma_shape_test.cu -- so a brick starts at z rounded
-// down to a multiple of 4 floats and is 4 points longer along z to keep 16 usable ones whatever the alignment.
-#define BRICK 16                         /* x and y: stencil bases may span BRICK-ORDER+1 = 12 cells */
-#define BRICK_Z 20
-#define BRICK_FLOATS (BRICK*BRICK*BRICK_Z)
-#define BRICK_BYTES (BRICK_FLOATS*4)
+// down to a multiple of 4 floats and is 4 points longer along z than along x and y.
+template <int BX_, int BY_, int BZ_> struct BrickShape {
+    enum { BX = BX_, BY = BY_, BZ = BZ_, FLOATS = BX_*BY_*BZ_, BYTES = FLOATS*4 };
+};
+typedef BrickShape<24, 24, 28> BigBrick;         // 64 512 bytes
+typedef BrickShape<16, 16, 20> SmallBrick;       // 20 480 bytes: grids with a dimension below 20 (24 along z)
 
 namespace {
 
@@ -64,8 +66,8 @@ __device__ __forceinline__ void bspline5f(float w, float* th, float* dth) {
     th[0] = div*(1.f-w)*th[0];
 }
 
-// this lane's atom: grid cell, fraction (fractional coordinates in double: positions may be far from the origin), charge
-__device__ __forceinline__ bool laneAtom(const PmeArgs& a, int k, int& atom, int idx[3], float frac[3], float& q, int& sub) {
+// this thread's atom: grid cell, fraction (fractional coordinates in double: positions may be far from the origin), charge
+__device__ __forceinline__ bool threadAtom(const PmeArgs& a, int k, int& atom, int idx[3], float frac[3], float& q, int& sub) {
     atom = -1; q = 0.f; sub = -1;
     idx[0] = idx[1] = idx[2] = 0;
     frac[0] = frac[1] = frac[2] = 0.f;
@@ -96,9 +98,112 @@ __device__ __forceinline__ bool laneAtom(const PmeArgs& a, int k, int& atom, int
     return true;
 }
 
-// The next set of atoms that shares one brick: same subset, stencils within BRICK points along every axis.  Starts from
-// all pending atoms of the first pending atom's subset and keeps the lower half (in lane = sorted order) until the set fits.
-__device__ __forceinline__ unsigned nextBrickSet(unsigned pending, int lane, int sub, const int idx[3], int origin[3], int& subset) {
+// Scratch of the CTA-wide votes below.
+struct SetScratch {
+    int lo[MAX_WARPS][3], hi[MAX_WARPS][3];
+    int count[MAX_WARPS], first[MAX_WARPS];
+    int subsetOfFirst;
+};
+
+// The next set of this CTA's atoms that shares one brick: same subset, stencils within the brick along every axis.  Starts
+// from all pending atoms of the first pending atom's subset and keeps the lower half (in thread = sorted order) until the
+// set fits.  Every thread of the CTA calls it (it synchronises the CTA); returns whether THIS thread's atom is in the set,
+// the brick's origin and its subset.
+template <typename B>
+__device__ __forceinline__ bool nextBrickSet(SetScratch& s, bool pending, int sub, const int idx[3], int origin[3], int& subset) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x&31, warp = threadIdx.x>>5, nwarps = blockDim.x>>5;
+    // subset of the first pending atom
+    {
+        const unsigned m = __ballot_sync(full, pending);
+        if (lane == 0)
+            s.first[warp] = m ? warp*32+__ffs(m)-1 : INT_MAX;
+        __syncthreads();
+        int first = INT_MAX;
+        for (int w = 0; w < nwarps; w++)
+            first = min(first, s.first[w]);
+        if ((int) threadIdx.x == first)
+            s.subsetOfFirst = sub;
+        __syncthreads();
+        subset = s.subsetOfFirst;
+    }
+    const bool cand = pending && sub == subset;
+    // rank of this thread among the candidates
+    int rank, count;
+    {
+        const unsigned m = __ballot_sync(full, cand);
+        if (lane == 0)
+            s.count[warp] = __popc(m);
+        __syncthreads();
+        rank = __popc(m&((1u<<lane)-1u));
+        count = 0;
+        for (int w = 0; w < nwarps; w++) {
+            if (w < warp)
+                rank += s.count[w];
+            count += s.count[w];
+        }
+    }
+    int limit = count;
+    for (;;) {
+        const bool in = cand && rank < limit;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int lo = __reduce_min_sync(full, in ? idx[d] : INT_MAX), hi = __reduce_max_sync(full, in ? idx[d] : INT_MIN);
+            if (lane == 0) {
+                s.lo[warp][d] = lo;
+                s.hi[warp][d] = hi;
+            }
+        }
+        __syncthreads();            // (also: the count / first reads above are over before the next call rewrites them)
+        bool fits = true;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            int lo = INT_MAX, hi = INT_MIN;
+            for (int w = 0; w < nwarps; w++) {
+                lo = min(lo, s.lo[w][d]);
+                hi = max(hi, s.hi[w][d]);
+            }
+            origin[d] = d == 2 ? lo&~3 : lo;        // z: 16-byte aligned box start
+            fits = fits && hi-origin[d]+ORDER <= (d == 0 ? (int) B::BX : d == 1 ? (int) B::BY : (int) B::BZ);
+        }
+        __syncthreads();            // everyone has read lo / hi
+        if (fits || limit <= 1)
+            return in;
+        limit = (limit+1)/2;
+    }
+}
+
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace
+
+// ---- spreading ----------------------------------------------------------------------------------------------------
+// One warp (a one-warp CTA) takes 32 consecutive sorted atoms and a PRIVATE 16x16x20 brick: no other warp touches it, so the
+// charges are added with plain shared-memory read-modify-writes -- one atom at a time, lane -> (iy, iz) of the stencil's yz
+// face (25 distinct points), serial over x, a __syncwarp between atoms.  The brick then goes to the grid as vector reductions
+// of the float4 groups that are not zero (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4), wrapped row by row, straight into the
+// dense grid cuFFT reads: ~30 floating-point adds reach the L2 per atom instead of 125.
+//
+// What the measurements ruled out (profiles/README.md, round 2):
+//   * shared-memory float atomics: there is no native instruction (atomicAdd = load / add / ATOMS.CAST.SPIN loop) and shared
+//     atomics of any kind retire ~2 lanes per clock and SM -- a 256-atom CTA on one brick took 388 us (one warp per atom) to
+//     655 us (one thread per atom) at STMV size; 32-bit fixed point (native ATOMS.ADD) was no faster and, with a scale that
+//     provably cannot overflow, too coarse where water's charges cancel;
+//   * adding whole bricks with one bulk tensor reduction (UTMAREDG): the L2 performs ~600 G float additions per second
+//     whoever asks, and a brick is mostly zeros -- 16 128 additions for ~170 atoms (5 120 for 32) against the ~5 500 (1 000)
+//     points they touch.
+#define WB_X 16
+#define WB_Y 16
+#define WB_Z 20
+#define WB_FLOATS (WB_X*WB_Y*WB_Z)
+
+namespace {
+
+// The next set of this warp's atoms that shares one brick: same subset, stencil bases within the brick along every axis.
+// Starts from all pending atoms of the first pending atom's subset and keeps the lower half (in lane = sorted order) until
+// the set fits; a single atom always fits.  ALIGN: the brick starts at a multiple of ALIGN points along z.
+template <int ALIGN>
+__device__ __forceinline__ unsigned nextWarpSet(unsigned pending, int lane, int sub, const int idx[3], int origin[3], int span[3], int& subset) {
     const unsigned full = 0xffffffffu;
     subset = __shfl_sync(full, sub, __ffs(pending)-1);
     unsigned cand = __ballot_sync(full, ((pending>>lane)&1u) && sub == subset);
@@ -108,8 +213,9 @@ __device__ __forceinline__ unsigned nextBrickSet(unsigned pending, int lane, int
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             const int lo = __reduce_min_sync(full, in ? idx[d] : INT_MAX), hi = __reduce_max_sync(full, in ? idx[d] : INT_MIN);
-            origin[d] = d == 2 ? lo&~3 : lo;        // z: 16-byte aligned box start
-            fits = fits && hi-origin[d]+ORDER <= (d == 2 ? BRICK_Z : BRICK);
+            origin[d] = d == 2 ? lo-lo%ALIGN : lo;
+            span[d] = hi-origin[d]+ORDER;
+            fits = fits && span[d] <= (d == 0 ? WB_X : d == 1 ? WB_Y : WB_Z);
         }
         const int count = __popc(cand);
         if (fits || count <= 1)
@@ -119,58 +225,52 @@ __device__ __forceinline__ unsigned nextBrickSet(unsigned pending, int lane, int
     }
 }
 
-__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 }  // namespace
 
-// ---- spreading ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_pmeSpreadBrick(PmeArgs a, const __grid_constant__ CUtensorMap tmap) {
-    __shared__ __align__(128) float sBrick[BRICK_FLOATS];
-    __shared__ float sTh[3][ORDER][32];         // spline weights of the 32 atoms (theta_x carries the charge)
-    __shared__ int sRel[3][32];
+// VEC = 4: nz is a multiple of 4, bricks start at multiples of 4 along z, float4 reductions.  VEC = 1: any nz, scalar reductions.
+template <int VEC>
+__global__ void __launch_bounds__(32) k_pmeSpreadWarp(PmeArgs a) {
+    __shared__ __align__(16) float sBrick[WB_FLOATS];
+    __shared__ __align__(16) float sW[32][16];      // q wx[0..4], wy[0..4], wz[0..4], -
+    __shared__ int sCell[32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
     int atom, idx[3], sub;
     float frac[3], q;
-    const bool valid = laneAtom(a, blockIdx.x*32+lane, atom, idx, frac, q, sub);
+    const bool valid = threadAtom(a, blockIdx.x*32+lane, atom, idx, frac, q, sub);
     {
-        float th[ORDER], dth[ORDER];
+        float w[16], dth[ORDER];
+        bspline5f(frac[0], w, dth);
+        bspline5f(frac[1], w+5, dth);
+        bspline5f(frac[2], w+10, dth);
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            bspline5f(frac[d], th, dth);
+        for (int i = 0; i < ORDER; i++)
+            w[i] *= q;
+        w[15] = 0.f;
 #pragma unroll
-            for (int i = 0; i < ORDER; i++)
-                sTh[d][i][lane] = d == 0 ? q*th[i] : th[i];
-        }
+        for (int i = 0; i < 4; i++)
+            ((float4*) sW[lane])[i] = make_float4(w[4*i], w[4*i+1], w[4*i+2], w[4*i+3]);
     }
+#pragma unroll
+    for (int k = 0; k < WB_FLOATS/(32*4); k++)
+        ((float4*) sBrick)[k*32+lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int iy = lane < ORDER*ORDER ? lane/ORDER : 0, iz = lane < ORDER*ORDER ? lane-iy*ORDER : 0;
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    float* grid = (float*) a.grid;
     unsigned pending = __ballot_sync(full, valid);
-    bool issued = false;
     while (pending) {
-        int origin[3], subset;
-        const unsigned set = nextBrickSet(pending, lane, sub, idx, origin, subset);
+        int origin[3], span[3], subset;
+        const unsigned set = nextWarpSet<VEC>(pending, lane, sub, idx, origin, span, subset);
         pending &= ~set;
-        // the previous brick must have been READ by the reduction before it is cleared
-        if (issued) {
-            if (lane == 0)
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-        }
-#pragma unroll
-        for (int k = 0; k < BRICK_FLOATS/(32*4); k++)
-            ((float4*) sBrick)[k*32+lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int d = 0; d < 3; d++)
-            sRel[d][lane] = idx[d]-origin[d];
+        sCell[lane] = ((idx[0]-origin[0])*WB_Y+idx[1]-origin[1])*WB_Z+idx[2]-origin[2];
         __syncwarp();
-        // one atom at a time (the next atom may touch the same cells from other lanes); the NEXT atom's weights and cell
-        // are fetched from shared memory before the current one's read-modify-write, so that the two latencies overlap
+        // ---- one atom at a time (the next atom may touch the same points from other lanes); the NEXT atom's weights and cell
+        // are fetched before the current one's read-modify-writes, so that the two latencies overlap
         auto fetch = [&](int t, int& cell, float& wyz, float (&wx)[ORDER]) {
-            cell = (sRel[0][t]*BRICK+sRel[1][t]+iy)*BRICK_Z+sRel[2][t]+iz;
-            wyz = sTh[1][iy][t]*sTh[2][iz][t];
-#pragma unroll
-            for (int ix = 0; ix < ORDER; ix++)
-                wx[ix] = sTh[0][ix][t];
+            cell = sCell[t]+iy*WB_Z+iz;
+            wyz = sW[t][5+iy]*sW[t][10+iz];
+            const float4 w03 = *(const float4*) sW[t];
+            wx[0] = w03.x; wx[1] = w03.y; wx[2] = w03.z; wx[3] = w03.w; wx[4] = sW[t][4];
         };
         unsigned m = set;
         int cell;
@@ -186,7 +286,7 @@ __global__ void __launch_bounds__(32) k_pmeSpreadBrick(PmeArgs a, const __grid_c
             if (lane < ORDER*ORDER) {
 #pragma unroll
                 for (int ix = 0; ix < ORDER; ix++)
-                    sBrick[cell+ix*BRICK*BRICK_Z] += wyz*wx[ix];
+                    sBrick[cell+ix*WB_Y*WB_Z] += wyz*wx[ix];
             }
             __syncwarp();
             if (!more)
@@ -197,54 +297,47 @@ __global__ void __launch_bounds__(32) k_pmeSpreadBrick(PmeArgs a, const __grid_c
             for (int ix = 0; ix < ORDER; ix++)
                 wx[ix] = wxN[ix];
         }
-        // shared-memory writes of the generic proxy -> visible to the bulk-copy engine; then brick += into the padded grid
-        fenceProxyAsync();
+        // ---- flush the touched box [0, span) of the brick into the grid (periodic wrap per row), and clear it
+        const int gz = (span[2]+VEC-1)/VEC;                 // groups of VEC points per row
+        const int perPlane = span[1]*gz, total = span[0]*perPlane;
+        const unsigned invPlane = (1u<<20)/(unsigned) perPlane+1u, invGz = (1u<<20)/(unsigned) gz+1u;  // k*inv >> 20 = k/d exactly for k < 2^20/d
+        float* base = grid+(size_t) subset*nx*ny*nz;
+        for (int k = lane; k < total; k += 32) {
+            const int x = (int) (((unsigned) k*invPlane)>>20), r = k-x*perPlane;
+            const int y = (int) (((unsigned) r*invGz)>>20), g = r-y*gz;
+            float* p = sBrick+(x*WB_Y+y)*WB_Z+g*VEC;
+            int X = origin[0]+x, Y = origin[1]+y, Z = origin[2]+g*VEC;
+            X -= X >= nx ? nx : 0;
+            Y -= Y >= ny ? ny : 0;
+            Z -= Z >= nz ? nz : 0;
+            float* dst = base+((size_t) X*ny+Y)*nz+Z;
+            if (VEC == 4) {
+                const float4 v = *(const float4*) p;
+                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                    *(float4*) p = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            else {
+                const float v = *p;
+                if (v != 0.f) {
+                    atomicAdd(dst, v);
+                    *p = 0.f;
+                }
+            }
+        }
         __syncwarp();
-        if (lane == 0) {
-            asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
-                         :: "l"((unsigned long long) &tmap), "r"(smemAddr(sBrick)), "r"(origin[2]), "r"(origin[1]), "r"(subset*(a.nx+4)+origin[0]) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        issued = true;
     }
-    // the CTA may leave once the engine has READ the brick; the writes complete on their own before the grid does
-    if (issued && lane == 0)
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// ---- halo fold: dense grid (cuFFT input) from the padded accumulation grid --------------------------------------------
-// One warp per grid row (s, x, y): lanes run along z, so the index arithmetic is per row and every access is coalesced.
 #define ROWS_PER_CTA 8
-__global__ void __launch_bounds__(32*ROWS_PER_CTA) k_pmeFold(PmeArgs a) {
-    const int nx = a.nx, ny = a.ny, nz = a.nz, py = ny+4, pz = a.nzp;
-    const int row = blockIdx.x*ROWS_PER_CTA+threadIdx.y;        // (s*nx+x)*ny+y
-    if (row >= a.numSubsets*nx*ny)
-        return;
-    const int y = row%ny, sx = row/ny, x = sx%nx, s = sx/nx;
-    const float* base = a.gridPad+(size_t) s*(nx+4)*py*pz;
-    float* out = (float*) a.grid+(size_t) row*nz;
-    // the row itself and its images in the halo (the halo is 4 points wide and every dimension has at least 16)
-    const float* src[4];
-    int ns = 0;
-    for (int ax = 0; ax <= (x < 4 ? 1 : 0); ax++)
-        for (int ay = 0; ay <= (y < 4 ? 1 : 0); ay++)
-            src[ns++] = base+((size_t) (x+ax*nx)*py+(y+ay*ny))*pz;
-    for (int z = threadIdx.x; z < nz; z += 32) {
-        float sum = 0.f;
-        for (int k = 0; k < ns; k++) {
-            sum += src[k][z];
-            if (z < 4)
-                sum += src[k][z+nz];
-        }
-        out[z] = sum;
-    }
-}
-
 // ---- potentials seen by each subset, written into the padded layout (halo = periodic images) -------------------------
-// One warp per padded row (x, y), all subsets: phi_k = sum_j lambda[slice(k,j)] grid_j.
+// One warp per padded row (x, y), all subsets: phi_k = sum_j lambda[slice(k,j)] grid_j.  VEC = 4 (nz a multiple of 4, hence
+// nzp = nz+4): float4 loads and stores, the halo group [nz, nz+4) is the row's first group; VEC = 1: any nz.
+template <int NS, int VEC>
 __global__ void __launch_bounds__(32*ROWS_PER_CTA) k_pmeCombinePad(PmeArgs a) {
     __shared__ float sLambda[SNB_MAX_SUBSETS*SNB_MAX_SUBSETS];
-    const int S = a.numSubsets, tid = threadIdx.y*32+threadIdx.x;
+    const int S = NS > 0 ? NS : a.numSubsets, tid = threadIdx.y*32+threadIdx.x;
     if (tid < S*S) {
         const int si = tid/S, sj = tid-si*S;
         sLambda[tid] = (float) (a.term == 0 ? a.sp->lambdaC : a.sp->lambdaV)[sliceOf(si, sj)];
@@ -258,8 +351,32 @@ __global__ void __launch_bounds__(32*ROWS_PER_CTA) k_pmeCombinePad(PmeArgs a) {
     const size_t P = (size_t) px*py*pz, G = (size_t) nx*ny*nz;
     const float* src = (const float*) a.grid+((size_t) (x >= nx ? x-nx : x)*ny+(y >= ny ? y-ny : y))*nz;
     float* dst = a.gridPad+(size_t) row*pz;
+    constexpr int MAXS = NS > 0 ? NS : SNB_MAX_SUBSETS;
+    if (VEC == 4) {
+        for (int z = 4*threadIdx.x; z < pz; z += 128) {
+            const int zs = z >= nz ? z-nz : z;
+            float4 v[MAXS];
+#pragma unroll
+            for (int j = 0; j < MAXS; j++)
+                if (j < S)
+                    v[j] = *(const float4*) (src+j*G+zs);
+#pragma unroll
+            for (int k = 0; k < MAXS; k++)
+                if (k < S) {
+                    float4 phi = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < MAXS; j++)
+                        if (j < S) {
+                            const float l = sLambda[k*S+j];
+                            phi.x += l*v[j].x; phi.y += l*v[j].y; phi.z += l*v[j].z; phi.w += l*v[j].w;
+                        }
+                    *(float4*) (dst+k*P+z) = phi;
+                }
+        }
+    }
+    else
     for (int z = threadIdx.x; z < pz; z += 32) {
-        float v[SNB_MAX_SUBSETS];
+        float v[MAXS];
         const bool real = z < nz+4;             // the tail of a row is alignment padding
         const int zs = z >= nz ? z-nz : z;
         for (int j = 0; j < S; j++)
@@ -274,36 +391,35 @@ __global__ void __launch_bounds__(32*ROWS_PER_CTA) k_pmeCombinePad(PmeArgs a) {
 }
 
 // ---- interpolation ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_pmeInterpBrick(PmeArgs a, const __grid_constant__ CUtensorMap tmap) {
-    __shared__ __align__(128) float sBrick[BRICK_FLOATS];
+template <typename B>
+__global__ void __launch_bounds__(32*MAX_WARPS) k_pmeInterpBrick(PmeArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char sDyn[];
+    const float* sBrick = (const float*) sDyn;
     __shared__ __align__(8) unsigned long long sBar;
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
+    __shared__ SetScratch sSet;
     const unsigned bar = smemAddr(&sBar);
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
     int atom, idx[3], sub;
     float frac[3], q;
-    const bool valid = laneAtom(a, blockIdx.x*32+lane, atom, idx, frac, q, sub);
+    const bool valid = threadAtom(a, blockIdx.x*blockDim.x+threadIdx.x, atom, idx, frac, q, sub);
     float th[3][ORDER], dth[3][ORDER];
 #pragma unroll
     for (int d = 0; d < 3; d++)
         bspline5f(frac[d], th[d], dth[d]);
-    unsigned pending = __ballot_sync(full, valid);
+    bool pending = valid;
     unsigned phase = 0;
-    while (pending) {
+    while (__syncthreads_or(pending)) {         // (the barrier also covers: mbarrier initialised; everyone done with the previous brick)
         int origin[3], subset;
-        const unsigned set = nextBrickSet(pending, lane, sub, idx, origin, subset);
-        pending &= ~set;
-        // every lane is done with the previous brick (__ballot_sync inside nextBrickSet ordered the warp)
-        fenceProxyAsync();
-        if (lane == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "n"(BRICK_BYTES) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                         :: "r"(smemAddr(sBrick)), "l"((unsigned long long) &tmap), "r"(bar), "r"(origin[2]), "r"(origin[1]), "r"(subset*(a.nx+4)+origin[0]) : "memory");
+        const bool in = nextBrickSet<B>(sSet, pending, sub, idx, origin, subset);
+        pending = pending && !in;
+        if (threadIdx.x == 0) {
+            fenceProxyAsync();
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "n"((int) B::BYTES) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         :: "r"(smemAddr(sBrick)), "l"((unsigned long long) &tmap), "r"(bar), "r"(origin[2]), "r"(origin[1]), "r"(origin[0]), "r"(subset) : "memory");
         }
         // wait for the bytes (bounded spin: a descriptor error must not hang the GPU)
         {
@@ -315,15 +431,15 @@ __global__ void __launch_bounds__(32) k_pmeInterpBrick(PmeArgs a, const __grid_c
                 __trap();
         }
         phase ^= 1u;
-        if ((set>>lane)&1u) {
-            const float* cell = sBrick+((idx[0]-origin[0])*BRICK+idx[1]-origin[1])*BRICK_Z+idx[2]-origin[2];
+        if (in) {
+            const float* cell = sBrick+((idx[0]-origin[0])*B::BY+idx[1]-origin[1])*B::BZ+idx[2]-origin[2];
             float fx = 0.f, fy = 0.f, fz = 0.f;
 #pragma unroll
             for (int ix = 0; ix < ORDER; ix++) {
                 float tyz = 0.f, dyz = 0.f, tzd = 0.f;      // sum_y theta_y s, sum_y dtheta_y s, sum_y theta_y d
 #pragma unroll
                 for (int iy = 0; iy < ORDER; iy++) {
-                    const float* row = cell+(ix*BRICK+iy)*BRICK_Z;
+                    const float* row = cell+(ix*B::BY+iy)*B::BZ;
                     float s = 0.f, d = 0.f;
 #pragma unroll
                     for (int iz = 0; iz < ORDER; iz++) {
@@ -350,12 +466,18 @@ __global__ void __launch_bounds__(32) k_pmeInterpBrick(PmeArgs a, const __grid_c
             addFixed(&a.forceOrig[a.paddedAtoms+atom], toFixedD(Fy));
             addFixed(&a.forceOrig[2*a.paddedAtoms+atom], toFixedD(Fz));
         }
-        __syncwarp();
     }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numSubsets, int nx, int ny, int nzp) {
+// Which brick an interpolation takes.  The big one (128 / 256 atoms per CTA) needs a padded grid at least one brick long along
+// every axis, and enough atoms to fill the GPU with such CTAs: below that the kernel is one wave of CTAs whose length is a
+// chain of latencies (gather, vote, 64 KB bulk load, 125 points), and 64-atom CTAs on 20 KB bricks finish it sooner.
+static bool bigBrick(int numAtoms, int nx, int ny, int nzp) {
+    return numAtoms >= 148*2*256 && nx+4 >= BigBrick::BX && ny+4 >= BigBrick::BY && nzp >= BigBrick::BZ;
+}
+
+bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numAtoms, int numSubsets, int nx, int ny, int nzp) {
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeTiled encode = nullptr;
@@ -368,24 +490,55 @@ bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numSubsets, int nx
         }
         encode = (EncodeTiled) fn;
     }
-    // innermost first: z (row), y, then x with the subsets stacked along it
-    const cuuint64_t dims[3] = {(cuuint64_t) nzp, (cuuint64_t) (ny+4), (cuuint64_t) numSubsets*(nx+4)};
-    const cuuint64_t strides[2] = {(cuuint64_t) nzp*4, (cuuint64_t) nzp*4*(ny+4)};
-    const cuuint32_t box[3] = {BRICK_Z, BRICK, BRICK}, elem[3] = {1, 1, 1};
-    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, gridPad, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (nx+4 < SmallBrick::BX || ny+4 < SmallBrick::BY || nzp < SmallBrick::BZ)
+        return false;
+    const bool big = bigBrick(numAtoms, nx, ny, nzp);
+    // innermost first: z (row), y, x, subset
+    const cuuint64_t dims[4] = {(cuuint64_t) nzp, (cuuint64_t) (ny+4), (cuuint64_t) (nx+4), (cuuint64_t) numSubsets};
+    const cuuint64_t strides[3] = {(cuuint64_t) nzp*4, (cuuint64_t) nzp*4*(ny+4), (cuuint64_t) nzp*4*(ny+4)*(nx+4)};
+    const cuuint32_t boxBig[4] = {BigBrick::BZ, BigBrick::BY, BigBrick::BX, 1}, boxSmall[4] = {SmallBrick::BZ, SmallBrick::BY, SmallBrick::BX, 1};
+    const cuuint32_t elem[4] = {1, 1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gridPad, dims, strides, big ? boxBig : boxSmall, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-void launchPmeSpreadBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream) {
-    const size_t padFloats = (size_t) a.numSubsets*(a.nx+4)*(a.ny+4)*a.nzp;
-    cudaMemsetAsync(a.gridPad, 0, sizeof(float)*padFloats, stream);
-    k_pmeSpreadBrick<<<(a.numAtoms+31)/32, 32, 0, stream>>>(a, map);
-    const int rows = a.numSubsets*a.nx*a.ny;
-    k_pmeFold<<<(rows+ROWS_PER_CTA-1)/ROWS_PER_CTA, dim3(32, ROWS_PER_CTA), 0, stream>>>(a);
+// atoms per CTA: 256 with the big brick, 64 with the small one (its stencil bases span 12 cells)
+static int brickThreads(bool big) { return big ? 256 : 64; }
+
+template <typename K> static cudaError_t allowSharedMemory(K kernel, size_t bytes) {
+    return bytes > 48*1024 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) : cudaSuccess;
 }
 
-void launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream) {
+cudaError_t launchPmeSpreadBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream) {
+    (void) map;
+    const cudaError_t err = cudaMemsetAsync(a.grid, 0, sizeof(float)*(size_t) a.numSubsets*a.nx*a.ny*a.nz, stream);
+    if (err != cudaSuccess)
+        return err;
+    const int blocks = (a.numAtoms+31)/32;
+    if (a.nz%4 == 0)
+        k_pmeSpreadWarp<4><<<blocks, 32, 0, stream>>>(a);
+    else
+        k_pmeSpreadWarp<1><<<blocks, 32, 0, stream>>>(a);
+    return cudaSuccess;
+}
+
+cudaError_t launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream) {
     const int rows = (a.nx+4)*(a.ny+4);
-    k_pmeCombinePad<<<(rows+ROWS_PER_CTA-1)/ROWS_PER_CTA, dim3(32, ROWS_PER_CTA), 0, stream>>>(a);
-    k_pmeInterpBrick<<<(a.numAtoms+31)/32, 32, 0, stream>>>(a, map);
+    const dim3 cgrid((rows+ROWS_PER_CTA-1)/ROWS_PER_CTA), cblock(32, ROWS_PER_CTA);
+    const bool vec = a.nz%4 == 0;       // (then every row of the dense grid starts 16-byte aligned, and nzp = nz+4)
+    if (vec && a.numSubsets == 1) k_pmeCombinePad<1, 4><<<cgrid, cblock, 0, stream>>>(a);
+    else if (vec && a.numSubsets == 2) k_pmeCombinePad<2, 4><<<cgrid, cblock, 0, stream>>>(a);
+    else if (vec && a.numSubsets <= 4) k_pmeCombinePad<4, 4><<<cgrid, cblock, 0, stream>>>(a);
+    else k_pmeCombinePad<0, 1><<<cgrid, cblock, 0, stream>>>(a);
+    const bool big = bigBrick(a.numAtoms, a.nx, a.ny, a.nzp);
+    const int threads = brickThreads(big), blocks = (a.numAtoms+threads-1)/threads;
+    if (big) {
+        const cudaError_t err = allowSharedMemory(k_pmeInterpBrick<BigBrick>, BigBrick::BYTES);
+        if (err != cudaSuccess)
+            return err;
+        k_pmeInterpBrick<BigBrick><<<blocks, threads, BigBrick::BYTES, stream>>>(a, map);
+    }
+    else
+        k_pmeInterpBrick<SmallBrick><<<blocks, threads, SmallBrick::BYTES, stream>>>(a, map);
+    return cudaSuccess;
 }
