@@ -1053,6 +1053,12 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         partitionRange(h.NB, h.world, h.rank, rank0Share(h), &lo, &hi);
         la.blockLo = (int) lo; la.blockHi = (int) hi;
         la.bitmapWords = (h.NB+31)/32;
+        // Atom-level refinement of the list (41 % -> 55 % of the pair slots in range): the direct-space kernel gets 16-20 %
+        // shorter and the list build 40-50 % longer.  Measured on B200: a wash for the whole evaluation at DHFR size (162.7 vs
+        // 163.6 us), a loss at STMV size (3.05 vs 2.85 ms), so it is on below SNB_PACKED_MIN_ATOMS atoms only.
+        // SNB_LIST_REFINE=0/1 overrides (A/B measurements).
+        static const char* refineEnv = getenv("SNB_LIST_REFINE");
+        la.refine = refineEnv ? atoi(refineEnv) != 0 : h.N < SNB_PACKED_MIN_ATOMS;
         CUDA_CHECK(launchBuildList(la, st, h.numSMs));
         tm.mark(2);
 

@@ -40,12 +40,55 @@ __device__ __forceinline__ void stSharedU32(unsigned ad, unsigned v) { asm volat
 enum { PL_XY = 0, PL_ZQ = 256, PL_SE = 512, PL_SM = 768, PL_BYTES = 1024 };
 
 
+// The pairs of one chunk that fell inside the band around the cutoff: the pair loop only notes that there is one; here the
+// lane finds them again in the pair planes (same r^2, bit for bit: pairDelta), decides each exactly, evaluates it and adds it
+// with atomics, so that the pair loop itself carries neither a call nor a per-step flag.  (bandRescan of direct_impl.cuh, reading
+// the packed kernel's own layout: slot = pair 2P+h -> word h of the pair's (x0,x1,y0,y1) (z0,z1,q0,q1) (s0,s1,e0,e1) (sub0,sub1,m0,m1).)
+template <bool ENERGY, bool DUMP>
+static __device__ __noinline__ void bandRescanPlanes(DirectOut o, DirectConsts<float> c, int lane, int ki, int origI, float cutLo, float cutHi,
+                                                     float4 pi, float4 si4, int perPair, const unsigned char* planes, const int2* entries) {
+    const int copy = lane>>3, k = lane&7;
+    const WrapBox<float> wb = makeWrapBox<float>(o.sp->exact.boxd);
+    for (int s = 0; s < 8; s++) {
+        const int slot = (copy<<3)|(k^s);
+        const float* P = (const float*) (planes+(slot>>1)*16)+(slot&1);
+        const float4 q = make_float4(P[PL_XY/4], P[PL_XY/4+2], P[PL_ZQ/4], P[PL_ZQ/4+2]);
+        const unsigned mask = __float_as_uint(P[PL_SM/4+2]);
+        float dx, dy, dz, r2;
+        if (perPair) r2 = pairDelta<1>(pi, q, wb, dx, dy, dz);
+        else r2 = pairDelta<0>(pi, q, wb, dx, dy, dz);
+        if ((mask>>k)&1u || r2 < cutLo || !(r2 < cutHi))
+            continue;
+        const float sigJ = P[PL_SE/4], epsJ = P[PL_SE/4+2], subJ = P[PL_SM/4];
+        const int j = entries[slot].x;
+        const int origJ = o.sortedAtom[j];
+        if (!exactInRange(o.posd, origI, origJ, &o.sp->exact))
+            continue;
+        float fc, fv, ec, ev, invR2;
+        pairMath<float, KIND_EWALD, false>(c, r2, pi.w*q.w, si4.x, si4.y, si4.w, sigJ, epsJ, 0.f, fc, fv, ec, ev, invR2);
+        const int slice = sliceOf((int) si4.z, (int) subJ);
+        const float f = ((float) o.sp->lambdaV[slice]*fv+(float) o.sp->lambdaC[slice]*fc)*invR2;
+        const long long fx = toFixed(f*dx), fy = toFixed(f*dy), fz = toFixed(f*dz);
+        addFixed(&o.forceSorted[ki], fx); addFixed(&o.forceSorted[o.paddedAtoms+ki], fy); addFixed(&o.forceSorted[2*o.paddedAtoms+ki], fz);
+        addFixed(&o.forceSorted[j], -fx); addFixed(&o.forceSorted[o.paddedAtoms+j], -fy); addFixed(&o.forceSorted[2*o.paddedAtoms+j], -fz);
+        if (ENERGY) {
+            atomicAdd(&o.energyTable[2*slice], (double) ec);
+            atomicAdd(&o.energyTable[2*slice+1], (double) ev);
+        }
+        if (DUMP) {
+            unsigned long long idx = atomicAdd(o.pairDumpCount, 1ull);
+            if ((long long) idx < o.pairDumpCapacity)
+                o.pairDump[idx] = make_int2(min(origI, origJ), max(origI, origJ));
+        }
+    }
+}
+
 template <int NSUB, bool ENERGY, bool DUMP>
 __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectArgs a) {
     static_assert(NSUB == 1 || NSUB == 2, "packed pair loop: one or two subsets");
     typedef Stage<float> St;
     __shared__ __align__(256) unsigned char sStage[2][St::BYTES];
-    __shared__ __align__(256) unsigned char sPairs[PL_BYTES];
+    __shared__ __align__(256) unsigned char sPairs[2][PL_BYTES];       // pair planes of the chunk in the loop and of the next one
     __shared__ __align__(16) int2 sEnt[4][32];          // list entries of chunks ch .. ch+2 (ring of four)
     __shared__ int sOct[4];                             // and their octets
     __shared__ double sAccC[NSUB*NSUB][32], sAccV[NSUB*NSUB][32];
@@ -64,7 +107,7 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
     const float bandHi = narrowOk ? c.cutoffHi : c.cutoffHiWide, bandLo = narrowOk ? c.cutoffLo : c.cutoffLoWide;
     const unsigned kBit = opaque(1u<<k);
     const unsigned stageBase = opaque((unsigned) __cvta_generic_to_shared(&sStage[0][0]));
-    const unsigned pairBase = opaque((unsigned) __cvta_generic_to_shared(&sPairs[0]));
+    const unsigned pairBase = opaque((unsigned) __cvta_generic_to_shared(&sPairs[0][0]));
     const unsigned entBase = opaque((unsigned) __cvta_generic_to_shared(&sEnt[0][0])+(unsigned) lane*8u);
     const unsigned octBase = opaque((unsigned) __cvta_generic_to_shared(&sOct[0]));
     const unsigned ownPair = opaque(pairBase+(unsigned) (lane>>1)*16u);                 // the slot pair of double-step 0
@@ -133,6 +176,47 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
             EC[s] = EV[s] = 0.0;
     };
 
+    // Fix-up of one chunk: every lane moves its staged j atom (stage buffer `sb`, list entry in ring slot `ring`) into the
+    // frame of the octet in flight and stores it into the pair planes at `pl`; tells whether the chunk is CLEAN -- no
+    // exclusion bit, no padding entry (mask 0xff), every j atom in the same subset: such a chunk takes the lean copy of the
+    // pair loop (no mask plane, one lambda pair and one energy pair for the whole chunk).
+    // (in three parts, so that the early fix-up can be threaded through the pair loop: the shared-memory instructions are
+    // volatile asm and keep their program order, the arithmetic between them is the compiler's to interleave)
+    struct Staged { float4 pj, cJ, prm; unsigned mask; };
+    auto fixupLoad = [&](unsigned sb, unsigned ring, Staged& t) {
+        t.pj = St::ld4(sb+lane*St::STRIDE);
+        t.cJ = ldSharedF4(sb+St::CTR+lane*16);
+        t.prm = St::ld4(sb+St::PRM+lane*St::STRIDE);
+        t.mask = ldSharedU32(entBase+ring*256u+4u);
+    };
+    auto fixupStore = [&](Staged& t, unsigned pl, bool perPairNow) {
+        fixupShift<float>(t.pj, t.cJ, cI, oc, !perPairNow, wb);
+        const float maskF = __uint_as_float(t.mask);
+        stSharedF32(st1+pl+PL_XY, swapStores ? t.pj.y : t.pj.x); stSharedF32(st2+pl+PL_XY, swapStores ? t.pj.x : t.pj.y);
+        stSharedF32(st1+pl+PL_ZQ, swapStores ? t.pj.w : t.pj.z); stSharedF32(st2+pl+PL_ZQ, swapStores ? t.pj.z : t.pj.w);
+        stSharedF32(st1+pl+PL_SE, swapStores ? t.prm.y : t.prm.x); stSharedF32(st2+pl+PL_SE, swapStores ? t.prm.x : t.prm.y);
+        stSharedF32(st1+pl+PL_SM, swapStores ? maskF : t.prm.z); stSharedF32(st2+pl+PL_SM, swapStores ? t.prm.z : maskF);
+    };
+    auto fixupVote = [&](const Staged& t, bool& cleanOut, float& subJ0Out) {
+        subJ0Out = __shfl_sync(full, t.prm.z, 0);
+        cleanOut = !__any_sync(full, t.mask != 0u || t.prm.z != subJ0Out);
+    };
+    auto fixup = [&](unsigned sb, unsigned ring, unsigned pl, bool perPairNow, bool& cleanOut, float& subJ0Out) {
+        Staged t;
+        fixupLoad(sb, ring, t);
+        fixupStore(t, pl, perPairNow);
+        fixupVote(t, cleanOut, subJ0Out);
+    };
+
+    // Pipeline (c = the chunk in the pair loop):  list entries of c+3 and atoms of c+2 in flight (cp.async), atoms of c+1
+    // staged and FIXED UP DURING the pair loop of c -- the fix-up's chain of shared-memory loads, roundings and stores has
+    // nothing to do with the pair arithmetic, so the two streams interleave (ncu on the version that fixed chunk c up at the
+    // top of its own iteration: 29 % of the instructions but 41 % of the warp time in that stretch).  The early fix-up
+    // uses the frame of the octet in flight; when chunk c+1 turns out to belong to the next octet it is simply redone at
+    // the top of its iteration (one chunk in eleven).
+    if (lane < 4)
+        sOct[lane] = 0;
+    __syncwarp();
     if (cBegin < cEnd) {
         fetchEntries(cBegin);
         if (cBegin+1 < cEnd)
@@ -141,22 +225,29 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
         cpAsyncWait<0>();
         __syncwarp();
         gather(cBegin);
+        if (cBegin+2 < cEnd)
+            fetchEntries(cBegin+2);
+        cpAsyncCommit();
+        cpAsyncWait<0>();
+        __syncwarp();
+        if (cBegin+1 < cEnd)
+            gather(cBegin+1);
         cpAsyncCommit();
     }
+    bool cleanNext = false;
+    float subJ0Next = 0.f;
     for (int ch = cBegin; ch < cEnd; ch++) {
-        const unsigned sb = stageBase+(unsigned) (ch&1)*BUF;
-        // the atoms of chunk ch and the entries of chunk ch+1 were requested a whole chunk ago
+        const unsigned sbNext = stageBase+(unsigned) ((ch+1)&1)*BUF;
+        const unsigned pl = (unsigned) (ch&1)*PL_BYTES, plNext = (unsigned) ((ch+1)&1)*PL_BYTES;
+        // the atoms of chunk ch+1 and the entries of chunk ch+2 were requested a whole chunk ago
         cpAsyncWait<0>();
         __syncwarp();                       // ... by every lane; and every lane is done with chunk ch-1
-        if (ch+1 < cEnd) {
-            gather(ch+1);
-            if (ch+2 < cEnd)
-                fetchEntries(ch+2);
-            cpAsyncCommit();
-        }
         const int octCur = __shfl_sync(full, (int) ldSharedU32(octBase+(unsigned) (ch&3)*4u), 0);
         // ---- octet switch
         const int O = octCur&0x3fffffff;
+        bool clean = cleanNext;
+        float subJ0 = subJ0Next;
+        const bool perPair = (octCur&0x40000000) != 0;      // octet too wide for one image per j atom
         if (O != curO) {
             if (curO >= 0)
                 flushOctet();
@@ -175,38 +266,25 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
                 dLamC = (float) a.sp->lambdaC[sliceOf(max(subI, 0), 1)]-lamC0;
                 dLamV = (float) a.sp->lambdaV[sliceOf(max(subI, 0), 1)]-lamV0;
             }
+            // a padding lane can never be "in range": its bounds are negative
+            myCutHi = iValid ? (perPair ? c.cutoffHiWide : bandHi) : -1.f;
+            myCutLo = iValid ? (perPair ? c.cutoffLoWide : bandLo) : -1.f;
+            // the pair loop only has to NOTICE a band pair (bandRescan then classifies every pair of the chunk again with the
+            // exact bounds): |r^2 - mid| < tol, a superset of [lo, hi) -- the difference is exact (Sterbenz), mid carries half
+            // an ulp (3e-8 against a band of 2.6e-6 at least), the tolerance is widened by 5% + 1e-7 for it
+            myCutMid = iValid ? 0.5f*(myCutHi+myCutLo) : -1.f;
+            myBandTol = iValid ? fmaf(0.5f*(myCutHi-myCutLo), 1.05f, 1e-7f) : 0.f;
+            // this chunk was fixed up in the previous octet's frame (or not at all): again, in its own (its atoms sit in the
+            // stage buffer the NEXT gather is about to reuse, hence before that gather is issued)
+            fixup(stageBase+(unsigned) (ch&1)*BUF, (unsigned) (ch&3), pl, perPair, clean, subJ0);
+            __syncwarp();
         }
-        const bool perPair = (octCur&0x40000000) != 0;      // octet too wide for one image per j atom
-        bool clean = false;
-        float subJ0 = 0.f;
-        // a padding lane can never be "in range": its bounds are negative
-        myCutHi = iValid ? (perPair ? c.cutoffHiWide : bandHi) : -1.f;
-        myCutLo = iValid ? (perPair ? c.cutoffLoWide : bandLo) : -1.f;
-        // the pair loop only has to NOTICE a band pair (bandRescan then classifies every pair of the chunk again with the
-        // exact bounds): |r^2 - mid| < tol, a superset of [lo, hi) -- the difference is exact (Sterbenz), mid carries half
-        // an ulp (3e-8 against a band of 2.6e-6 at least), the tolerance is widened by 5% + 1e-7 for it
-        myCutMid = iValid ? 0.5f*(myCutHi+myCutLo) : -1.f;
-        myBandTol = iValid ? fmaf(0.5f*(myCutHi-myCutLo), 1.05f, 1e-7f) : 0.f;
-        // ---- fix-up: this lane's staged j atom moves into the octet's block frame, then into the pair planes
-        {
-            float4 pj = St::ld4(sb+lane*St::STRIDE);
-            const float4 cJ = ldSharedF4(sb+St::CTR+lane*16);
-            const float4 prm = St::ld4(sb+St::PRM+lane*St::STRIDE);
-            const unsigned mask = ldSharedU32(entBase+(unsigned) (ch&3)*256u+4u);
-            fixupShift<float>(pj, cJ, cI, oc, !perPair, wb);
-            St::st4(sb+lane*St::STRIDE, pj);            // bandRescan reads the fixed-up atoms (and their list entries) from the stage
-            stSharedV2U32(sb+St::AUX+lane*St::AUXS, ldSharedU32(entBase+(unsigned) (ch&3)*256u), mask);
-            const float maskF = __uint_as_float(mask);
-            stSharedF32(st1+PL_XY, swapStores ? pj.y : pj.x); stSharedF32(st2+PL_XY, swapStores ? pj.x : pj.y);
-            stSharedF32(st1+PL_ZQ, swapStores ? pj.w : pj.z); stSharedF32(st2+PL_ZQ, swapStores ? pj.z : pj.w);
-            stSharedF32(st1+PL_SE, swapStores ? prm.y : prm.x); stSharedF32(st2+PL_SE, swapStores ? prm.x : prm.y);
-            stSharedF32(st1+PL_SM, swapStores ? maskF : prm.z); stSharedF32(st2+PL_SM, swapStores ? prm.z : maskF);
-            // a CLEAN chunk -- no exclusion bit, no padding entry (mask 0xff), every j atom in the same subset -- takes the lean
-            // copy of the pair loop: no mask plane, one lambda pair and one energy pair for the whole chunk.  Nineteen chunks in twenty.
-            subJ0 = __shfl_sync(full, prm.z, 0);
-            clean = !__any_sync(full, mask != 0u || prm.z != subJ0);
+        if (ch+2 < cEnd) {
+            gather(ch+2);
+            if (ch+3 < cEnd)
+                fetchEntries(ch+3);
         }
-        __syncwarp();
+        cpAsyncCommit();
         float2 fix = bc(0.f), fiy = bc(0.f), fiz = bc(0.f), fjx = bc(0.f), fjy = bc(0.f), fjz = bc(0.f);
         float2 eCt = bc(0.f), eVt = bc(0.f), eC1 = bc(0.f), eV1 = bc(0.f);
         bool anyBand = false;
@@ -216,9 +294,15 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
         constexpr bool CLEAN = decltype(cleanTag)::value;
         // CLEAN: the lambdas of the chunk's one j subset
         const float lamCc = fmaf(subJ0, dLamC, lamC0), lamVc = fmaf(subJ0, dLamV, lamV0);
+        // the next chunk's fix-up, threaded through the pair arithmetic (see above): its loads first, its stores after the
+        // second double-step's loads
+        Staged nextAtoms;
+        fixupLoad(sbNext, (unsigned) ((ch+1)&3), nextAtoms);
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-            const unsigned ad = ownPair^(unsigned) (d*16);
+            if (d == 2)
+                fixupStore(nextAtoms, plNext, PERPAIR);
+            const unsigned ad = (ownPair+pl)^(unsigned) (d*16);
             const float4 xy = ldSharedF4(ad+PL_XY), zq = ldSharedF4(ad+PL_ZQ);
             const float4 se = ldSharedF4(ad+PL_SE);
             float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -300,7 +384,7 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
                 }
             }
             if (DUMP && (in0 || in1)) {
-                const unsigned slot0 = (((ad-pairBase)>>4)<<1);
+                const unsigned slot0 = (((ad-pairBase-pl)>>4)<<1);
 #pragma unroll
                 for (int h = 0; h < 2; h++)
                     if (h == 0 ? in0 : in1) {
@@ -316,6 +400,7 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
             fjy.x = __shfl_xor_sync(full, fjy.x, hop); fjy.y = __shfl_xor_sync(full, fjy.y, hop);
             fjz.x = __shfl_xor_sync(full, fjz.x, hop); fjz.y = __shfl_xor_sync(full, fjz.y, hop);
         }
+        fixupVote(nextAtoms, cleanNext, subJ0Next);
         };
         if (perPair)
             steps(std::true_type(), std::false_type());     // rare (octets wider than half the box minus the cutoff): one copy
@@ -333,7 +418,7 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
                 o.posd = a.posd; o.sortedAtom = a.sortedAtom; o.sp = a.sp; o.forceSorted = a.forceSorted; o.paddedAtoms = a.paddedAtoms;
                 o.energyTable = a.energyBuf+(size_t) (blockIdx.x%ENERGY_REPLICAS)*2*SNB_MAX_SLICES;
                 o.pairDump = a.pairDump; o.pairDumpCount = a.pairDumpCount; o.pairDumpCapacity = a.pairDumpCapacity;
-                bandRescan<float, KIND_EWALD, PBC_SHIFT, ENERGY, DUMP, false>(o, c, lane, ki, origI, myCutLo, myCutHi, pi, si4, perPair ? 1 : 0, &sStage[ch&1][0]);
+                bandRescanPlanes<ENERGY, DUMP>(o, c, lane, ki, origI, myCutLo, myCutHi, pi, si4, perPair ? 1 : 0, &sPairs[ch&1][0], &sEnt[ch&3][0]);
             }
         }
         // lanes k and k^1 hold the two partial sums of the same slot pair: the even lane keeps slot 2P, the odd one 2P+1

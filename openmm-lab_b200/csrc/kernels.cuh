@@ -72,6 +72,7 @@ struct ListArgs {
     const double* extent;   // non-periodic methods: bounding box of all atoms (min[3], max[3])
     int blockLo, blockHi;   // this rank's i blocks
     int bitmapWords;        // ceil(numBlocks/32)
+    int refine;             // test the candidates against the octet's atoms, not only their box (tuning switch, default on)
 };
 cudaError_t launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 

@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 #define ORDER SNB_PME_ORDER
 #define MAX_WARPS 8                      /* CTAs of 128 or 256 threads */
@@ -272,59 +273,82 @@ __global__ void __launch_bounds__(32) k_pmeSpreadWarp(PmeArgs a) {
             const float4 w03 = *(const float4*) sW[t];
             wx[0] = w03.x; wx[1] = w03.y; wx[2] = w03.z; wx[3] = w03.w; wx[4] = sW[t][4];
         };
-        unsigned m = set;
-        int cell;
-        float wyz, wx[ORDER];
-        fetch(__ffs(m)-1, cell, wyz, wx);
-        m &= m-1u;
-        for (;;) {
-            int cellN = 0;
-            float wyzN = 0.f, wxN[ORDER] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            const bool more = m != 0u;
-            if (more)
-                fetch(__ffs(m)-1, cellN, wyzN, wxN);
+        auto add = [&](int cell, float wyz, const float (&wx)[ORDER]) {
             if (lane < ORDER*ORDER) {
 #pragma unroll
                 for (int ix = 0; ix < ORDER; ix++)
                     sBrick[cell+ix*WB_Y*WB_Z] += wyz*wx[ix];
             }
             __syncwarp();
-            if (!more)
+        };
+        // (two register sets taking turns: no copies between "this atom" and "the next one")
+        unsigned m = set;
+        int cellA, cellB = 0;
+        float wyzA, wyzB = 0.f, wxA[ORDER], wxB[ORDER] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        fetch(__ffs(m)-1, cellA, wyzA, wxA);
+        m &= m-1u;
+        for (;;) {
+            const bool moreB = m != 0u;
+            if (moreB) {
+                fetch(__ffs(m)-1, cellB, wyzB, wxB);
+                m &= m-1u;
+            }
+            add(cellA, wyzA, wxA);
+            if (!moreB)
                 break;
-            m &= m-1u;
-            cell = cellN; wyz = wyzN;
-#pragma unroll
-            for (int ix = 0; ix < ORDER; ix++)
-                wx[ix] = wxN[ix];
+            const bool moreA = m != 0u;
+            if (moreA) {
+                fetch(__ffs(m)-1, cellA, wyzA, wxA);
+                m &= m-1u;
+            }
+            add(cellB, wyzB, wxB);
+            if (!moreA)
+                break;
         }
-        // ---- flush the touched box [0, span) of the brick into the grid (periodic wrap per row), and clear it
+        // ---- flush the touched box [0, span) of the brick into the grid (periodic wrap per row), and clear it.  A lane keeps
+        // the same (y, group) columns of the box for every x plane (at most 16 x 5 = 80 float4 columns: three per lane), so the
+        // column's decoding, wrapping and addresses are computed once and the walk over x is five instructions per group
         const int gz = (span[2]+VEC-1)/VEC;                 // groups of VEC points per row
-        const int perPlane = span[1]*gz, total = span[0]*perPlane;
-        const unsigned invPlane = (1u<<20)/(unsigned) perPlane+1u, invGz = (1u<<20)/(unsigned) gz+1u;  // k*inv >> 20 = k/d exactly for k < 2^20/d
+        const int perPlane = span[1]*gz;
+        const unsigned invGz = (1u<<20)/(unsigned) gz+1u;   // r*inv >> 20 = r/gz exactly for r < 2^20/gz
         float* base = grid+(size_t) subset*nx*ny*nz;
-        for (int k = lane; k < total; k += 32) {
-            const int x = (int) (((unsigned) k*invPlane)>>20), r = k-x*perPlane;
+        constexpr int NCOL = VEC == 4 ? 3 : 10;             // 16 x 5 float4 columns, or 16 x 20 scalar ones, over 32 lanes
+        int colS[NCOL], colG[NCOL];                         // shared-memory and grid offsets of this lane's columns (-1: none)
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) {
+            const int r = lane+32*c;
             const int y = (int) (((unsigned) r*invGz)>>20), g = r-y*gz;
-            float* p = sBrick+(x*WB_Y+y)*WB_Z+g*VEC;
-            int X = origin[0]+x, Y = origin[1]+y, Z = origin[2]+g*VEC;
-            X -= X >= nx ? nx : 0;
+            int Y = origin[1]+y, Z = origin[2]+g*VEC;
             Y -= Y >= ny ? ny : 0;
             Z -= Z >= nz ? nz : 0;
-            float* dst = base+((size_t) X*ny+Y)*nz+Z;
-            if (VEC == 4) {
-                const float4 v = *(const float4*) p;
-                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-                    *(float4*) p = make_float4(0.f, 0.f, 0.f, 0.f);
+            colS[c] = r < perPlane ? y*WB_Z+g*VEC : -1;
+            colG[c] = Y*nz+Z;
+        }
+        for (int x = 0; x < span[0]; x++) {
+            int X = origin[0]+x;
+            X -= X >= nx ? nx : 0;
+            float* plane = base+(size_t) X*ny*nz;
+            float* sp = sBrick+x*WB_Y*WB_Z;
+#pragma unroll
+            for (int c = 0; c < NCOL; c++)
+                if (colS[c] >= 0) {
+                    float* p = sp+colS[c];
+                    float* dst = plane+colG[c];
+                    if (VEC == 4) {
+                        const float4 v = *(const float4*) p;
+                        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                            *(float4*) p = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    else {
+                        const float v = *p;
+                        if (v != 0.f) {
+                            atomicAdd(dst, v);
+                            *p = 0.f;
+                        }
+                    }
                 }
-            }
-            else {
-                const float v = *p;
-                if (v != 0.f) {
-                    atomicAdd(dst, v);
-                    *p = 0.f;
-                }
-            }
         }
         __syncwarp();
     }
@@ -474,7 +498,8 @@ __global__ void __launch_bounds__(32*MAX_WARPS) k_pmeInterpBrick(PmeArgs a, cons
 // every axis, and enough atoms to fill the GPU with such CTAs: below that the kernel is one wave of CTAs whose length is a
 // chain of latencies (gather, vote, 64 KB bulk load, 125 points), and 64-atom CTAs on 20 KB bricks finish it sooner.
 static bool bigBrick(int numAtoms, int nx, int ny, int nzp) {
-    return numAtoms >= 148*2*256 && nx+4 >= BigBrick::BX && ny+4 >= BigBrick::BY && nzp >= BigBrick::BZ;
+    static const bool forceSmall = getenv("SNB_PME_SMALL_BRICK") != nullptr;    // A/B measurements
+    return !forceSmall && numAtoms >= 148*2*256 && nx+4 >= BigBrick::BX && ny+4 >= BigBrick::BY && nzp >= BigBrick::BZ;
 }
 
 bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numAtoms, int numSubsets, int nx, int ny, int nzp) {

@@ -1,0 +1,9 @@
+OUT=gpurun_out; TAG=r2p
+mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest=$?" >> $OUT/${TAG}_status.txt
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu --no-parity > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench=$?" >> $OUT/${TAG}_status.txt
+SNB_NO_LIST_REFINE=1 timeout 300 python bench.py --workload stmv --steps 30 --warmup 5 --no-cpu --no-parity --no-others > $OUT/${TAG}_stmv_norefine.json 2> /dev/null
+SNB_PME_SMALL_BRICK=1 timeout 300 python bench.py --workload stmv --steps 30 --warmup 5 --no-cpu --no-parity --no-others > $OUT/${TAG}_stmv_smallbrick.json 2> /dev/null
+SNB_NO_LIST_REFINE=1 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu --no-parity --no-others > $OUT/${TAG}_dhfr_norefine.json 2> /dev/null
+timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu --no-parity --no-others --direct-kernel packed > $OUT/${TAG}_dhfr_packed.json 2> /dev/null
+cat $OUT/${TAG}_status.txt; tail -5 $OUT/${TAG}_pytest.log
