@@ -26,6 +26,9 @@ shared by all ranks ("scaling": "strong"), on N > 1 GPUs -- the configuration no
   roofline      direct-space tile kernel: algorithmic flop per interacting pair (67 for PME Coulomb+LJ
                 with energies and derivatives, 105 for LJPME) / its CUDA-event duration, against the FP32 FMA peak
                 (non-tensor path); the memory-bound PME kernels are listed against the measured HBM peak in "kernels"
+  md            (N = 1) the timed workload along a trajectory -- positions rewritten on the device before every step --
+                with the tile list rebuilt every evaluation (as on the main line) and with platform property ListSkin
+                (list built for cutoff + skin, kept until an atom has moved skin/2; rebuild count reported)
   N > 1         tile list and exceptions partitioned, reciprocal space on rank 0 overlapping the ncclReduce of the
                 other ranks' fixed-point forces.  "replicas" = every rank evaluates its own DHFR-size copy (the lambda
                 windows of an alchemical calculation), no collective -- reported as a sub-object.
@@ -391,6 +394,38 @@ class Runner:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0].item()), float(t[1].item())
 
+    def measure_md(self, steps, warmup, flush, sigma=0.001, period=40):
+        """Device-resident evaluations/s along a trajectory: the positions change EVERY step, as between the steps of a
+        simulation (ballistic motion with a per-component velocity of `sigma` nm/step, reversed every `period` steps so
+        that atoms never overlap), positions written by a torch kernel outside the timed region."""
+        torch = self.torch
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(1234)
+        vel = torch.randn((self.n, 3), generator=gen, device="cuda", dtype=torch.float32)*sigma
+        base = self.posq[:, :3].clone()
+
+        def place(k):
+            phase = k % (2*period)
+            self.posq[:, :3] = base+float(phase if phase <= period else 2*period-phase)*vel
+
+        for k in range(warmup):
+            place(k)
+            self.step_device()
+        c0 = self.kernel.getCounters()
+        total, dev = 0.0, 0.0
+        for k in range(warmup, warmup+steps):
+            place(k)
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            self.step_device()
+            total += time.perf_counter()-t0
+            dev += self.kernel.getLastDeviceMs()*1e-3
+        c1 = self.kernel.getCounters()
+        self.posq[:, :3] = base
+        return {"value": steps/total, "ms_per_step": 1e3*total/steps, "device_ms_per_step": 1e3*dev/steps,
+                "rebuilds": int(c1[6]-c0[6]), "steps": steps}
+
     def phases(self, reps, flush):
         """Per-phase CUDA-event times (this mode serialises the streams), averaged."""
         k = self.kernel
@@ -465,6 +500,26 @@ class Runner:
         return out
 
 
+def md_report(name, w, local, rank, world, dist, flush, steps, skin):
+    """The same workload along a trajectory (positions move every step): tile list rebuilt every evaluation (the main
+    line's mode, Reference-platform behaviour) against platform property ListSkin (list kept until an atom has moved
+    skin/2; the exact predicate still decides the pair set every step) -- include/slicednb.h snb_set_list_skin."""
+    out = {"trajectory": "ballistic, 0.001 nm per step and component (thermal speed of a 10 u particle at 300 K over 2 fs), reversed every 40 steps; "
+                         "positions rewritten on the device before every step, outside the timed region",
+           "list_skin_nm": skin}
+    for key, props in (("rebuild_every_step", {}), ("list_reuse", {"ListSkin": str(skin)})):
+        r = Runner(name, local, rank, world, dist, properties=props, workload=w)
+        m = r.measure_md(steps, 8, flush)
+        if key == "list_reuse":
+            m["steps_per_rebuild"] = round(m["steps"]/max(1, m["rebuilds"]), 1)
+        else:
+            m.pop("rebuilds")
+        out[key] = m
+        del r
+    out["speedup"] = out["list_reuse"]["value"]/out["rebuild_every_step"]["value"]
+    return out
+
+
 def short(res, keys=("value", "ms_per_step", "device_ms_per_step", "e2e", "roofline", "gpu_launches", "kernels", "phases_ms")):
     out = {k: res[k] for k in keys if k in res}
     if "roofline" in out:
@@ -519,6 +574,8 @@ def run_b200(args):
             del dbl
         if not args.no_cpu:
             extras["cpu_baseline"] = cpu_reference(main_w)
+        if not args.no_md:
+            extras["md"] = md_report(name, main_w, local, rank, world, dist, flush, min(steps, 200), args.list_skin)
         others = [] if args.no_others else [x for x in ("stmv", "apoa1", "fep") if x != name]
         for other in others:
             r = Runner(other, local, rank, world, dist)
@@ -539,7 +596,7 @@ def run_b200(args):
             del r
     if rank == 0:
         # short objects first, the bulky ones last (a truncated tail must not cost the headline sub-objects)
-        for k in ("parity", "value_double", "cpu_baseline", "stmv", "apoa1", "fep", "replicas_dhfr"):
+        for k in ("parity", "value_double", "cpu_baseline", "md", "stmv", "apoa1", "fep", "replicas_dhfr"):
             if k in extras:
                 line[k] = extras[k]
         line["kernels"] = res.get("kernels")
@@ -564,6 +621,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-md", action="store_true", help="skip the trajectory sub-object (list reuse)")
+    ap.add_argument("--list-skin", type=float, default=0.1, help="ListSkin (nm) of the trajectory sub-object")
     ap.add_argument("--no-others", action="store_true", help="skip the sub-objects of the other workloads")
     ap.add_argument("--no-stmv", action="store_true", help="(kept for old command lines) same as --no-others")
     ap.add_argument("--multi", default="auto", choices=["auto", "replicas", "partition"])

@@ -81,6 +81,8 @@ enum {
     SNB_FLAG_DIRECT_GENERAL = 8
 };
 #define SNB_PACKED_MIN_ATOMS 65536
+    /* PME interpolation goes through shared-memory bricks (TMA) from this many atoms on; the per-atom kernel below */
+#define SNB_PME_BRICK_MIN_ATOMS 250000
 
 typedef struct snb_desc {
     int32_t struct_size;               /* = sizeof(snb_desc); guards against ABI drift */
@@ -214,6 +216,17 @@ void snb_free(void* p);
  * evaluation overflow, grow the buffers and repeat -- the path a locally dense system takes on its first evaluation. */
 int snb_set_list_capacity(snb_handle* h, int64_t chunks);
 
+/* Tile-list reuse (platform property ListSkin).  skin_nm > 0: the sorted order and the tile list are built with
+ * cutoff + skin and KEPT between evaluations until some atom has moved more than skin/2 since the build (checked on
+ * the device every evaluation), the box vectors change, or the list buffers / the multi-GPU partition do; block
+ * boxes and local coordinates are refreshed every evaluation.  The exact cutoff predicate still decides the pair set
+ * every evaluation, so energies, forces and the set of interacting pairs do not depend on when the list was built.
+ * 0 (default): rebuilt every evaluation, as the Reference platform does
+ * (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:203); OpenMM's CUDA platform, from which the reference's
+ * CUDA kernels inherit their neighbour list, pads and reuses its list the same way.  A periodic box clips the skin
+ * to 0.9 (L_min/2 - cutoff). */
+int snb_set_list_skin(snb_handle* h, double skin_nm);
+
 /* per-phase device times (ms) of the last execute, when timing is enabled */
 enum { SNB_PHASE_SORT = 0, SNB_PHASE_LIST, SNB_PHASE_DIRECT, SNB_PHASE_BONDED,
        SNB_PHASE_SPREAD, SNB_PHASE_FFT, SNB_PHASE_CONV, SNB_PHASE_INTERP,
@@ -226,7 +239,8 @@ int snb_get_last_device_ms(snb_handle* h, float* ms);
 /* counters of the last execute: [0] unused (the interacting pairs are counted on request: snb_count_pairs),
  * [1] chunks of 32 tile-list entries, [2] kernel launches of this library, [3] k_computeParameters launches since
  * creation, [4] 1 when the evaluation was replayed from a captured CUDA graph, [5] 1 when the packed-FP32 direct-space
- * kernel (k_directPacked) took the launch, 0 for the general one (k_direct) */
+ * kernel (k_directPacked) took the launch, 0 for the general one (k_direct), [6] tile-list rebuilds and [7]
+ * direct-space evaluations since list reuse was switched on (snb_set_list_skin) */
 int snb_get_counters(snb_handle* h, int64_t* out /*[8]*/);
 
 const char* snb_last_error(void);

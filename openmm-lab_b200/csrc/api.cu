@@ -180,7 +180,7 @@ struct GraphKey {
     int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast;
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
-    double share;
+    double share, listSkin;
 };
 
 #define SNB_ENERGY_FLAGS 32
@@ -248,6 +248,16 @@ struct snb_handle {
     PinnedBuf<double> hPos, hForces, hEnergy;
     PinnedBuf<int> hCounters;
     size_t maxChunks = 0;
+    // ---- tile-list reuse (platform property ListSkin, snb_set_list_skin; 0 = rebuilt every evaluation) ----
+    double listSkin = 0;                // as requested
+    double skinNow = 0;                 // in effect for the evaluation being prepared (a small box clips it: cutoff + skin <= half the box)
+    DevBuf<double> posRef;              // positions at the last rebuild
+    DevBuf<float4> wrapImage;           // periodic image every atom was wrapped by at the last rebuild
+    DevBuf<int> listState;              // [0] chunks of the kept list
+    bool listKept = false;              // a list built with this skin, box, capacity and partition is on the device
+    double listBox[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, listShare = 0, listBuiltSkin = 0;
+    size_t listMaxChunks = 0;
+    long long listRebuilds = 0, listEvals = 0;
     PmeGrid pme, dpme;
     // ---- multi-GPU (comm.cuh): tile list and exceptions partitioned, reciprocal space on rank 0 ----
     ncclComm_t comm = nullptr;
@@ -501,8 +511,14 @@ void setupPme(snb_handle& h, PmeGrid& g, const int n[3], double alpha) {
         g.fixed.alloc(G*h.S);
     // shared-memory bricks + TMA (pme_brick.cu): mixed precision, float atomics allowed (not the deterministic mode),
     // every dimension at least one brick long
+    // Measured on B200 (gpurun_out r2q, profiles/README.md): the brick interpolation wins from a few hundred thousand atoms
+    // on (STMV size: 146 us with its combine pass against 390 us) and loses below (ApoA1 size 134 vs 112 us, DHFR size 48 vs
+    // 39 us: a CTA's chain of vote -> 64 KB bulk load -> 125 points is longer than the per-atom kernel's when there are too
+    // few CTAs to overlap).  SNB_PME_BRICK_MIN_ATOMS overrides the threshold (A/B measurements).
     g.brick = false;
-    if (!h.doublePrecision && !h.deterministic && n[0] >= 16 && n[1] >= 16 && n[2] >= 16 && getenv("SNB_NO_PME_BRICKS") == nullptr) {
+    const char* brickEnv = getenv("SNB_PME_BRICK_MIN_ATOMS");
+    const long brickMinAtoms = brickEnv ? atol(brickEnv) : SNB_PME_BRICK_MIN_ATOMS;
+    if (!h.doublePrecision && !h.deterministic && h.N >= brickMinAtoms && n[0] >= 20 && n[1] >= 20 && n[2] >= 24 && getenv("SNB_NO_PME_BRICKS") == nullptr) {
         g.nzp = (n[2]+4+3)&~3;
         g.pad.alloc((size_t) h.S*(n[0]+4)*(n[1]+4)*g.nzp);
         g.brick = makeBrickTensorMap(&g.brickMap, g.pad.p, h.N, h.S, n[0], n[1], g.nzp);
@@ -803,7 +819,7 @@ void ensureListCapacity(snb_handle& h, const double* box, bool periodic) {
         perOctet = h.NB+2;
     else {
         double density = periodic ? h.N/(box[0]*box[4]*box[8]) : 100.0;
-        double reach = h.cutoff+0.3;
+        double reach = h.cutoff+h.skinNow+0.3;
         double atoms = 0.5*density*(4.0/3.0*M_PI*reach*reach*reach)*1.3+72;
         perOctet = std::min<size_t>((size_t) (atoms/32)+2, (size_t) h.NB+2);
     }
@@ -851,6 +867,11 @@ int prepareStep(snb_handle& h, const double* box, bool periodic) {
     BoxD bd;
     BoxF bf;
     makeBox(box, bd, bf);
+    h.skinNow = h.method == SNB_NO_CUTOFF ? 0.0 : h.listSkin;
+    if (periodic && h.skinNow > 0) {
+        const double room = 0.5*std::min(bd.ax, std::min(bd.by, bd.cz))-h.cutoff;
+        h.skinNow = std::max(0.0, std::min(h.skinNow, 0.9*room));
+    }
     setupCells(h, box, periodic);
     ensureListCapacity(h, box, periodic);
     int pbcMode = PBC_NONE;
@@ -867,6 +888,14 @@ int prepareStep(snb_handle& h, const double* box, bool periodic) {
     for (int s = 0; s < SNB_MAX_SLICES; s++) {
         sp.lambdaC[s] = s < h.L ? h.lambdaC[s] : 0.0;
         sp.lambdaV[s] = s < h.L ? h.lambdaV[s] : 0.0;
+    }
+    // list reuse: the host's own reasons for a rebuild (the device adds "an atom has moved more than skin/2", sort.cu)
+    sp.skinHalf2 = 0.25*h.skinNow*h.skinNow;
+    sp.forceRebuild = 0;
+    if (h.skinNow > 0) {
+        const double share = h.comm ? rank0Share(h) : 0.0;
+        if (!h.listKept || memcmp(h.listBox, box, sizeof(h.listBox)) != 0 || h.listMaxChunks != h.maxChunks || h.listShare != share || h.listBuiltSkin != h.skinNow)
+            sp.forceRebuild = 1;
     }
     return pbcMode;
 }
@@ -981,6 +1010,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         sa.cellRange = h.cellRange.p; sa.tileSum = h.tileSum.p; sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
+        sa.reuse = h.skinNow > 0; sa.posRef = h.posRef.p; sa.wrapImage = h.wrapImage.p;
         launchSort(sa, st);
     }
     tm.mark(1);
@@ -1008,9 +1038,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             CUFFT_CHECK(cufftSetStream(g.inv, ps));
             // atoms in sorted order + mixed precision: shared-memory bricks moved by TMA; else the per-atom kernels
             const bool bricks = g.brick && pa.sortedAtom != nullptr;
-            static const bool noBrickSpread = getenv("SNB_NO_BRICK_SPREAD") != nullptr, noBrickInterp = getenv("SNB_NO_BRICK_INTERP") != nullptr;
-            if (bricks && !noBrickSpread) CUDA_CHECK(launchPmeSpreadBrick(pa, g.brickMap, ps));
-            else launchPmeSpread(pa, ps);
+            static const bool noBrickInterp = getenv("SNB_NO_BRICK_INTERP") != nullptr;
+            launchPmeSpread(pa, ps);
             if (term == 0) tm.mark(5);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecD2Z(g.fwd, (double*) g.real.p, (cufftDoubleComplex*) g.cplx.p));
             else CUFFT_CHECK(cufftExecR2C(g.fwd, (float*) g.real.p, (cufftComplex*) g.cplx.p));
@@ -1040,7 +1069,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         memset(&la, 0, sizeof(la));
         la.numAtoms = h.N; la.numBlocks = h.NB; la.pbcMode = in.pbcMode; la.periodic = periodic;
         la.useCutoff = h.method != SNB_NO_CUTOFF;
-        la.cutoff = (float) (h.cutoff*(1.0+1e-5)+1e-5);
+        la.cutoff = (float) ((h.cutoff+h.skinNow)*(1.0+1e-5)+1e-5);
+        la.reuse = h.skinNow > 0; la.skin = (float) h.skinNow;
         la.sp = h.stepD.p;
         la.sortedAtom = h.sortedAtom.p; la.sortedPos = h.sortedPos.p; la.posqLocal = h.posqLocal.p;
         la.blockCenter = h.blockCenter.p; la.blockExt = h.blockExt.p; la.octetCenter = h.octetCenter.p; la.octetExt = h.octetExt.p;
@@ -1058,7 +1088,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         // 163.6 us), a loss at STMV size (3.05 vs 2.85 ms), so it is on below SNB_PACKED_MIN_ATOMS atoms only.
         // SNB_LIST_REFINE=0/1 overrides (A/B measurements).
         static const char* refineEnv = getenv("SNB_LIST_REFINE");
-        la.refine = refineEnv ? atoi(refineEnv) != 0 : h.N < SNB_PACKED_MIN_ATOMS;
+        // (a kept list pays for its build once in ~10 evaluations and for every entry in all of them: always refined)
+        la.refine = refineEnv ? atoi(refineEnv) != 0 : (h.N < SNB_PACKED_MIN_ATOMS || h.skinNow > 0);
         CUDA_CHECK(launchBuildList(la, st, h.numSMs));
         tm.mark(2);
 
@@ -1087,7 +1118,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         da.posqLocalD = h.posqLocalD.p; da.sparamsD = h.sparamsD.p;
         da.sortedAtom = h.sortedAtom.p; da.posqLocal = h.posqLocal.p; da.sparams = h.sparams.p;
         da.blockCenter = h.blockCenter.p; da.octetCenter = h.octetCenter.p; da.posd = h.posd.p; da.jList = h.jList.p; da.chunkOctet = h.chunkOctet.p; da.maxChunks = (int) h.maxChunks;
-        da.counters = h.counters.p; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
+        da.counters = h.counters.p; da.listState = h.skinNow > 0 ? h.listState.p : nullptr; da.forceSorted = h.forceSorted.p; da.paddedAtoms = h.NP; da.energyBuf = h.energyBuf.p;
         h.packedLaunched = launchDirect(da, st, h.numSMs);
         if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evDirEnd, st));
         tm.mark(3);
@@ -1201,6 +1232,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     key.maxChunks = h.maxChunks;
     key.share = h.comm ? rank0Share(h) : 0.0;
+    key.listSkin = h.skinNow;
     key.broadcast = h.comm && h.broadcastPositions;
     key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p; key.hostPos = hostPos;
     const bool graphable = h.useGraph && !h.timing && (!h.comm || h.balanceFrozen);
@@ -1293,15 +1325,29 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
             h.jList.alloc(h.maxChunks*32);
             h.chunkOctet.alloc(h.maxChunks);
         }
-        if (anyOverflow)
+        if (anyOverflow) {
+            h.listKept = false;
             return false;       // all ranks repeat together (the flag travelled with the all-reduce)
+        }
     }
     if (h.timing) {
         for (int k = 0; k < 9; k++)
             CUDA_CHECK(cudaEventElapsedTime(&h.phaseMs[k], h.ev[k], h.ev[k+1]));
         CUDA_CHECK(cudaEventElapsedTime(&h.phaseMs[SNB_PHASE_TOTAL], h.ev[0], h.ev[9]));
     }
+    if (includeDirect && h.skinNow > 0) {
+        // the device has the list of this evaluation's (or an earlier) rebuild: remember what it was built for
+        h.listKept = true;
+        memcpy(h.listBox, box, sizeof(h.listBox));
+        h.listMaxChunks = h.maxChunks;
+        h.listShare = h.comm ? rank0Share(h) : 0.0;
+        h.listBuiltSkin = h.skinNow;
+        h.listEvals++;
+        if (h.hCounters.p[SNB_COUNTER_REBUILD]) h.listRebuilds++;
+    }
     h.countersOut[1] = h.hCounters.p[0];
+    h.countersOut[6] = h.listRebuilds;
+    h.countersOut[7] = h.listEvals;
     h.countersOut[3] = h.paramLaunches;
     h.countersOut[4] = h.graphExec ? 1 : 0;
     h.countersOut[5] = includeDirect && h.packedLaunched ? 1 : 0;
@@ -1582,10 +1628,30 @@ int snb_set_list_capacity(snb_handle* h, int64_t chunks) {
     CUDA_CHECK(cudaSetDevice(h->device));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     dropGraph(*h);
+    h->listKept = false;
     h->jList.release(); h->chunkOctet.release();
     h->maxChunks = (size_t) chunks;
     h->jList.alloc(h->maxChunks*32);
     h->chunkOctet.alloc(h->maxChunks);
+    return SNB_OK;
+    SNB_CATCH
+}
+
+/* Tile-list reuse: skin_nm > 0 builds the list with cutoff + skin and keeps it (and the sorted order) until an atom has moved
+ * more than skin/2, the box changes, or the buffers / the multi-GPU partition do; 0 (default) rebuilds every evaluation. */
+int snb_set_list_skin(snb_handle* h, double skin_nm) {
+    SNB_TRY
+    if (!h || !(skin_nm >= 0.0) || skin_nm > 10.0) throw SnbException(SNB_ERR_INVALID, "bad list skin");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (skin_nm > 0 && h->N > 0 && !h->posRef.p) {
+        h->posRef.alloc(3*(size_t) h->N);
+        h->wrapImage.alloc(h->N);
+        h->listState.alloc(4);
+        CUDA_CHECK(cudaMemset(h->listState.p, 0, 4*sizeof(int)));
+    }
+    h->listSkin = skin_nm;
+    h->listKept = false;
     return SNB_OK;
     SNB_CATCH
 }

@@ -276,6 +276,22 @@ template <typename R> __device__ __forceinline__ void fixupShift(typename Real<R
     pj.z = fma(-mz, wb.czLo, pj.z+fma(-mz, wb.czHi, sz));
 }
 
+// Chunks of the tile list this evaluation works on (0 when the list overflowed its buffers: the host discards the pass and
+// repeats it).  List reuse: an evaluation that kept the list finds its length in listState[0] (device-resident between
+// evaluations; the counters are zeroed every evaluation), one that rebuilt it leaves the new length there.
+__device__ __forceinline__ int listChunks(const DirectArgs& a) {
+    int n = a.counters[0];
+    if (a.listState) {
+        if (a.counters[SNB_COUNTER_REBUILD] == 0)
+            n = a.listState[0];
+        if (blockIdx.x == 0 && threadIdx.x == 0 && !a.counters[2]) {
+            a.listState[0] = n;
+            a.counters[0] = n;          // (the host reads the length from the counters)
+        }
+    }
+    return a.counters[2] ? 0 : min(n, a.maxChunks);
+}
+
 // what the rare out-of-line paths need, by value (taking the address of the kernel's parameter block
 // would copy all of it to the stack)
 struct DirectOut {
@@ -409,7 +425,7 @@ __global__ void __launch_bounds__(32, sizeof(R) == 4 ? (NSUB > 2 || NSUB == 0 ? 
     // (values loaded from a uniform address are broadcast through a shuffle so that the compiler KNOWS they are
     // warp-uniform: the loops and branches they steer then carry no divergence bookkeeping)
     // (a list that overflowed its buffers holds unwritten chunks: the host discards this pass and repeats it)
-    const int numChunks = __shfl_sync(full, a.counters[2] ? 0 : min(a.counters[0], a.maxChunks), 0);
+    const int numChunks = __shfl_sync(full, listChunks(a), 0);
     const int per = (numChunks+(int) gridDim.x-1)/(int) gridDim.x;
     const int cBegin = min(numChunks, (int) blockIdx.x*per), cEnd = min(numChunks, cBegin+per);
     const BoxD boxd = a.sp->exact.boxd;

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(32, PACKED_CTAS_PER_SM) k_directPacked(DirectA
     const unsigned full = 0xffffffffu;
     const DirectConsts<float>& c = a.cf;
     // a list that overflowed its buffers holds unwritten chunks: the host discards this pass and repeats it
-    const int numChunks = __shfl_sync(full, a.counters[2] ? 0 : min(a.counters[0], a.maxChunks), 0);
+    const int numChunks = __shfl_sync(full, listChunks(a), 0);
     const int per = (numChunks+(int) gridDim.x-1)/(int) gridDim.x;
     const int cBegin = min(numChunks, (int) blockIdx.x*per), cEnd = min(numChunks, cBegin+per);
     const WrapBox<float> wb = makeWrapBox<float>(a.sp->exact.boxd);

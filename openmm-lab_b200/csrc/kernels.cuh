@@ -48,6 +48,11 @@ struct SortArgs {
     float4* blockCenter;    // [numBlocks] centre of every block (exact in float, see k_blockBounds)
     float4* blockExt;
     float4 *octetCenter, *octetExt;  // [4*numBlocks] block-local centre / half extents of every octet
+    // tile-list reuse (off: reuse = 0 and the pointers are null).  The sorted order and the list are rebuilt only when
+    // k_listCheck raises counters[SNB_COUNTER_REBUILD]; k_blockBounds runs every evaluation on the kept order.
+    int reuse;
+    double* posRef;         // [N][3] positions at the last rebuild
+    float4* wrapImage;      // [N] periodic image (whole box vectors) every atom was wrapped by at the last rebuild
 };
 void launchSort(const SortArgs& a, cudaStream_t stream);
 
@@ -73,6 +78,8 @@ struct ListArgs {
     int blockLo, blockHi;   // this rank's i blocks
     int bitmapWords;        // ceil(numBlocks/32)
     int refine;             // test the candidates against the octet's atoms, not only their box (tuning switch, default on)
+    int reuse;              // list reuse on: build only when counters[SNB_COUNTER_REBUILD] is raised
+    float skin;             // (cutoff already includes it) octets this close to the one-image limit wrap per pair: they may grow
 };
 cudaError_t launchBuildList(const ListArgs& a, cudaStream_t stream, int numSMs);
 
@@ -107,6 +114,7 @@ struct DirectArgs {
     const int* chunkOctet;
     int maxChunks;
     int* counters;
+    int* listState;             // list reuse: [0] chunks of the kept list (device-resident between evaluations), or null
     long long* forceSorted;     // [3][paddedAtoms]
     int paddedAtoms;
     double* energyBuf;          // [numSlices][2]
@@ -159,7 +167,6 @@ void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);
 // brick path (mixed precision, sorted atoms): shared-memory grid bricks moved by TMA
 bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numAtoms, int numSubsets, int nx, int ny, int nzp);
-cudaError_t launchPmeSpreadBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
 cudaError_t launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream);
 
 struct EwaldArgs {

@@ -130,6 +130,9 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
     const int I = a.blockLo+blockIdx.x;                 // i block; warp w owns its octet w
     if (I >= a.blockHi)
         return;
+    // list reuse: nothing to do unless this evaluation rebuilds (sort.cu, k_listCheck)
+    if (a.reuse && a.counters[SNB_COUNTER_REBUILD] == 0)
+        return;
     const int O = 4*I+w;
     // shared: bitmap | candidates of the window | flag words of the batch under test | per-octet hit lists
     unsigned* bm = sMem;
@@ -271,7 +274,8 @@ template <int PBC> __global__ void __launch_bounds__(LIST_WARPS*32, 7) k_buildLi
     int nh = 0;
     bool first = true, dead = false;
     // octets too wide for the one-image-per-j-atom shortcut wrap every pair instead
-    const int wide = (pbcMode == PBC_SHIFT && (ext.x >= a.sp->shiftLimit[0] || ext.y >= a.sp->shiftLimit[1] || ext.z >= a.sp->shiftLimit[2])) ? 1 : 0;
+    // (a kept list: the octet's box may grow by skin/2 on every side, and its centre move as much, before the next rebuild)
+    const int wide = (pbcMode == PBC_SHIFT && (ext.x+a.skin >= a.sp->shiftLimit[0] || ext.y+a.skin >= a.sp->shiftLimit[1] || ext.z+a.skin >= a.sp->shiftLimit[2])) ? 1 : 0;
     const int ki = O*8+(lane&7);
     const int atomK = mine ? a.sortedAtom[ki] : -1;     // atom k = lane&7 of the octet, on every lane
     const int atomI = lane < 8 ? atomK : -1;

@@ -1,25 +1,24 @@
-// Sliced PME spreading and interpolation through shared-memory grid bricks (mixed precision, atoms in the sorted order of
-// the tile list; every other case keeps the kernels of pme.cu).
+// Sliced PME interpolation through shared-memory grid bricks (mixed precision, atoms in the sorted order of the tile list,
+// large systems; every other case -- and all spreading -- keeps the kernels of pme.cu).
 //
-// The atoms arrive spatially sorted, so consecutive atoms and their 5x5x5 stencils sit in a small brick of the grid.
-//   spreading      a warp accumulates 32 atoms into a private 16x16x20 brick in shared memory (plain read-modify-writes,
-//                  a fixed order, no atomics) and sends the touched part to the grid as float4 reductions
-//                  (red.global.add.v4.f32): see k_pmeSpreadWarp below for what that replaces and why;
-//   interpolation  a CTA of 128 / 256 atoms fetches the 24x24x28 brick of the (lambda-combined) potential with ONE bulk tensor
-//                  load (cp.async.bulk.tensor.4d, SASS UTMALDG, completion on an mbarrier) and then works one THREAD per
-//                  atom: 125 shared-memory loads and ~460 FMAs with the atom's spline weights in registers, no shuffles,
-//                  no reduction.
+// The atoms arrive spatially sorted, so consecutive atoms and their 5x5x5 stencils sit in a small brick of the grid.  A CTA
+// of 256 atoms fetches the 24x24x28 brick of the (lambda-combined) potential with ONE bulk tensor load
+// (cp.async.bulk.tensor.4d, SASS UTMALDG, completion on an mbarrier) and then works one THREAD per atom: 125 shared-memory
+// loads and ~460 FMAs with the atom's spline weights in registers, no shuffles, no reduction.
 // A set of atoms whose stencils do not fit one brick (a jump of the space-filling curve, the periodic boundary, a subset
 // boundary: the grids are per subset) is halved, in sorted order, until it does; a single atom always fits.
 //
-// Interpolation bricks never wrap: they address a PADDED copy of the potentials, [S][nx+4][ny+4][nzp] with nzp = nz+4 rounded
-// up to a multiple of 4 floats (TMA strides are multiples of 16 bytes); a brick hanging over the padded extent is clipped by
-// the TMA unit itself (the subset is the tensor's fourth coordinate).  After the inverse transform k_pmeCombinePad writes
+// Bricks never wrap: they address a PADDED copy of the potentials, [S][nx+4][ny+4][nzp] with nzp = nz+4 rounded up to a
+// multiple of 4 floats (TMA strides are multiples of 16 bytes); a brick hanging over the padded extent is clipped by the TMA
+// unit itself (the subset is the tensor's fourth coordinate).  After the inverse transform k_pmeCombinePad writes
 // phi_i = sum_j lambda[slice(i,j)] grid_j straight into the padded layout, halo included.
 //
-// Arithmetic: platforms/reference/src/ReferencePME.cpp:196-256 (index, fraction), :264-317 (B-splines), :320-396 (spreading),
-// :598-702 (interpolation; subset stride nx, see pme.cu).  (GPU behavioural cross-reference:
-// platforms/common/src/kernels/pme.cc:27-135,296-408.)
+// Spreading through bricks was built and measured three ways in round 2 and lost to the per-atom kernel of pme.cu every
+// time: whole-brick bulk tensor reductions (UTMAREDG), shared-memory atomics, and a warp-private brick
+// flushed with red.global.add.v4.f32 -- 256 / 48 / 22 us against 225 / 32 / 15.5 us at STMV / ApoA1 / DHFR size.
+//
+// Arithmetic: platforms/reference/src/ReferencePME.cpp:196-256 (index, fraction), :264-317 (B-splines), :598-702
+// (interpolation; subset stride nx, see pme.cu).  (GPU behavioural cross-reference: platforms/common/src/kernels/pme.cc:296-408.)
 #include "kernels.cuh"
 
 #include <climits>
@@ -35,7 +34,6 @@ template <int BX_, int BY_, int BZ_> struct BrickShape {
     enum { BX = BX_, BY = BY_, BZ = BZ_, FLOATS = BX_*BY_*BZ_, BYTES = FLOATS*4 };
 };
 typedef BrickShape<24, 24, 28> BigBrick;         // 64 512 bytes
-typedef BrickShape<16, 16, 20> SmallBrick;       // 20 480 bytes: grids with a dimension below 20 (24 along z)
 
 namespace {
 
@@ -178,182 +176,6 @@ __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.as
 
 }  // namespace
 
-// ---- spreading ----------------------------------------------------------------------------------------------------
-// One warp (a one-warp CTA) takes 32 consecutive sorted atoms and a PRIVATE 16x16x20 brick: no other warp touches it, so the
-// charges are added with plain shared-memory read-modify-writes -- one atom at a time, lane -> (iy, iz) of the stencil's yz
-// face (25 distinct points), serial over x, a __syncwarp between atoms.  The brick then goes to the grid as vector reductions
-// of the float4 groups that are not zero (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4), wrapped row by row, straight into the
-// dense grid cuFFT reads: ~30 floating-point adds reach the L2 per atom instead of 125.
-//
-// What the measurements ruled out (profiles/README.md, round 2):
-//   * shared-memory float atomics: there is no native instruction (atomicAdd = load / add / ATOMS.CAST.SPIN loop) and shared
-//     atomics of any kind retire ~2 lanes per clock and SM -- a 256-atom CTA on one brick took 388 us (one warp per atom) to
-//     655 us (one thread per atom) at STMV size; 32-bit fixed point (native ATOMS.ADD) was no faster and, with a scale that
-//     provably cannot overflow, too coarse where water's charges cancel;
-//   * adding whole bricks with one bulk tensor reduction (UTMAREDG): the L2 performs ~600 G float additions per second
-//     whoever asks, and a brick is mostly zeros -- 16 128 additions for ~170 atoms (5 120 for 32) against the ~5 500 (1 000)
-//     points they touch.
-#define WB_X 16
-#define WB_Y 16
-#define WB_Z 20
-#define WB_FLOATS (WB_X*WB_Y*WB_Z)
-
-namespace {
-
-// The next set of this warp's atoms that shares one brick: same subset, stencil bases within the brick along every axis.
-// Starts from all pending atoms of the first pending atom's subset and keeps the lower half (in lane = sorted order) until
-// the set fits; a single atom always fits.  ALIGN: the brick starts at a multiple of ALIGN points along z.
-template <int ALIGN>
-__device__ __forceinline__ unsigned nextWarpSet(unsigned pending, int lane, int sub, const int idx[3], int origin[3], int span[3], int& subset) {
-    const unsigned full = 0xffffffffu;
-    subset = __shfl_sync(full, sub, __ffs(pending)-1);
-    unsigned cand = __ballot_sync(full, ((pending>>lane)&1u) && sub == subset);
-    for (;;) {
-        const bool in = (cand>>lane)&1u;
-        bool fits = true;
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const int lo = __reduce_min_sync(full, in ? idx[d] : INT_MAX), hi = __reduce_max_sync(full, in ? idx[d] : INT_MIN);
-            origin[d] = d == 2 ? lo-lo%ALIGN : lo;
-            span[d] = hi-origin[d]+ORDER;
-            fits = fits && span[d] <= (d == 0 ? WB_X : d == 1 ? WB_Y : WB_Z);
-        }
-        const int count = __popc(cand);
-        if (fits || count <= 1)
-            return cand;
-        const int rank = __popc(cand&((1u<<lane)-1u));
-        cand = __ballot_sync(full, in && rank < count/2);
-    }
-}
-
-}  // namespace
-
-// VEC = 4: nz is a multiple of 4, bricks start at multiples of 4 along z, float4 reductions.  VEC = 1: any nz, scalar reductions.
-template <int VEC>
-__global__ void __launch_bounds__(32) k_pmeSpreadWarp(PmeArgs a) {
-    __shared__ __align__(16) float sBrick[WB_FLOATS];
-    __shared__ __align__(16) float sW[32][16];      // q wx[0..4], wy[0..4], wz[0..4], -
-    __shared__ int sCell[32];
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
-    int atom, idx[3], sub;
-    float frac[3], q;
-    const bool valid = threadAtom(a, blockIdx.x*32+lane, atom, idx, frac, q, sub);
-    {
-        float w[16], dth[ORDER];
-        bspline5f(frac[0], w, dth);
-        bspline5f(frac[1], w+5, dth);
-        bspline5f(frac[2], w+10, dth);
-#pragma unroll
-        for (int i = 0; i < ORDER; i++)
-            w[i] *= q;
-        w[15] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            ((float4*) sW[lane])[i] = make_float4(w[4*i], w[4*i+1], w[4*i+2], w[4*i+3]);
-    }
-#pragma unroll
-    for (int k = 0; k < WB_FLOATS/(32*4); k++)
-        ((float4*) sBrick)[k*32+lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int iy = lane < ORDER*ORDER ? lane/ORDER : 0, iz = lane < ORDER*ORDER ? lane-iy*ORDER : 0;
-    const int nx = a.nx, ny = a.ny, nz = a.nz;
-    float* grid = (float*) a.grid;
-    unsigned pending = __ballot_sync(full, valid);
-    while (pending) {
-        int origin[3], span[3], subset;
-        const unsigned set = nextWarpSet<VEC>(pending, lane, sub, idx, origin, span, subset);
-        pending &= ~set;
-        sCell[lane] = ((idx[0]-origin[0])*WB_Y+idx[1]-origin[1])*WB_Z+idx[2]-origin[2];
-        __syncwarp();
-        // ---- one atom at a time (the next atom may touch the same points from other lanes); the NEXT atom's weights and cell
-        // are fetched before the current one's read-modify-writes, so that the two latencies overlap
-        auto fetch = [&](int t, int& cell, float& wyz, float (&wx)[ORDER]) {
-            cell = sCell[t]+iy*WB_Z+iz;
-            wyz = sW[t][5+iy]*sW[t][10+iz];
-            const float4 w03 = *(const float4*) sW[t];
-            wx[0] = w03.x; wx[1] = w03.y; wx[2] = w03.z; wx[3] = w03.w; wx[4] = sW[t][4];
-        };
-        auto add = [&](int cell, float wyz, const float (&wx)[ORDER]) {
-            if (lane < ORDER*ORDER) {
-#pragma unroll
-                for (int ix = 0; ix < ORDER; ix++)
-                    sBrick[cell+ix*WB_Y*WB_Z] += wyz*wx[ix];
-            }
-            __syncwarp();
-        };
-        // (two register sets taking turns: no copies between "this atom" and "the next one")
-        unsigned m = set;
-        int cellA, cellB = 0;
-        float wyzA, wyzB = 0.f, wxA[ORDER], wxB[ORDER] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        fetch(__ffs(m)-1, cellA, wyzA, wxA);
-        m &= m-1u;
-        for (;;) {
-            const bool moreB = m != 0u;
-            if (moreB) {
-                fetch(__ffs(m)-1, cellB, wyzB, wxB);
-                m &= m-1u;
-            }
-            add(cellA, wyzA, wxA);
-            if (!moreB)
-                break;
-            const bool moreA = m != 0u;
-            if (moreA) {
-                fetch(__ffs(m)-1, cellA, wyzA, wxA);
-                m &= m-1u;
-            }
-            add(cellB, wyzB, wxB);
-            if (!moreA)
-                break;
-        }
-        // ---- flush the touched box [0, span) of the brick into the grid (periodic wrap per row), and clear it.  A lane keeps
-        // the same (y, group) columns of the box for every x plane (at most 16 x 5 = 80 float4 columns: three per lane), so the
-        // column's decoding, wrapping and addresses are computed once and the walk over x is five instructions per group
-        const int gz = (span[2]+VEC-1)/VEC;                 // groups of VEC points per row
-        const int perPlane = span[1]*gz;
-        const unsigned invGz = (1u<<20)/(unsigned) gz+1u;   // r*inv >> 20 = r/gz exactly for r < 2^20/gz
-        float* base = grid+(size_t) subset*nx*ny*nz;
-        constexpr int NCOL = VEC == 4 ? 3 : 10;             // 16 x 5 float4 columns, or 16 x 20 scalar ones, over 32 lanes
-        int colS[NCOL], colG[NCOL];                         // shared-memory and grid offsets of this lane's columns (-1: none)
-#pragma unroll
-        for (int c = 0; c < NCOL; c++) {
-            const int r = lane+32*c;
-            const int y = (int) (((unsigned) r*invGz)>>20), g = r-y*gz;
-            int Y = origin[1]+y, Z = origin[2]+g*VEC;
-            Y -= Y >= ny ? ny : 0;
-            Z -= Z >= nz ? nz : 0;
-            colS[c] = r < perPlane ? y*WB_Z+g*VEC : -1;
-            colG[c] = Y*nz+Z;
-        }
-        for (int x = 0; x < span[0]; x++) {
-            int X = origin[0]+x;
-            X -= X >= nx ? nx : 0;
-            float* plane = base+(size_t) X*ny*nz;
-            float* sp = sBrick+x*WB_Y*WB_Z;
-#pragma unroll
-            for (int c = 0; c < NCOL; c++)
-                if (colS[c] >= 0) {
-                    float* p = sp+colS[c];
-                    float* dst = plane+colG[c];
-                    if (VEC == 4) {
-                        const float4 v = *(const float4*) p;
-                        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-                            *(float4*) p = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-                    else {
-                        const float v = *p;
-                        if (v != 0.f) {
-                            atomicAdd(dst, v);
-                            *p = 0.f;
-                        }
-                    }
-                }
-        }
-        __syncwarp();
-    }
-}
-
 #define ROWS_PER_CTA 8
 // ---- potentials seen by each subset, written into the padded layout (halo = periodic images) -------------------------
 // One warp per padded row (x, y), all subsets: phi_k = sum_j lambda[slice(k,j)] grid_j.  VEC = 4 (nz a multiple of 4, hence
@@ -494,15 +316,8 @@ __global__ void __launch_bounds__(32*MAX_WARPS) k_pmeInterpBrick(PmeArgs a, cons
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-// Which brick an interpolation takes.  The big one (128 / 256 atoms per CTA) needs a padded grid at least one brick long along
-// every axis, and enough atoms to fill the GPU with such CTAs: below that the kernel is one wave of CTAs whose length is a
-// chain of latencies (gather, vote, 64 KB bulk load, 125 points), and 64-atom CTAs on 20 KB bricks finish it sooner.
-static bool bigBrick(int numAtoms, int nx, int ny, int nzp) {
-    static const bool forceSmall = getenv("SNB_PME_SMALL_BRICK") != nullptr;    // A/B measurements
-    return !forceSmall && numAtoms >= 148*2*256 && nx+4 >= BigBrick::BX && ny+4 >= BigBrick::BY && nzp >= BigBrick::BZ;
-}
-
 bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numAtoms, int numSubsets, int nx, int ny, int nzp) {
+    (void) numAtoms;
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeTiled encode = nullptr;
@@ -515,36 +330,16 @@ bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numAtoms, int numS
         }
         encode = (EncodeTiled) fn;
     }
-    if (nx+4 < SmallBrick::BX || ny+4 < SmallBrick::BY || nzp < SmallBrick::BZ)
+    // the padded grid is at least one brick long along every axis
+    if (nx+4 < BigBrick::BX || ny+4 < BigBrick::BY || nzp < BigBrick::BZ)
         return false;
-    const bool big = bigBrick(numAtoms, nx, ny, nzp);
     // innermost first: z (row), y, x, subset
     const cuuint64_t dims[4] = {(cuuint64_t) nzp, (cuuint64_t) (ny+4), (cuuint64_t) (nx+4), (cuuint64_t) numSubsets};
     const cuuint64_t strides[3] = {(cuuint64_t) nzp*4, (cuuint64_t) nzp*4*(ny+4), (cuuint64_t) nzp*4*(ny+4)*(nx+4)};
-    const cuuint32_t boxBig[4] = {BigBrick::BZ, BigBrick::BY, BigBrick::BX, 1}, boxSmall[4] = {SmallBrick::BZ, SmallBrick::BY, SmallBrick::BX, 1};
+    const cuuint32_t box[4] = {BigBrick::BZ, BigBrick::BY, BigBrick::BX, 1};
     const cuuint32_t elem[4] = {1, 1, 1, 1};
-    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gridPad, dims, strides, big ? boxBig : boxSmall, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gridPad, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// atoms per CTA: 256 with the big brick, 64 with the small one (its stencil bases span 12 cells)
-static int brickThreads(bool big) { return big ? 256 : 64; }
-
-template <typename K> static cudaError_t allowSharedMemory(K kernel, size_t bytes) {
-    return bytes > 48*1024 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes) : cudaSuccess;
-}
-
-cudaError_t launchPmeSpreadBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream) {
-    (void) map;
-    const cudaError_t err = cudaMemsetAsync(a.grid, 0, sizeof(float)*(size_t) a.numSubsets*a.nx*a.ny*a.nz, stream);
-    if (err != cudaSuccess)
-        return err;
-    const int blocks = (a.numAtoms+31)/32;
-    if (a.nz%4 == 0)
-        k_pmeSpreadWarp<4><<<blocks, 32, 0, stream>>>(a);
-    else
-        k_pmeSpreadWarp<1><<<blocks, 32, 0, stream>>>(a);
-    return cudaSuccess;
 }
 
 cudaError_t launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, cudaStream_t stream) {
@@ -555,15 +350,10 @@ cudaError_t launchPmeInterpolateBrick(const PmeArgs& a, const CUtensorMap& map, 
     else if (vec && a.numSubsets == 2) k_pmeCombinePad<2, 4><<<cgrid, cblock, 0, stream>>>(a);
     else if (vec && a.numSubsets <= 4) k_pmeCombinePad<4, 4><<<cgrid, cblock, 0, stream>>>(a);
     else k_pmeCombinePad<0, 1><<<cgrid, cblock, 0, stream>>>(a);
-    const bool big = bigBrick(a.numAtoms, a.nx, a.ny, a.nzp);
-    const int threads = brickThreads(big), blocks = (a.numAtoms+threads-1)/threads;
-    if (big) {
-        const cudaError_t err = allowSharedMemory(k_pmeInterpBrick<BigBrick>, BigBrick::BYTES);
-        if (err != cudaSuccess)
-            return err;
-        k_pmeInterpBrick<BigBrick><<<blocks, threads, BigBrick::BYTES, stream>>>(a, map);
-    }
-    else
-        k_pmeInterpBrick<SmallBrick><<<blocks, threads, SmallBrick::BYTES, stream>>>(a, map);
+    const int threads = 32*MAX_WARPS, blocks = (a.numAtoms+threads-1)/threads;
+    const cudaError_t err = cudaFuncSetAttribute(k_pmeInterpBrick<BigBrick>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BigBrick::BYTES);
+    if (err != cudaSuccess)
+        return err;
+    k_pmeInterpBrick<BigBrick><<<blocks, threads, BigBrick::BYTES, stream>>>(a, map);
     return cudaSuccess;
 }

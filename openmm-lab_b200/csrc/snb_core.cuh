@@ -28,6 +28,7 @@
 #define SNB_FORCE_SCALE 4294967296.0f       /* 2^32, as the reference's fixed-point forces (realToFixedPoint.cu:1-2) */
 #define SNB_FORCE_SCALE_D 4294967296.0
 #define SNB_NARROW_MAX_EXTENT 1.0f         /* nm: largest block half extent for which the narrow cutoff band is valid */
+#define SNB_COUNTER_REBUILD 6               /* counters[]: nonzero = this evaluation rebuilds the sorted order and the tile list (list reuse on) */
 #define SNB_COUNTER_MAX_EXTENT 5            /* counters[]: float bits of the largest block half extent of this evaluation */
 
 enum { PBC_NONE = 0, PBC_SHIFT = 1, PBC_PAIR_ORTHO = 2, PBC_PAIR_TRICLINIC = 3 };
@@ -82,6 +83,10 @@ struct StepParams {
     BoxF box;
     float shiftLimit[3];                // halfBox - cutoff per axis (one-image-per-j-atom shortcut)
     double lambdaC[SNB_MAX_SLICES], lambdaV[SNB_MAX_SLICES];
+    // tile-list reuse (ListSkin > 0): squared displacement since the last build beyond which the list is rebuilt, and the
+    // host's own reasons for a rebuild (first evaluation, box / capacity / partition / parameters changed)
+    double skinHalf2;
+    int forceRebuild;
 };
 
 // ---- small device helpers ---------------------------------------------------------

@@ -8,15 +8,38 @@
 #include "snb_core.cuh"
 #include "kernels.cuh"
 
+// ---- 0. tile-list reuse (platform property ListSkin > 0) ---------------------------------------------
+// The list of the last rebuild was built with cutoff + skin, so it holds every pair that is within the cutoff now as long
+// as no atom has moved more than skin/2 since (the exact predicate of the direct-space kernel still decides the pair set
+// every evaluation, so the results do not depend on when the list was built).  k_listCheck raises the rebuild flag when
+// an atom has moved farther, or the host asked (first evaluation, box / capacity / partition change); without the flag the
+// sort and list kernels return at once and k_blockBounds refreshes the boxes and local coordinates of the kept order.
+// (OpenMM's CUDA platform, which the reference inherits its neighbour list from, reuses a padded list the same way.)
+__device__ __forceinline__ bool keepList(const SortArgs& a) { return a.reuse && a.counters[SNB_COUNTER_REBUILD] == 0; }
+
+__global__ void k_listCheck(SortArgs a) {
+    const int i = blockIdx.x*blockDim.x+threadIdx.x;
+    bool moved = i == 0 && a.sp->forceRebuild != 0;
+    if (i < a.numAtoms) {
+        const double dx = a.posd[3*i]-a.posRef[3*i], dy = a.posd[3*i+1]-a.posRef[3*i+1], dz = a.posd[3*i+2]-a.posRef[3*i+2];
+        moved = moved || !(dx*dx+dy*dy+dz*dz <= a.sp->skinHalf2);      // (a NaN position rebuilds, too)
+    }
+    if (__any_sync(0xffffffffu, moved) && (threadIdx.x&31) == 0)
+        a.counters[SNB_COUNTER_REBUILD] = 1;
+}
+
 // ---- 1. cell assignment -------------------------------------------------------------
 // One thread per atom.  cellRank[] maps a linear cell index to its position along the Hilbert
 // curve (host-built table).  The slot within the cell comes from an atomic counter; the
 // within-cell order is made deterministic afterwards by sortCells.
 __global__ void k_assignCells(SortArgs a) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
-    if (i >= a.numAtoms)
+    if (i >= a.numAtoms || keepList(a))
         return;
     double x = a.posd[3*i], y = a.posd[3*i+1], z = a.posd[3*i+2];
+    if (a.reuse) {
+        a.posRef[3*i] = x; a.posRef[3*i+1] = y; a.posRef[3*i+2] = z;
+    }
     int c[3];
     if (a.periodic) {
         // fractional coordinates, frac = pos * recip (lower triangular)
@@ -46,7 +69,9 @@ __global__ void k_assignCells(SortArgs a) {
 
 // bounding box of all atoms (non-periodic methods): extent[0..2] = min, [3..5] = max.
 // Ordered-int trick on doubles is avoided: two-stage reduction with one block.
-__global__ void k_extent(const double* posd, int numAtoms, double* extent) {
+__global__ void k_extent(const double* posd, int numAtoms, double* extent, const int* keep) {
+    if (keep && *keep == 0)
+        return;
     __shared__ double smin[3][256], smax[3][256];
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int i = threadIdx.x; i < numAtoms; i += blockDim.x)
@@ -100,7 +125,10 @@ __device__ __forceinline__ int blockExclusiveScan(int v, int* warpSums, int& tot
     return (warp > 0 ? warpSums[warp-1] : 0)+incl-v;
 }
 
-__global__ void __launch_bounds__(1024) k_scanCells(const int* __restrict__ count, int* __restrict__ start, int numCells) {
+// keep: null, or the rebuild flag of a handle with list reuse on (0 = nothing to do)
+__global__ void __launch_bounds__(1024) k_scanCells(const int* __restrict__ count, int* __restrict__ start, int numCells, const int* keep) {
+    if (keep && *keep == 0)
+        return;
     __shared__ int warpSums[32];
     const int per = (numCells+blockDim.x-1)/blockDim.x;
     const int first = min(numCells, (int) threadIdx.x*per), last = min(numCells, first+per);
@@ -117,7 +145,9 @@ __global__ void __launch_bounds__(1024) k_scanCells(const int* __restrict__ coun
         start[numCells] = total;
 }
 
-__global__ void __launch_bounds__(SCAN_TILE) k_scanTileSums(const int* __restrict__ count, int* __restrict__ tileSum, int numCells) {
+__global__ void __launch_bounds__(SCAN_TILE) k_scanTileSums(const int* __restrict__ count, int* __restrict__ tileSum, int numCells, const int* keep) {
+    if (keep && *keep == 0)
+        return;
     __shared__ int warpSums[32];
     const int i = blockIdx.x*SCAN_TILE+threadIdx.x;
     int total;
@@ -126,7 +156,9 @@ __global__ void __launch_bounds__(SCAN_TILE) k_scanTileSums(const int* __restric
         tileSum[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) k_scanTileOffsets(int* __restrict__ tileSum, int numTiles, int* __restrict__ start, int numCells) {
+__global__ void __launch_bounds__(1024) k_scanTileOffsets(int* __restrict__ tileSum, int numTiles, int* __restrict__ start, int numCells, const int* keep) {
+    if (keep && *keep == 0)
+        return;
     // exclusive scan of the tile sums in place (numTiles can exceed the block: carried loop)
     __shared__ int warpSums[32];
     int carry = 0;
@@ -144,7 +176,9 @@ __global__ void __launch_bounds__(1024) k_scanTileOffsets(int* __restrict__ tile
         start[numCells] = carry;
 }
 
-__global__ void __launch_bounds__(SCAN_TILE) k_scanTiles(const int* __restrict__ count, const int* __restrict__ tileOffset, int* __restrict__ start, int numCells) {
+__global__ void __launch_bounds__(SCAN_TILE) k_scanTiles(const int* __restrict__ count, const int* __restrict__ tileOffset, int* __restrict__ start, int numCells, const int* keep) {
+    if (keep && *keep == 0)
+        return;
     __shared__ int warpSums[32];
     const int i = blockIdx.x*SCAN_TILE+threadIdx.x;
     int total;
@@ -159,6 +193,8 @@ __global__ void __launch_bounds__(SCAN_TILE) k_scanTiles(const int* __restrict__
 // atoms of the same cell with a smaller index, so the sorted order is a function of the positions only.
 __global__ void k_scatterAtoms(SortArgs a) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (keepList(a))
+        return;
     if (i < a.numAtoms)
         a.cellScratch[a.cellStart[a.atomCell[i]]+a.atomSlot[i]] = i;
     // sorted range of every cell, addressed by its linear index (the tile-list build walks cells)
@@ -175,7 +211,7 @@ __global__ void k_scatterAtoms(SortArgs a) {
 
 __global__ void k_rankInCell(SortArgs a) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
-    if (i >= a.numAtoms)
+    if (i >= a.numAtoms || keepList(a))
         return;
     const int c = a.atomCell[i], s = a.cellStart[c], e = a.cellStart[c+1];
     int rank = 0;
@@ -200,9 +236,20 @@ __global__ void k_blockBounds(SortArgs a) {
     if (atom >= 0) {
         p[0] = a.posd[3*atom]; p[1] = a.posd[3*atom+1]; p[2] = a.posd[3*atom+2];
         if (a.periodic) {
-            double fz = floor(p[2]*a.sp->exact.boxd.recip[2][2]);
-            double fy = floor(p[1]*a.sp->exact.boxd.recip[1][1]+p[2]*a.sp->exact.boxd.recip[2][1]);
-            double fx = floor(p[0]*a.sp->exact.boxd.recip[0][0]+p[1]*a.sp->exact.boxd.recip[1][0]+p[2]*a.sp->exact.boxd.recip[2][0]);
+            double fz, fy, fx;
+            if (keepList(a)) {
+                // the kept order was cut from atoms wrapped by THESE box vectors: an atom that has crossed a face of the unit
+                // cell since stays with its block (a fresh floor would send it to the opposite face)
+                const float4 w = a.wrapImage[atom];
+                fx = w.x; fy = w.y; fz = w.z;
+            }
+            else {
+                fz = floor(p[2]*a.sp->exact.boxd.recip[2][2]);
+                fy = floor(p[1]*a.sp->exact.boxd.recip[1][1]+p[2]*a.sp->exact.boxd.recip[2][1]);
+                fx = floor(p[0]*a.sp->exact.boxd.recip[0][0]+p[1]*a.sp->exact.boxd.recip[1][0]+p[2]*a.sp->exact.boxd.recip[2][0]);
+                if (a.reuse)
+                    a.wrapImage[atom] = make_float4((float) fx, (float) fy, (float) fz, 0.f);
+            }
             p[0] -= fx*a.sp->exact.boxd.ax+fy*a.sp->exact.boxd.bx+fz*a.sp->exact.boxd.cx;
             p[1] -= fy*a.sp->exact.boxd.by+fz*a.sp->exact.boxd.cy;
             p[2] -= fz*a.sp->exact.boxd.cz;
@@ -283,16 +330,19 @@ __global__ void k_blockBounds(SortArgs a) {
 void launchSort(const SortArgs& a, cudaStream_t stream) {
     int threads = 256;
     int atomBlocks = (a.paddedAtoms+threads-1)/threads;
+    const int* keep = a.reuse ? a.counters+SNB_COUNTER_REBUILD : nullptr;
+    if (a.reuse)
+        k_listCheck<<<atomBlocks, threads, 0, stream>>>(a);
     if (!a.periodic)
-        k_extent<<<1, 256, 0, stream>>>(a.posd, a.numAtoms, a.extent);
+        k_extent<<<1, 256, 0, stream>>>(a.posd, a.numAtoms, a.extent, keep);
     k_assignCells<<<atomBlocks, threads, 0, stream>>>(a);
     if (a.numCells <= SCAN_SINGLE)
-        k_scanCells<<<1, 1024, 0, stream>>>(a.cellCount, a.cellStart, a.numCells);
+        k_scanCells<<<1, 1024, 0, stream>>>(a.cellCount, a.cellStart, a.numCells, keep);
     else {
         const int tiles = (a.numCells+SCAN_TILE-1)/SCAN_TILE;
-        k_scanTileSums<<<tiles, SCAN_TILE, 0, stream>>>(a.cellCount, a.tileSum, a.numCells);
-        k_scanTileOffsets<<<1, 1024, 0, stream>>>(a.tileSum, tiles, a.cellStart, a.numCells);
-        k_scanTiles<<<tiles, SCAN_TILE, 0, stream>>>(a.cellCount, a.tileSum, a.cellStart, a.numCells);
+        k_scanTileSums<<<tiles, SCAN_TILE, 0, stream>>>(a.cellCount, a.tileSum, a.numCells, keep);
+        k_scanTileOffsets<<<1, 1024, 0, stream>>>(a.tileSum, tiles, a.cellStart, a.numCells, keep);
+        k_scanTiles<<<tiles, SCAN_TILE, 0, stream>>>(a.cellCount, a.tileSum, a.cellStart, a.numCells, keep);
     }
     k_scatterAtoms<<<(max(a.paddedAtoms, a.numCells)+threads-1)/threads, threads, 0, stream>>>(a);
     k_rankInCell<<<atomBlocks, threads, 0, stream>>>(a);

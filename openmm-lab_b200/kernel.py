@@ -150,11 +150,24 @@ def load_library():
 class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
     """The sm_100a implementation, registered on platform "B200" (platform.py)."""
 
-    def __init__(self, device_index=0, precision="mixed", deterministic=False, direct_kernel="auto"):
+    def __init__(self, device_index=0, precision="mixed", deterministic=False, direct_kernel="auto", list_skin=0.0):
+        self.listSkin = float(list_skin)
         flags = (_abi.FLAG_DOUBLE_PRECISION if precision == "double" else 0) | (_abi.FLAG_DETERMINISTIC if deterministic else 0) | \
                 {"auto": 0, "packed": _abi.FLAG_DIRECT_PACKED, "general": _abi.FLAG_DIRECT_GENERAL}[direct_kernel]
         super().__init__(load_library(), "snb_", device_index, flags)
         self.precision = precision
+
+    def initialize(self, system, force):
+        super().initialize(system, force)
+        if self.listSkin > 0:
+            self.setListSkin(self.listSkin)
+
+    def setListSkin(self, skin_nm):
+        """Tile-list reuse (snb_set_list_skin): list built with cutoff + skin, kept until an atom has moved skin/2; 0 = off."""
+        fn = self._lib.snb_set_list_skin
+        fn.argtypes = [C.c_void_p, C.c_double]
+        self._check(fn(self._handle, float(skin_nm)))
+        self.listSkin = float(skin_nm)
 
     def executeDevice(self, posq_ptr, box, params, flags, forces_ptr):
         fn = self._lib.snb_execute_device

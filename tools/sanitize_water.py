@@ -19,7 +19,7 @@ def main():
     from openmmlab_b200 import systems
     for method in (F.PME, F.CutoffPeriodic):
         w = systems.water_box(method=method)
-        for props in ({}, {"DirectKernel": "packed"}, {"Precision": "double"}, {"DeterministicForces": "true"}):
+        for props in ({}, {"DirectKernel": "packed"}, {"Precision": "double"}, {"DeterministicForces": "true"}, {"ListSkin": "0.02"}):
             ctx = mm.Context(w.system, "B200", props)
             ctx.setPositions(w.positions)
             for k, v in w.parameters.items():
