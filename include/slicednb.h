@@ -171,6 +171,28 @@ int snb_execute_device(snb_handle* h, const void* posq_dev, const double* box,
 int snb_read_energies(snb_handle* h, int flags, double* energy, double* slice_energies,
                       double* derivatives);
 
+/* The same, in the layout OpenMM's CUDA platform keeps its atoms in -- what a zero-copy binding to that platform hands over
+ * (the reference: platforms/cuda/src/CudaOpenMMLabKernels.cpp:736-758 registers posq / parameters with
+ * CudaNonbondedUtilities; force-buffer layout platforms/common/src/kernels/pme.cc:399-405).  Atoms sit in the platform's
+ * REORDERED order, padded to a multiple of 32:
+ *   posq             [padded] float4 (x, y, z, q), or double4 when positions_double (platform in double precision)
+ *   posq_correction  [padded] float4 added to posq (platform in mixed precision), or NULL
+ *   atom_index       [N] original index of the atom in slot i (CudaContext::getAtomIndexArray), or NULL = original order
+ *   forces           [3][padded] long long, 2^32 fixed point: force[c*padded + slot]; ADDED to; may be NULL
+ * All pointers are device pointers on the handle's device.  plugin/src/B200CudaOpenMMLabKernels.cpp is the binding. */
+typedef struct snb_device_layout {
+    int32_t struct_size;            /* = sizeof(snb_device_layout) */
+    int32_t padded_num_atoms;
+    int32_t positions_double;
+    int32_t reserved;
+    const void* posq;
+    const void* posq_correction;
+    const int32_t* atom_index;
+    void* forces;
+} snb_device_layout;
+int snb_execute_device_ordered(snb_handle* h, const snb_device_layout* layout, const double* box,
+                               const double* global_parameters, int flags);
+
 int snb_get_pme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz);
 int snb_get_ljpme_parameters(const snb_handle* h, double* alpha, int* nx, int* ny, int* nz);
 

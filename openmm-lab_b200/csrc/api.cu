@@ -180,6 +180,8 @@ struct GraphKey {
     int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast;
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
+    const void *posqCorrection, *atomIndex;     // snb_execute_device_ordered: the caller's atom order
+    long long outStride, positionsDouble;
     double share, listSkin;
 };
 
@@ -276,6 +278,10 @@ struct snb_handle {
     PinnedBuf<double> loadH;            // this rank's measured times of the previous evaluation, sent with the all-reduce
     bool loadValid = false, autoBalance = true;
     double tunedShare = -1;
+    // ---- snb_execute_device_ordered: the caller's layout for the evaluation in progress (all null / 0 otherwise) ----
+    const void* ordCorrection = nullptr;
+    const int* ordAtomIndex = nullptr;
+    int ordStride = 0, ordDouble = 0;
     // ---- results of the last execute ----
     std::vector<double> sliceEnergies;
     double lastEnergy = 0;
@@ -953,7 +959,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             CUDA_CHECK(cudaMemcpyAsync(h.posd.p, in.hostPos, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
     }
     else if (!receivePositions)
-        launchConvertPositions((const float4*) in.posqDev, h.posd.p, h.N, st);
+        launchConvertPositions(in.posqDev, h.ordCorrection, h.ordAtomIndex, h.ordDouble, h.posd.p, h.N, st);
     if (nccl && h.broadcastPositions)
         NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, st));
     CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
@@ -1145,6 +1151,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     fa.sortedPos = includeDirect ? h.sortedPos.p : nullptr;
     fa.forceSorted = h.forceSorted.p; fa.forceOrig = h.forceOrig.p;
     fa.counters = h.counters.p;
+    fa.outIndex = h.ordAtomIndex; fa.outStride = h.ordStride ? h.ordStride : h.N;
     if (nccl) {
         // Direct space + exceptions of every rank -> rank 0: ncclReduce(sum, int64) of the [3][N] fixed-point forces, grouped
         // with a small all-reduce of the slice-energy table, the list-overflow flag (every rank must take the same retry
@@ -1168,7 +1175,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
         if (includeForces && root)
             launchEmitReduced(h.reduceRecv.p, h.N, h.NP, splitRecip ? h.forcePme.p : nullptr, in.hostPositions ? h.forcesOutD.p : nullptr,
-                              (long long*) in.forcesFixedOut, h.reduceRecv.p+nf+32*2*SNB_MAX_SLICES, st);
+                              (long long*) in.forcesFixedOut, h.ordAtomIndex, h.ordStride ? h.ordStride : h.N, h.reduceRecv.p+nf+32*2*SNB_MAX_SLICES, st);
     }
     else {
         if (doRecip && !h.timing)
@@ -1235,6 +1242,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     key.listSkin = h.skinNow;
     key.broadcast = h.comm && h.broadcastPositions;
     key.posqDev = posqDev; key.forcesFixedOut = forcesFixedOut; key.jList = h.jList.p; key.hostPos = hostPos;
+    key.posqCorrection = h.ordCorrection; key.atomIndex = h.ordAtomIndex; key.outStride = h.ordStride; key.positionsDouble = h.ordDouble;
     const bool graphable = h.useGraph && !h.timing && (!h.comm || h.balanceFrozen);
     const bool sameKey = h.graphKeyValid && memcmp(&key, &h.graphKey, sizeof(key)) == 0;
     if (!graphable || !sameKey)
@@ -1527,6 +1535,24 @@ int snb_execute_device(snb_handle* h, const void* posq_dev, const double* box, c
     SNB_TRY
     if (!posq_dev) throw SnbException(SNB_ERR_INVALID, "positions are null");
     evaluate(*h, nullptr, posq_dev, box, globals, flags, forces_dev);
+    return SNB_OK;
+    SNB_CATCH
+}
+
+int snb_execute_device_ordered(snb_handle* h, const snb_device_layout* layout, const double* box, const double* globals, int flags) {
+    SNB_TRY
+    if (!layout || layout->struct_size != (int32_t) sizeof(snb_device_layout)) throw SnbException(SNB_ERR_INVALID, "snb_device_layout.struct_size does not match this library");
+    if (!layout->posq) throw SnbException(SNB_ERR_INVALID, "positions are null");
+    if (layout->padded_num_atoms < h->N) throw SnbException(SNB_ERR_INVALID, "padded_num_atoms is smaller than the number of particles");
+    struct Scope {      // the layout applies to this evaluation only, whatever way it ends
+        snb_handle* h;
+        ~Scope() { h->ordCorrection = nullptr; h->ordAtomIndex = nullptr; h->ordStride = 0; h->ordDouble = 0; }
+    } scope{h};
+    h->ordCorrection = layout->positions_double ? nullptr : layout->posq_correction;
+    h->ordAtomIndex = layout->atom_index;
+    h->ordStride = layout->padded_num_atoms;
+    h->ordDouble = layout->positions_double ? 1 : 0;
+    evaluate(*h, nullptr, layout->posq, box, globals, flags, layout->forces);
     return SNB_OK;
     SNB_CATCH
 }

@@ -11,6 +11,10 @@ __global__ void k_finish(FinishArgs a) {
     }
     if (i >= a.numAtoms)
         return;
+    // thread t serves the atom of the caller's slot t (original order unless the caller handed its own)
+    const int t = i;
+    if (a.outIndex)
+        i = a.outIndex[t];
     const int k = a.sortedPos ? a.sortedPos[i] : i;
     // a pass whose tile list overflowed is discarded and repeated by the host: it must leave the caller's accumulator alone
     const bool discard = a.counters[2] != 0;
@@ -19,16 +23,20 @@ __global__ void k_finish(FinishArgs a) {
         if (a.forcesOut)
             a.forcesOut[3*i+c] = (double) f*(1.0/SNB_FORCE_SCALE_D);
         if (a.forcesFixedOut && !discard)
-            a.forcesFixedOut[(size_t) c*a.numAtoms+i] += f;
+            a.forcesFixedOut[(size_t) c*a.outStride+t] += f;
         if (a.reduceOut)
             a.reduceOut[(size_t) c*a.numAtoms+i] = f;
     }
 }
 
-__global__ void k_emitReduced(const long long* reduced, int numAtoms, int paddedAtoms, const long long* extra, double* forcesOut, long long* forcesFixedOut, const long long* overflow) {
+__global__ void k_emitReduced(const long long* reduced, int numAtoms, int paddedAtoms, const long long* extra, double* forcesOut, long long* forcesFixedOut,
+                              const int* outIndex, int outStride, const long long* overflow) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
     if (i >= numAtoms)
         return;
+    const int t = i;
+    if (outIndex)
+        i = outIndex[t];
     // some rank's tile list overflowed: every rank repeats the evaluation, nothing of this pass may reach the caller's accumulator
     const bool discard = overflow && *overflow != 0;
     for (int c = 0; c < 3; c++) {
@@ -37,16 +45,29 @@ __global__ void k_emitReduced(const long long* reduced, int numAtoms, int padded
         if (forcesOut)
             forcesOut[3*i+c] = (double) f*(1.0/SNB_FORCE_SCALE_D);
         if (forcesFixedOut && !discard)
-            forcesFixedOut[(size_t) c*numAtoms+i] += f;
+            forcesFixedOut[(size_t) c*outStride+t] += f;
     }
 }
 
-__global__ void k_convertPositions(const float4* posq, double* posd, int numAtoms) {
-    int i = blockIdx.x*blockDim.x+threadIdx.x;
-    if (i >= numAtoms)
+__global__ void k_convertPositions(const void* posq, const float4* correction, const int* atomIndex, int positionsDouble, double* posd, int numAtoms) {
+    int t = blockIdx.x*blockDim.x+threadIdx.x;
+    if (t >= numAtoms)
         return;
-    float4 p = posq[i];
-    posd[3*i] = p.x; posd[3*i+1] = p.y; posd[3*i+2] = p.z;
+    double x, y, z;
+    if (positionsDouble) {
+        const double4 p = ((const double4*) posq)[t];
+        x = p.x; y = p.y; z = p.z;
+    }
+    else {
+        const float4 p = ((const float4*) posq)[t];
+        x = p.x; y = p.y; z = p.z;
+        if (correction) {
+            const float4 c = correction[t];
+            x += (double) c.x; y += (double) c.y; z += (double) c.z;
+        }
+    }
+    const int i = atomIndex ? atomIndex[t] : t;
+    posd[3*i] = x; posd[3*i+1] = y; posd[3*i+2] = z;
 }
 
 void launchFinish(const FinishArgs& a, cudaStream_t stream) {
@@ -56,12 +77,12 @@ void launchFinish(const FinishArgs& a, cudaStream_t stream) {
 }
 
 void launchEmitReduced(const long long* reduced, int numAtoms, int paddedAtoms, const long long* extra, double* forcesOut, long long* forcesFixedOut,
-                       const long long* overflow, cudaStream_t stream) {
+                       const int* outIndex, int outStride, const long long* overflow, cudaStream_t stream) {
     if (numAtoms > 0)
-        k_emitReduced<<<(numAtoms+255)/256, 256, 0, stream>>>(reduced, numAtoms, paddedAtoms, extra, forcesOut, forcesFixedOut, overflow);
+        k_emitReduced<<<(numAtoms+255)/256, 256, 0, stream>>>(reduced, numAtoms, paddedAtoms, extra, forcesOut, forcesFixedOut, outIndex, outStride, overflow);
 }
 
-void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream) {
+void launchConvertPositions(const void* posq, const void* correction, const int* atomIndex, int positionsDouble, double* posd, int numAtoms, cudaStream_t stream) {
     if (numAtoms > 0)
-        k_convertPositions<<<(numAtoms+255)/256, 256, 0, stream>>>(posq, posd, numAtoms);
+        k_convertPositions<<<(numAtoms+255)/256, 256, 0, stream>>>(posq, (const float4*) correction, atomIndex, positionsDouble, posd, numAtoms);
 }

@@ -189,7 +189,9 @@ struct FinishArgs {
     const long long* forceSorted;
     const long long* forceOrig;
     double* forcesOut;              // [N][3] host-visible staging (device), or null
-    long long* forcesFixedOut;      // [3][N] added to, or null
+    long long* forcesFixedOut;      // [3][outStride] added to, or null
+    const int* outIndex;            // null: forcesFixedOut is in original atom order; else slot t holds atom outIndex[t] (the caller's order)
+    int outStride;                  // component stride of forcesFixedOut (numAtoms, or the caller's padded atom count)
     long long* reduceOut;           // [3][N] overwritten: this rank's contribution to the NCCL force reduction, or null
     const int* counters;            // list-build counters; [2] = overflow flag
     const double* energyIn;         // multi-GPU: the slice-energy table + flags, appended to reduceOut in 2^32 fixed point
@@ -199,8 +201,11 @@ struct FinishArgs {
 // overflow: the reduced list-overflow flag (device pointer, nonzero = the pass is being discarded) or null
 // extra: forces to add on top of the reduced ones ([3][paddedAtoms], original order), or null
 void launchEmitReduced(const long long* reduced, int numAtoms, int paddedAtoms, const long long* extra, double* forcesOut, long long* forcesFixedOut,
-                       const long long* overflow, cudaStream_t stream);
+                       const int* outIndex, int outStride, const long long* overflow, cudaStream_t stream);
 void launchFinish(const FinishArgs& a, cudaStream_t stream);
-void launchConvertPositions(const float4* posq, double* posd, int numAtoms, cudaStream_t stream);
+// device positions -> the double array in original atom order.  posq: float4 (or double4 when positionsDouble) per slot;
+// correction: float4 per slot added to a float4 position (OpenMM's mixed precision), or null; atomIndex: original index of
+// the atom in every slot, or null when the slots are in original order
+void launchConvertPositions(const void* posq, const void* correction, const int* atomIndex, int positionsDouble, double* posd, int numAtoms, cudaStream_t stream);
 
 #endif

@@ -176,6 +176,20 @@ class B200CalcSlicedNonbondedForceKernel(CalcSlicedNonbondedForceKernel):
         params = np.ascontiguousarray(params, dtype=np.float64)
         self._check(fn(self._handle, posq_ptr, box.ctypes.data_as(_dp), params.ctypes.data_as(_dp), flags, forces_ptr))
 
+    def executeDeviceOrdered(self, posq_ptr, box, params, flags, forces_ptr, padded_num_atoms, atom_index_ptr=None,
+                             posq_correction_ptr=None, positions_double=False):
+        """snb_execute_device_ordered: positions / forces in the caller's own (reordered, padded) atom order, as OpenMM's CUDA
+        platform keeps them (include/slicednb.h, snb_device_layout)."""
+        class Layout(C.Structure):
+            _fields_ = [("struct_size", C.c_int32), ("padded_num_atoms", C.c_int32), ("positions_double", C.c_int32), ("reserved", C.c_int32),
+                        ("posq", C.c_void_p), ("posq_correction", C.c_void_p), ("atom_index", C.c_void_p), ("forces", C.c_void_p)]
+        layout = Layout(C.sizeof(Layout), int(padded_num_atoms), int(bool(positions_double)), 0, posq_ptr, posq_correction_ptr, atom_index_ptr, forces_ptr)
+        fn = self._lib.snb_execute_device_ordered
+        fn.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, C.c_int]
+        box = np.ascontiguousarray(box, dtype=np.float64).reshape(9)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(fn(self._handle, C.byref(layout), box.ctypes.data_as(_dp), params.ctypes.data_as(_dp), flags))
+
     def readEnergies(self, flags):
         fn = self._lib.snb_read_energies
         fn.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), _dp, _dp]

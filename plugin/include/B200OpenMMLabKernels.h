@@ -36,7 +36,7 @@ public:
     /* OpenMMLabKernels.h:77,86 ; ReferenceOpenMMLabKernels.cpp:314-330 */
     void getPMEParameters(double& alpha, int& nx, int& ny, int& nz) const;
     void getLJPMEParameters(double& alpha, int& nx, int& ny, int& nz) const;
-private:
+protected:
     struct Snapshot;                      /* flat copy of the force: the arrays an snb_desc points into */
     void fill(const OpenMM::System& system, const SlicedNonbondedForce& force, Snapshot& s) const;
     snb_handle* handle;

@@ -9,6 +9,8 @@ public:
     virtual ~Platform() {}
     static int getNumPlatforms();
     static Platform& getPlatform(int index);
+    static Platform& getPlatformByName(const std::string& name);
+    const std::string& getName() const;
     void registerKernelFactory(const std::string& name, KernelFactory* factory);
 };
 }

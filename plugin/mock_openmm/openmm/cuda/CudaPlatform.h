@@ -1,0 +1,2 @@
+/* STAND-IN (compile check only): see CudaContext.h */
+#include "CudaContext.h"

@@ -2,8 +2,8 @@
  * See plugin/include/B200OpenMMLabKernels.h.  The kernel keeps host buffers in the layout of the platform it
  * is registered on -- the Reference platform's PlatformData (vector<Vec3> positions / forces, box vectors,
  * energyParameterDerivatives; field use as in platforms/reference/src/ReferenceOpenMMLabKernels.cpp:35-58) --
- * and hands them to snb_execute.  (A zero-copy binding to OpenMM's CUDA platform through
- * snb_execute_device is the next adapter: SURVEY.md section 8f, rank 1.)
+ * and hands them to snb_execute.  The zero-copy binding to OpenMM's CUDA platform (snb_execute_device_ordered) is
+ * B200CudaOpenMMLabKernels.cpp.
  */
 #include "B200OpenMMLabKernels.h"
 
@@ -200,8 +200,11 @@ extern "C" void registerKernelFactories() {
     }
 }
 
+extern "C" void registerOpenMMLabB200CudaKernelFactories();     /* B200CudaOpenMMLabKernels.cpp: the zero-copy binding */
+
 extern "C" void registerOpenMMLabB200KernelFactories() {
     registerKernelFactories();
+    registerOpenMMLabB200CudaKernelFactories();
 }
 
 KernelImpl* B200OpenMMLabKernelFactory::createKernelImpl(std::string name, const Platform& platform, ContextImpl& context) const {

@@ -76,3 +76,10 @@ def test_openmm_plugin_adapter_compiles_against_reference_headers():
                    "B200CalcSlicedNonbondedForceKernel::initialize", "B200CalcSlicedNonbondedForceKernel::copyParametersToContext",
                    "B200OpenMMLabKernelFactory::createKernelImpl"):
         assert needed in syms
+    # the zero-copy binding to OpenMM's CUDA platform (stand-in CudaContext headers): snb_execute_device_ordered is what it drives
+    obj = os.path.join(ROOT, "plugin", "build", "B200CudaOpenMMLabKernels.check.o")
+    syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    for needed in ("registerOpenMMLabB200CudaKernelFactories", "B200CudaCalcSlicedNonbondedForceKernel::execute",
+                   "B200CudaCalcSlicedNonbondedForceKernel::initialize", "B200CudaOpenMMLabKernelFactory::createKernelImpl",
+                   "snb_execute_device_ordered", "snb_set_list_skin"):
+        assert needed in syms
