@@ -181,7 +181,7 @@ struct GraphKey {
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
     const void *posqCorrection, *atomIndex;     // snb_execute_device_ordered: the caller's atom order
-    long long outStride, positionsDouble;
+    long long outStride, positionsDouble, pmeEarly;
     double share, listSkin;
 };
 
@@ -271,6 +271,11 @@ struct snb_handle {
     PinnedBuf<double> hEnergyPme;
     PinnedBuf<long long> hEnergyFixed;  // the all-reduced energy table as it arrives (2^32 fixed point)
     cudaEvent_t evPacked = nullptr;     // this rank's contribution is packed (timing; load balance)
+    // rank 0 with no share of the tile list (4 ranks and more): reciprocal space need not wait for this evaluation's sort --
+    // the sorted order only gives its kernels locality, any permutation is correct -- so it starts with the inputs, on a COPY of
+    // the previous evaluation's order (the sort kernels rewrite the live one meanwhile)
+    DevBuf<int> sortedAtomPme;
+    bool sortedPmeValid = false, pmeEarly = false;
     bool broadcastPositions = true;     // false: the caller guarantees identical positions on every rank
     bool balanceFrozen = false;         // after a few measured evaluations the partition is fixed (and graphs take over)
     int commEvals = 0;
@@ -992,8 +997,9 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         ba.forceOrig = h.forceOrig.p; ba.paddedAtoms = h.NP; ba.energyBuf = h.energyBuf.p;
         launchBonded(ba, bs);
     };
-    if (includeDirect && h.X > 0 && !h.timing) {
+    if (!h.timing && ((includeDirect && h.X > 0) || h.pmeEarly))
         CUDA_CHECK(cudaEventRecord(h.evInputs, st));
+    if (includeDirect && h.X > 0 && !h.timing) {
         CUDA_CHECK(cudaStreamWaitEvent(h.bondedStream, h.evInputs, 0));
         bonded(h.bondedStream);
         CUDA_CHECK(cudaEventRecord(h.evBondedDone, h.bondedStream));
@@ -1039,6 +1045,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
             PmeGrid& g = term == 0 ? h.pme : h.dpme;
             PmeArgs pa = pmeArgs(h, term, includeDirect);
+            if (h.pmeEarly && ps != st)
+                pa.sortedAtom = h.sortedAtomPme.p;
             pa.forceOrig = recipForce; pa.energyBuf = recipEnergy;
             CUFFT_CHECK(cufftSetStream(g.fwd, ps));
             CUFFT_CHECK(cufftSetStream(g.inv, ps));
@@ -1061,7 +1069,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     };
     const bool doRecip = includeRecip && ewaldFamily && h.rank == 0;
     if (doRecip && !h.timing) {
-        CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.evSorted, 0));
+        CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.pmeEarly ? h.evInputs : h.evSorted, 0));
         if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evRecBegin, h.pmeStream));
         reciprocal(h.pmeStream);
         if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evRecEnd, h.pmeStream));
@@ -1173,6 +1181,9 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         NCCL_CHECK(nccl, nccl->GroupEnd());
         if (doRecip && !h.timing)
             CUDA_CHECK(cudaStreamWaitEvent(st, h.evPmeDone, 0));
+        // (reciprocal space is done with the copy of the previous order; this evaluation's order is final: next copy)
+        if (root && includeDirect && h.sortedAtomPme.p)
+            CUDA_CHECK(cudaMemcpyAsync(h.sortedAtomPme.p, h.sortedAtom.p, sizeof(int)*(size_t) h.NP, cudaMemcpyDeviceToDevice, st));
         if (includeForces && root)
             launchEmitReduced(h.reduceRecv.p, h.N, h.NP, splitRecip ? h.forcePme.p : nullptr, in.hostPositions ? h.forcesOutD.p : nullptr,
                               (long long*) in.forcesFixedOut, h.ordAtomIndex, h.ordStride ? h.ordStride : h.N, h.reduceRecv.p+nf+32*2*SNB_MAX_SLICES, st);
@@ -1231,8 +1242,10 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
             }
         }
 
+    h.pmeEarly = h.comm && h.rank == 0 && includeDirect && includeRecip && pmeFamily && !h.timing && h.sortedPmeValid && rank0Share(h) == 0.0;
     GraphKey key;
     memset(&key, 0, sizeof(key));
+    key.pmeEarly = h.pmeEarly;
     key.flags = flags; key.hostPositions = in.hostPositions; key.pbcMode = in.pbcMode;
     for (int k = 0; k < 3; k++) key.cellDim[k] = h.cellDim[k];
     key.numCells = h.numCells;
@@ -1282,6 +1295,8 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventElapsedTime(&h.lastDeviceMs, h.evBegin, h.evEnd));
     h.listValid = includeDirect;
+    if (h.comm && h.rank == 0 && includeDirect && h.sortedAtomPme.p)
+        h.sortedPmeValid = true;
     if (h.comm) {
         const NcclApi* nccl = ncclApi(nullptr);
         ncclResult_t asyncErr = ncclSuccess;
@@ -1737,7 +1752,11 @@ int snb_comm_init(snb_handle* h, const void* id128, int rank, int world_size) {
         h->energyPme.alloc(2*SNB_MAX_SLICES);
         h->hEnergyPme.alloc(2*SNB_MAX_SLICES);
         std::fill(h->hEnergyPme.p, h->hEnergyPme.p+2*SNB_MAX_SLICES, 0.0);
+        if (world_size >= 3 && getenv("SNB_NO_EARLY_PME") == nullptr)      // (two ranks: rank 0 always keeps a share of the list)
+            h->sortedAtomPme.alloc(h->NP);
     }
+    h->sortedPmeValid = false;
+    h->listKept = false;
     h->balanceFrozen = false; h->commEvals = 0;
     return SNB_OK;
     SNB_CATCH
