@@ -148,8 +148,11 @@ def residuals(ref, got, stride=1):
     dF = fr-fg
     rms_f = ref.get("rms_force") or max(float(np.sqrt((fr**2).sum(axis=1).mean())), 1.0)
     L = ref["slices"].shape[0]
+    worst = max(((rel(ref["slices"][s, t], got["slices"][s, t]), s, t) for s in range(L) for t in range(2)))
     return {"energy_rel": rel(ref["energy"], got["energy"]),
-            "worst_slice_rel": max(rel(ref["slices"][s, t], got["slices"][s, t]) for s in range(L) for t in range(2)),
+            "worst_slice_rel": worst[0],
+            "worst_slice": {"slice": worst[1], "term": "Coulomb" if worst[2] == 0 else "vdW", "reference": float(ref["slices"][worst[1], worst[2]]),
+                            "abs_error": float(abs(ref["slices"][worst[1], worst[2]]-got["slices"][worst[1], worst[2]]))},
             "worst_derivative_rel": max([rel(ref["derivs"][k], got["derivs"][k]) for k in ref["derivs"]] or [0.0]),
             "force_per_atom_metric": float((np.abs(dF).max(axis=1)/scale).max()),
             "force_rms_over_rms_force": float(np.sqrt((dF**2).sum(axis=1).mean())/rms_f),

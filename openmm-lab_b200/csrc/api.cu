@@ -271,7 +271,7 @@ struct snb_handle {
     PinnedBuf<double> hEnergyPme;
     PinnedBuf<long long> hEnergyFixed;  // the all-reduced energy table as it arrives (2^32 fixed point)
     cudaEvent_t evPacked = nullptr;     // this rank's contribution is packed (timing; load balance)
-    // rank 0 with no share of the tile list (4 ranks and more): reciprocal space need not wait for this evaluation's sort --
+    // rank 0 with (next to) no share of the tile list (4 ranks and more): reciprocal space need not wait for this evaluation's sort --
     // the sorted order only gives its kernels locality, any permutation is correct -- so it starts with the inputs, on a COPY of
     // the previous evaluation's order (the sort kernels rewrite the live one meanwhile)
     DevBuf<int> sortedAtomPme;
@@ -1242,7 +1242,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
             }
         }
 
-    h.pmeEarly = h.comm && h.rank == 0 && includeDirect && includeRecip && pmeFamily && !h.timing && h.sortedPmeValid && rank0Share(h) == 0.0;
+    h.pmeEarly = h.comm && h.rank == 0 && includeDirect && includeRecip && pmeFamily && !h.timing && h.sortedPmeValid && rank0Share(h) <= 0.1;
     GraphKey key;
     memset(&key, 0, sizeof(key));
     key.pmeEarly = h.pmeEarly;

@@ -13,9 +13,10 @@
 // unit itself (the subset is the tensor's fourth coordinate).  After the inverse transform k_pmeCombinePad writes
 // phi_i = sum_j lambda[slice(i,j)] grid_j straight into the padded layout, halo included.
 //
-// Spreading through bricks was built and measured three ways in round 2 and lost to the per-atom kernel of pme.cu every
-// time: whole-brick bulk tensor reductions (UTMAREDG), shared-memory atomics, and a warp-private brick
-// flushed with red.global.add.v4.f32 -- 256 / 48 / 22 us against 225 / 32 / 15.5 us at STMV / ApoA1 / DHFR size.
+// Spreading through bricks was built and measured four ways in round 2 and never beat the per-atom kernel of pme.cu
+// (DESIGN.md section 7a): whole-brick bulk tensor reductions (UTMAREDG), shared-memory atomics, a warp-private 16x16x20 brick
+// flushed with red.global.add.v4.f32 (256 / 48 / 22 us against 225 / 32 / 15.5 us at STMV / ApoA1 / DHFR size), and the same
+// with a 12x12x16 brick for twice the resident warps (229 us at STMV size).
 //
 // Arithmetic: platforms/reference/src/ReferencePME.cpp:196-256 (index, fraction), :264-317 (B-splines), :598-702
 // (interpolation; subset stride nx, see pme.cu).  (GPU behavioural cross-reference: platforms/common/src/kernels/pme.cc:296-408.)
@@ -75,12 +76,13 @@ __device__ __forceinline__ bool threadAtom(const PmeArgs& a, int k, int& atom, i
     atom = a.sortedAtom[k];
     if (atom < 0)
         return false;
+    // (position and parameters are requested together: one DRAM round trip after the atom's index, not two)
     const float4 prm = a.params4[atom];
+    const double x = a.posd[3*(size_t) atom], y = a.posd[3*(size_t) atom+1], z = a.posd[3*(size_t) atom+2];
     q = a.term == 0 ? prm.x : 8.0f*prm.y*prm.y*prm.y*prm.z;
     if (q == 0.f)
         return false;
     sub = __float_as_int(prm.w);
-    const double x = a.posd[3*(size_t) atom], y = a.posd[3*(size_t) atom+1], z = a.posd[3*(size_t) atom+2];
     const BoxD& b = a.sp->exact.boxd;
     double t[3];
     t[0] = x*b.recip[0][0]+y*b.recip[1][0]+z*b.recip[2][0];

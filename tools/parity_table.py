@@ -67,6 +67,7 @@ def main():
                 print("| %-12s | %-13s | %-6s | %.1e | %.1e | %.1e | %.1e | %.1e | %.1e | %s | %s |" % (
                     w.name, mode, part, r["energy_rel"], r["worst_slice_rel"], r["worst_derivative_rel"], r["force_per_atom_metric"],
                     r["force_rms_over_rms_force"], r["force_max_over_rms_force"], row.get("pair_set_equal", ""), row["within_1e-5"]), file=sys.stderr, flush=True)
+                print("    worst slice: %r" % (r["worst_slice"],), file=sys.stderr, flush=True)
                 del got
     print(json.dumps(table))
 
