@@ -11,9 +11,10 @@ from .force import OpenMMException, SlicedNonbondedForce
 from .kernel import B200CalcSlicedNonbondedForceKernel, CalcSlicedNonbondedForceKernel, load_library, partition
 from .platform import registerKernelFactories, registerPlatforms
 from . import systems
+from .serialization import SlicedNonbondedForceProxy, XmlSerializer
 
 registerKernelFactories()
 
 __all__ = ["SlicedNonbondedForce", "System", "Context", "State", "Platform", "OpenMMException", "SnbError",
            "CalcSlicedNonbondedForceKernel", "B200CalcSlicedNonbondedForceKernel", "load_library",
-           "registerKernelFactories", "registerPlatforms"]
+           "registerKernelFactories", "registerPlatforms", "XmlSerializer", "SlicedNonbondedForceProxy"]

@@ -56,6 +56,7 @@ class SlicedNonbondedForce:
         self._recipForceGroup = -1
         self._includeDirectSpace = True
         self._forceGroup = 0
+        self._name = "SlicedNonbondedForce"     # OpenMM Force::getName default: the class name
         self._particles = []            # [charge, sigma, epsilon]
         self._exceptions = []           # [p1, p2, chargeProd, sigma, epsilon]
         self._exceptionMap = {}
@@ -98,6 +99,8 @@ class SlicedNonbondedForce:
     # ---- OpenMM NonbondedForce surface (third party; names as used by the reference tests) ----
     def getForceGroup(self): return self._forceGroup
     def setForceGroup(self, g): self._forceGroup = int(g)
+    def getName(self): return self._name
+    def setName(self, name): self._name = str(name)
     def getNonbondedMethod(self): return self._method
     def setNonbondedMethod(self, m):
         if m not in range(6):
