@@ -258,7 +258,8 @@ int snb_get_phase_times(snb_handle* h, float* ms /*[SNB_NUM_PHASES]*/);
 /* CUDA-event time (ms) of the last execute on the handle's stream: first memset .. last read-back copy
  * (excludes the host->device copy of the positions, which precedes it) */
 int snb_get_last_device_ms(snb_handle* h, float* ms);
-/* counters of the last execute: [0] unused (the interacting pairs are counted on request: snb_count_pairs),
+/* counters of the last execute: [0] 1 when the sort ran as the one cooperative kernel (k_sortFused), 0 for the separate
+ * kernels, -1 when its launch was refused once and it is off for this handle,
  * [1] chunks of 32 tile-list entries, [2] kernel launches of this library, [3] k_computeParameters launches since
  * creation, [4] 1 when the evaluation was replayed from a captured CUDA graph, [5] 1 when the packed-FP32 direct-space
  * kernel (k_directPacked) took the launch, 0 for the general one (k_direct), [6] tile-list rebuilds and [7]

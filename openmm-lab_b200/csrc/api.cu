@@ -177,7 +177,7 @@ struct PmeGrid {
 // same nodes with the same arguments (the box and the lambdas travel through StepParams in device
 // memory), so the second one onwards replays a captured CUDA graph.
 struct GraphKey {
-    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast;
+    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast, fusedSort;
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
     const void *posqCorrection, *atomIndex;     // snb_execute_device_ordered: the caller's atom order
@@ -237,6 +237,9 @@ struct snb_handle {
     cudaEvent_t evSorted = nullptr, evPmeDone = nullptr, evBegin = nullptr, evEnd = nullptr;
     float lastDeviceMs = 0;
     int numSMs = 148;
+    int fusedSort = 1;          // the sort as one cooperative kernel where it applies (SNB_FUSED_SORT=0: separate kernels); cleared if its launch fails
+    bool fusedSortUsed = false; // the last enqueueStep launched it
+    bool fusedSortFailed = false;
     DevBuf<double> posd, paramsD, exception14, extent, energyBuf, forcesOutD;
     DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt, blockCenter;
     DevBuf<double4> posqLocalD, sparamsD;
@@ -566,6 +569,7 @@ snb_handle* createHandle(const snb_desc& d) {
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evInputs, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evBondedDone, cudaEventDisableTiming));
         h.useGraph = getenv("SNB_NO_GRAPH") == nullptr;
+        if (const char* env = getenv("SNB_FUSED_SORT")) h.fusedSort = atoi(env) != 0;
         h.stepD.alloc(1);
         h.stepH.alloc(1);
         memset(h.stepH.p, 0, sizeof(StepParams));
@@ -958,12 +962,36 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     // the other ranks receive them over NVLink -- and every rank then builds the identical sorted order
     const bool root = h.rank == 0;
     const bool receivePositions = nccl && h.broadcastPositions && !root;
+    // the sort's arguments come first: whether it runs as ONE cooperative kernel (sort.cu, k_sortFused) decides where the
+    // conversion of a device-resident caller's positions happens -- inside that kernel (single GPU), else in a kernel of its own
+    SortArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    if (includeDirect) {
+        sa.numAtoms = h.N; sa.paddedAtoms = h.NP; sa.numBlocks = h.NB; sa.numCells = h.numCells; sa.periodic = periodic;
+        for (int k = 0; k < 3; k++) sa.cellDim[k] = h.cellDim[k];
+        sa.counters = h.counters.p;
+        sa.sqrtK = (float) sqrt(SNB_ONE_4PI_EPS0);
+        sa.sp = h.stepD.p;
+        sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.paramsD = h.paramsD.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
+        sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
+        sa.cellRange = h.cellRange.p; sa.tileSum = h.tileSum.p; sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
+        sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
+        sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
+        sa.reuse = h.skinNow > 0; sa.posRef = h.posRef.p; sa.wrapImage = h.wrapImage.p;
+        sa.fused = h.fusedSort; sa.numSMs = h.numSMs;
+    }
+    const bool fusedSort = includeDirect && sortFusedGrid(sa) > 0;
+    const bool convertInSort = fusedSort && !in.hostPositions && !nccl;
+    if (convertInSort) {
+        sa.posqIn = in.posqDev; sa.posqInCorrection = (const float4*) h.ordCorrection; sa.posqInIndex = h.ordAtomIndex;
+        sa.posqInDouble = h.ordDouble; sa.posdOut = h.posd.p;
+    }
     Range* range = new Range("snb inputs");
     if (in.hostPositions) {
         if (!receivePositions)
             CUDA_CHECK(cudaMemcpyAsync(h.posd.p, in.hostPos, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
     }
-    else if (!receivePositions)
+    else if (!receivePositions && !convertInSort)
         launchConvertPositions(in.posqDev, h.ordCorrection, h.ordAtomIndex, h.ordDouble, h.posd.p, h.N, st);
     if (nccl && h.broadcastPositions)
         NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, st));
@@ -999,34 +1027,30 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     };
     if (!h.timing && ((includeDirect && h.X > 0) || h.pmeEarly))
         CUDA_CHECK(cudaEventRecord(h.evInputs, st));
-    if (includeDirect && h.X > 0 && !h.timing) {
-        CUDA_CHECK(cudaStreamWaitEvent(h.bondedStream, h.evInputs, 0));
+    auto forkBonded = [&](cudaEvent_t after) {
+        CUDA_CHECK(cudaStreamWaitEvent(h.bondedStream, after, 0));
         bonded(h.bondedStream);
         CUDA_CHECK(cudaEventRecord(h.evBondedDone, h.bondedStream));
         bondedForked = true;
-    }
+    };
+    if (includeDirect && h.X > 0 && !h.timing && !convertInSort)
+        forkBonded(h.evInputs);
 
     DirectArgs da;
     memset(&da, 0, sizeof(da));
+    h.fusedSortUsed = false;
     if (includeDirect) {
         Range sortRange("snb sort");
-        SortArgs sa;
-        memset(&sa, 0, sizeof(sa));
-        sa.numAtoms = h.N; sa.paddedAtoms = h.NP; sa.numBlocks = h.NB; sa.numCells = h.numCells; sa.periodic = periodic;
-        for (int k = 0; k < 3; k++) sa.cellDim[k] = h.cellDim[k];
-        sa.counters = h.counters.p;
-        sa.sqrtK = (float) sqrt(SNB_ONE_4PI_EPS0);
-        sa.sp = h.stepD.p;
-        sa.posd = h.posd.p; sa.params4 = h.params4.p; sa.paramsD = h.paramsD.p; sa.cellRank = h.cellRank.p; sa.extent = h.extent.p;
-        sa.posqLocalD = h.doublePrecision ? h.posqLocalD.p : nullptr; sa.sparamsD = h.doublePrecision ? h.sparamsD.p : nullptr;
-        sa.cellRange = h.cellRange.p; sa.tileSum = h.tileSum.p; sa.cellCount = h.cellCount.p; sa.cellStart = h.cellStart.p; sa.atomCell = h.atomCell.p; sa.atomSlot = h.atomSlot.p; sa.cellScratch = h.cellScratch.p;
-        sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
-        sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
-        sa.reuse = h.skinNow > 0; sa.posRef = h.posRef.p; sa.wrapImage = h.wrapImage.p;
-        launchSort(sa, st);
+        bool used = false;
+        const cudaError_t err = launchSort(sa, st, &used);
+        h.fusedSortUsed = used;
+        CUDA_CHECK(err);
     }
     tm.mark(1);
     if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
+    // (positions converted inside the sort: the exceptions' stream starts here instead of beside it)
+    if (includeDirect && h.X > 0 && !h.timing && convertInSort)
+        forkBonded(h.evSorted);
 
     // ---- reciprocal space (rank 0): its own stream, beside the tile list / direct-space kernels ----
     auto reciprocal = [&](cudaStream_t ps) {
@@ -1249,6 +1273,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     key.flags = flags; key.hostPositions = in.hostPositions; key.pbcMode = in.pbcMode;
     for (int k = 0; k < 3; k++) key.cellDim[k] = h.cellDim[k];
     key.numCells = h.numCells;
+    key.fusedSort = h.fusedSort;
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     key.maxChunks = h.maxChunks;
     key.share = h.comm ? rank0Share(h) : 0.0;
@@ -1262,6 +1287,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
         dropGraph(h);
 
     CUDA_CHECK(cudaEventRecord(h.evBegin, st));
+    bool captureFailed = false;
     if (graphable && sameKey) {
         if (!h.graphExec) {
             // second evaluation with this shape: capture it (the first ran eagerly and did every lazy set-up)
@@ -1273,22 +1299,50 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
             catch (...) {
                 cudaStreamEndCapture(st, &graph);
                 if (graph) cudaGraphDestroy(graph);
-                throw;
+                if (!h.fusedSort)
+                    throw;
+                graph = nullptr;
+                captureFailed = true;       // (the cooperative kernel is the one node kind this graph had not held before)
             }
-            CUDA_CHECK(cudaStreamEndCapture(st, &graph));
-            cudaError_t err = cudaGraphInstantiate(&h.graphExec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (err != cudaSuccess) {
-                h.graphExec = nullptr;
-                throw SnbException(SNB_ERR_CUDA, std::string("cudaGraphInstantiate: ")+cudaGetErrorString(err));
+            if (!captureFailed) {
+                CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+                cudaError_t err = cudaGraphInstantiate(&h.graphExec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (err != cudaSuccess) {
+                    h.graphExec = nullptr;
+                    if (!h.fusedSortUsed)
+                        throw SnbException(SNB_ERR_CUDA, std::string("cudaGraphInstantiate: ")+cudaGetErrorString(err));
+                    captureFailed = true;
+                }
             }
         }
-        CUDA_CHECK(cudaGraphLaunch(h.graphExec, st));
+        if (!captureFailed)
+            CUDA_CHECK(cudaGraphLaunch(h.graphExec, st));
     }
     else {
-        enqueueStep(h, in);
+        try {
+            enqueueStep(h, in);
+        }
+        catch (...) {
+            if (!h.fusedSortUsed)
+                throw;
+            captureFailed = true;           // the cooperative launch was refused: this evaluation again, with the separate kernels
+        }
         h.graphKey = key;
-        h.graphKeyValid = graphable;
+        h.graphKeyValid = graphable && !captureFailed;
+    }
+    if (captureFailed) {
+        // the fused sort kernel could not be launched or captured here: off for this handle, the evaluation runs eagerly
+        // with the separate kernels (and is captured the time after next, under its new key)
+        cudaGetLastError();
+        cudaStreamSynchronize(st);
+        cudaGetLastError();
+        h.fusedSort = 0;
+        h.fusedSortFailed = true;
+        dropGraph(h);
+        h.graphKeyValid = false;
+        CUDA_CHECK(cudaEventRecord(h.evBegin, st));
+        enqueueStep(h, in);
     }
     CUDA_CHECK(cudaEventRecord(h.evEnd, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1368,6 +1422,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
         h.listEvals++;
         if (h.hCounters.p[SNB_COUNTER_REBUILD]) h.listRebuilds++;
     }
+    h.countersOut[0] = h.fusedSortFailed ? -1 : (includeDirect && h.fusedSortUsed ? 1 : 0);
     h.countersOut[1] = h.hCounters.p[0];
     h.countersOut[6] = h.listRebuilds;
     h.countersOut[7] = h.listEvals;
@@ -1376,13 +1431,13 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     h.countersOut[5] = includeDirect && h.packedLaunched ? 1 : 0;
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
-    if (includeDirect) launches += (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0)+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
+    if (includeDirect) launches += (h.fusedSortUsed ? 1 : (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0))+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
     if (includeRecip && h.method == SNB_EWALD && h.rank == 0) launches += 2;    // structure factors, forces
     if (includeRecip && pmeFamily && h.rank == 0)      // spread (+ finish or fold), convolution, combine, interpolate
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++)
             launches += h.deterministic ? 5 : 4;
     if (includeForces || h.comm) launches += 1+(h.comm && includeForces ? 1 : 0);
-    if (posqDev) launches += 1;
+    if (posqDev && !(h.fusedSortUsed && !h.comm)) launches += 1;     // position conversion (inside the fused sort kernel otherwise)
     h.countersOut[2] = launches;
     return true;
 }

@@ -53,8 +53,19 @@ struct SortArgs {
     int reuse;
     double* posRef;         // [N][3] positions at the last rebuild
     float4* wrapImage;      // [N] periodic image (whole box vectors) every atom was wrapped by at the last rebuild
+    // the sort as one cooperative kernel (k_sortFused: periodic, no list reuse, at most SORT_FUSED_MAX_CELLS cells)
+    int fused, numSMs;
+    const void* posqIn;     // device-resident caller: positions converted inside the fused kernel (null: posd is ready)
+    const float4* posqInCorrection;
+    const int* posqInIndex;
+    int posqInDouble;
+    double* posdOut;
 };
-void launchSort(const SortArgs& a, cudaStream_t stream);
+#define SORT_FUSED_MAX_CELLS 8192
+// usedFused (optional): whether the fused kernel took the launch; the error is the cooperative launch's (the caller may
+// fall back to the separate kernels by clearing `fused`)
+cudaError_t launchSort(const SortArgs& a, cudaStream_t stream, bool* usedFused = nullptr);
+int sortFusedGrid(const SortArgs& a);     // > 0: launchSort will take the fused kernel with this grid
 
 struct ListArgs {
     int numAtoms, numBlocks, pbcMode, periodic, useCutoff;

@@ -8,6 +8,8 @@
 #include "snb_core.cuh"
 #include "kernels.cuh"
 
+#include <cooperative_groups.h>
+
 // ---- 0. tile-list reuse (platform property ListSkin > 0) ---------------------------------------------
 // The list of the last rebuild was built with cutoff + skin, so it holds every pair that is within the cutoff now as long
 // as no atom has moved more than skin/2 since (the exact predicate of the direct-space kernel still decides the pair set
@@ -32,14 +34,7 @@ __global__ void k_listCheck(SortArgs a) {
 // One thread per atom.  cellRank[] maps a linear cell index to its position along the Hilbert
 // curve (host-built table).  The slot within the cell comes from an atomic counter; the
 // within-cell order is made deterministic afterwards by sortCells.
-__global__ void k_assignCells(SortArgs a) {
-    int i = blockIdx.x*blockDim.x+threadIdx.x;
-    if (i >= a.numAtoms || keepList(a))
-        return;
-    double x = a.posd[3*i], y = a.posd[3*i+1], z = a.posd[3*i+2];
-    if (a.reuse) {
-        a.posRef[3*i] = x; a.posRef[3*i+1] = y; a.posRef[3*i+2] = z;
-    }
+__device__ __forceinline__ int cellRankOf(const SortArgs& a, double x, double y, double z) {
     int c[3];
     if (a.periodic) {
         // fractional coordinates, frac = pos * recip (lower triangular)
@@ -62,7 +57,18 @@ __global__ void k_assignCells(SortArgs a) {
             c[d] = max(0, min(a.cellDim[d]-1, (int) (w*a.cellDim[d])));
         }
     }
-    int rank = a.cellRank[(c[0]*a.cellDim[1]+c[1])*a.cellDim[2]+c[2]];
+    return a.cellRank[(c[0]*a.cellDim[1]+c[1])*a.cellDim[2]+c[2]];
+}
+
+__global__ void k_assignCells(SortArgs a) {
+    int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (i >= a.numAtoms || keepList(a))
+        return;
+    double x = a.posd[3*i], y = a.posd[3*i+1], z = a.posd[3*i+2];
+    if (a.reuse) {
+        a.posRef[3*i] = x; a.posRef[3*i+1] = y; a.posRef[3*i+2] = z;
+    }
+    const int rank = cellRankOf(a, x, y, z);
     a.atomCell[i] = rank;
     a.atomSlot[i] = atomicAdd(&a.cellCount[rank], 1);
 }
@@ -225,10 +231,7 @@ __global__ void k_rankInCell(SortArgs a) {
 // binning), the block centre is the middle of the axis-aligned bounding box, and every atom
 // stores its offset from that centre in single precision: |offset| < ~1 nm, so the absolute
 // coordinate error is ~3e-8 nm whatever the size of the system.
-__global__ void k_blockBounds(SortArgs a) {
-    int warp = (blockIdx.x*blockDim.x+threadIdx.x)>>5, lane = threadIdx.x&31;
-    if (warp >= a.numBlocks)
-        return;
+__device__ __forceinline__ void blockBoundsWarp(const SortArgs& a, const int warp, const int lane) {
     int k = warp*SNB_BLOCK+lane;
     int atom = a.sortedAtom[k];
     double p[3] = {0, 0, 0};
@@ -327,7 +330,145 @@ __global__ void k_blockBounds(SortArgs a) {
     }
 }
 
-void launchSort(const SortArgs& a, cudaStream_t stream) {
+__global__ void k_blockBounds(SortArgs a) {
+    const int warp = (blockIdx.x*blockDim.x+threadIdx.x)>>5, lane = threadIdx.x&31;
+    if (warp < a.numBlocks)
+        blockBoundsWarp(a, warp, lane);
+}
+
+// ---- 5. the whole sort as ONE cooperative kernel (small and medium systems) ---------------------------------
+// Below ~100 000 atoms every kernel above runs for 3-5 us of which most is launch ramp and one chain of dependent memory
+// accesses, and the six of them (with the position conversion) are the head of BOTH critical chains of an evaluation
+// (list -> direct space, and reciprocal space).  Here they are the phases of one kernel, separated by grid-wide barriers
+// (cooperative launch: every CTA is resident), and the exclusive scan of the cell counts is done by every CTA for itself
+// in shared memory (at most SORT_FUSED_MAX_CELLS cells), which saves the barrier around a one-CTA scan:
+//   A  position conversion (device-resident callers), cell of every atom, slot by atomic counter     | barrier
+//   B  scan of the counts -> shared memory; C  scatter into the cell segments, sorted range of every cell | barrier
+//   D  rank inside the cell (deterministic order), counters re-zeroed                                 | barrier
+//   E  blocks of 32: boxes, centres, local coordinates (blockBoundsWarp).
+// Periodic methods without list reuse; everything else takes the separate kernels.
+#define SORT_FUSED_THREADS 256
+
+__global__ void __launch_bounds__(SORT_FUSED_THREADS) k_sortFused(SortArgs a) {
+    extern __shared__ int sStart[];                     // [numCells+1] exclusive scan of the cell counts
+    __shared__ int warpSums[32];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
+    // ---- A
+    for (int t = tid; t < a.numAtoms; t += nThreads) {
+        int i = t;
+        double x, y, z;
+        if (a.posqIn) {
+            // k_convertPositions (finish.cu) folded in: the caller's float4 (+ correction) or double4 positions, in its order
+            if (a.posqInDouble) {
+                const double4 p = ((const double4*) a.posqIn)[t];
+                x = p.x; y = p.y; z = p.z;
+            }
+            else {
+                const float4 p = ((const float4*) a.posqIn)[t];
+                x = p.x; y = p.y; z = p.z;
+                if (a.posqInCorrection) {
+                    const float4 c = a.posqInCorrection[t];
+                    x += (double) c.x; y += (double) c.y; z += (double) c.z;
+                }
+            }
+            if (a.posqInIndex)
+                i = a.posqInIndex[t];
+            a.posdOut[3*i] = x; a.posdOut[3*i+1] = y; a.posdOut[3*i+2] = z;
+        }
+        else {
+            x = a.posd[3*i]; y = a.posd[3*i+1]; z = a.posd[3*i+2];
+        }
+        const int rank = cellRankOf(a, x, y, z);
+        a.atomCell[i] = rank;
+        a.atomSlot[i] = atomicAdd(&a.cellCount[rank], 1);
+    }
+    grid.sync();
+    // ---- B (every CTA for itself)
+    {
+        // the counts arrive coalesced; every thread then owns a contiguous run of cells
+        for (int i = threadIdx.x; i < a.numCells; i += blockDim.x)
+            sStart[i] = __ldcg(a.cellCount+i);
+        __syncthreads();
+        const int per = (a.numCells+(int) blockDim.x-1)/(int) blockDim.x;
+        const int first = min(a.numCells, (int) threadIdx.x*per), last = min(a.numCells, first+per);
+        int sum = 0;
+        for (int i = first; i < last; i++)
+            sum += sStart[i];
+        int total;
+        int running = blockExclusiveScan(sum, warpSums, total);
+        for (int i = first; i < last; i++) {
+            const int v = sStart[i];
+            sStart[i] = running;
+            running += v;
+        }
+        if (threadIdx.x == 0)
+            sStart[a.numCells] = total;
+        __syncthreads();
+    }
+    // ---- C
+    for (int t = tid; t < a.numAtoms; t += nThreads)
+        a.cellScratch[sStart[__ldcg(a.atomCell+t)]+__ldcg(a.atomSlot+t)] = t;
+    for (int i = tid; i < a.numCells; i += nThreads) {
+        const int r = a.cellRank[i];
+        a.cellRange[i] = make_int2(sStart[r], sStart[r+1]);
+    }
+    for (int i = tid; i < a.paddedAtoms-a.numAtoms; i += nThreads)
+        a.sortedAtom[a.numAtoms+i] = -1;
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i <= a.numCells; i += blockDim.x)
+            a.cellStart[i] = sStart[i];
+    grid.sync();
+    // ---- D
+    for (int t = tid; t < a.numAtoms; t += nThreads) {
+        const int c = __ldcg(a.atomCell+t), s = sStart[c], e = sStart[c+1];
+        int rank = 0;
+        for (int k = s; k < e; k++)
+            rank += __ldcg(a.cellScratch+k) < t;
+        a.sortedAtom[s+rank] = t;
+    }
+    for (int i = tid; i < a.numCells; i += nThreads)
+        a.cellCount[i] = 0;         // ready for the next evaluation
+    grid.sync();
+    // ---- E
+    const int lane = threadIdx.x&31;
+    for (int warp = tid>>5; warp < a.numBlocks; warp += nThreads>>5)
+        blockBoundsWarp(a, warp, lane);
+}
+
+// Grid of the fused kernel if this is its case and it fits on the device (every CTA resident), else 0: the separate kernels.
+int sortFusedGrid(const SortArgs& a) {
+    if (!a.fused || a.reuse || !a.periodic || a.numCells > SORT_FUSED_MAX_CELLS || a.numAtoms <= 0)
+        return 0;
+    const size_t smem = sizeof(int)*((size_t) a.numCells+1);
+    int perSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sortFused, SORT_FUSED_THREADS, smem) != cudaSuccess || perSM < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    const int want = (a.paddedAtoms+SORT_FUSED_THREADS-1)/SORT_FUSED_THREADS;
+    return max(1, min(want, perSM*max(a.numSMs, 1)));
+}
+
+static bool launchSortFused(const SortArgs& a, cudaStream_t stream, cudaError_t& err) {
+    err = cudaSuccess;
+    const int grid = sortFusedGrid(a);
+    if (grid <= 0)
+        return false;
+    const size_t smem = sizeof(int)*((size_t) a.numCells+1);
+    SortArgs copy = a;
+    void* args[] = {&copy};
+    err = cudaLaunchCooperativeKernel((const void*) k_sortFused, dim3(grid), dim3(SORT_FUSED_THREADS), args, smem, stream);
+    return true;
+}
+
+cudaError_t launchSort(const SortArgs& a, cudaStream_t stream, bool* usedFused) {
+    cudaError_t fusedErr;
+    const bool fused = launchSortFused(a, stream, fusedErr);
+    if (usedFused)
+        *usedFused = fused;
+    if (fused)
+        return fusedErr;
     int threads = 256;
     int atomBlocks = (a.paddedAtoms+threads-1)/threads;
     const int* keep = a.reuse ? a.counters+SNB_COUNTER_REBUILD : nullptr;
@@ -347,4 +488,5 @@ void launchSort(const SortArgs& a, cudaStream_t stream) {
     k_scatterAtoms<<<(max(a.paddedAtoms, a.numCells)+threads-1)/threads, threads, 0, stream>>>(a);
     k_rankInCell<<<atomBlocks, threads, 0, stream>>>(a);
     k_blockBounds<<<(a.numBlocks*32+threads-1)/threads, threads, 0, stream>>>(a);
+    return cudaSuccess;
 }
