@@ -177,7 +177,7 @@ struct PmeGrid {
 // same nodes with the same arguments (the box and the lambdas travel through StepParams in device
 // memory), so the second one onwards replays a captured CUDA graph.
 struct GraphKey {
-    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast, fusedSort;
+    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast, fusedSort, beginKernel;
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
     const void *posqCorrection, *atomIndex;     // snb_execute_device_ordered: the caller's atom order
@@ -240,6 +240,12 @@ struct snb_handle {
     int fusedSort = 1;          // the sort as one cooperative kernel where it applies (SNB_FUSED_SORT=0: separate kernels); cleared if its launch fails
     bool fusedSortUsed = false; // the last enqueueStep launched it
     bool fusedSortFailed = false;
+    int beginKernel = 1;        // k_begin instead of copy + memset + conversion kernel (SNB_BEGIN_KERNEL=0: those three)
+    bool beginKernelUsed = false;
+    const int* stepHDev = nullptr;
+    int hostResults = 1;        // k_finish stores energies / counters into the pinned mirrors (SNB_HOST_RESULTS=0: copies)
+    double* hEnergyDev = nullptr;
+    int* hCountersDev = nullptr;
     DevBuf<double> posd, paramsD, exception14, extent, energyBuf, forcesOutD;
     DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt, blockCenter;
     DevBuf<double4> posqLocalD, sparamsD;
@@ -570,9 +576,16 @@ snb_handle* createHandle(const snb_desc& d) {
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evBondedDone, cudaEventDisableTiming));
         h.useGraph = getenv("SNB_NO_GRAPH") == nullptr;
         if (const char* env = getenv("SNB_FUSED_SORT")) h.fusedSort = atoi(env) != 0;
+        if (const char* env = getenv("SNB_HOST_RESULTS")) h.hostResults = atoi(env) != 0;
+        if (const char* env = getenv("SNB_BEGIN_KERNEL")) h.beginKernel = atoi(env) != 0;
         h.stepD.alloc(1);
         h.stepH.alloc(1);
         memset(h.stepH.p, 0, sizeof(StepParams));
+        {
+            void* dev = nullptr;
+            if (cudaHostGetDevicePointer(&dev, h.stepH.p, 0) == cudaSuccess) h.stepHDev = (const int*) dev;
+            else cudaGetLastError();
+        }
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evSorted, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evPmeDone, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreate(&h.evBegin));
@@ -693,6 +706,15 @@ snb_handle* createHandle(const snb_desc& d) {
         h.hPos.alloc(3*(size_t) h.N); h.hForces.alloc(3*(size_t) h.N);
         h.hEnergy.alloc(SNB_ENERGY_DOUBLES);
         h.hCounters.alloc(8);
+        // device-side addresses of the two pinned mirrors (unified addressing maps cudaMallocHost memory): k_finish stores
+        // its results there; without a mapping the evaluation keeps its two device->host copies
+        void *eDev = nullptr, *cDev = nullptr;
+        if (cudaHostGetDevicePointer(&eDev, h.hEnergy.p, 0) == cudaSuccess && cudaHostGetDevicePointer(&cDev, h.hCounters.p, 0) == cudaSuccess) {
+            h.hEnergyDev = (double*) eDev;
+            h.hCountersDev = (int*) cDev;
+        }
+        else
+            cudaGetLastError();
         h.sliceEnergies.assign(2*h.L, 0.0);
         if (h.method == SNB_PME || h.method == SNB_LJPME)
             setupPme(h, h.pme, h.grid, h.alpha);
@@ -962,8 +984,6 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     // the other ranks receive them over NVLink -- and every rank then builds the identical sorted order
     const bool root = h.rank == 0;
     const bool receivePositions = nccl && h.broadcastPositions && !root;
-    // the sort's arguments come first: whether it runs as ONE cooperative kernel (sort.cu, k_sortFused) decides where the
-    // conversion of a device-resident caller's positions happens -- inside that kernel (single GPU), else in a kernel of its own
     SortArgs sa;
     memset(&sa, 0, sizeof(sa));
     if (includeDirect) {
@@ -980,23 +1000,32 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         sa.reuse = h.skinNow > 0; sa.posRef = h.posRef.p; sa.wrapImage = h.wrapImage.p;
         sa.fused = h.fusedSort; sa.numSMs = h.numSMs;
     }
-    const bool fusedSort = includeDirect && sortFusedGrid(sa) > 0;
-    const bool convertInSort = fusedSort && !in.hostPositions && !nccl;
-    if (convertInSort) {
-        sa.posqIn = in.posqDev; sa.posqInCorrection = (const float4*) h.ordCorrection; sa.posqInIndex = h.ordAtomIndex;
-        sa.posqInDouble = h.ordDouble; sa.posdOut = h.posd.p;
-    }
+    // single GPU: the copy of the step's parameters, the memset of the accumulators and the position conversion are ONE
+    // kernel (k_begin, finish.cu) -- three graph nodes fewer at the head of every chain of the evaluation
+    const bool beginKernel = !nccl && h.beginKernel && h.stepHDev != nullptr;
+    h.beginKernelUsed = beginKernel;
     Range* range = new Range("snb inputs");
     if (in.hostPositions) {
         if (!receivePositions)
             CUDA_CHECK(cudaMemcpyAsync(h.posd.p, in.hostPos, sizeof(double)*3*(size_t) h.N, cudaMemcpyHostToDevice, st));
     }
-    else if (!receivePositions && !convertInSort)
+    else if (!receivePositions && !beginKernel)
         launchConvertPositions(in.posqDev, h.ordCorrection, h.ordAtomIndex, h.ordDouble, h.posd.p, h.N, st);
+    if (beginKernel) {
+        BeginArgs bg;
+        memset(&bg, 0, sizeof(bg));
+        bg.stepHost = h.stepHDev; bg.stepDev = (int*) h.stepD.p; bg.stepWords = (int) (sizeof(StepParams)/4);
+        bg.zero = (unsigned long long*) h.zeroBlock.p; bg.zeroWords = h.zeroBytes/8;
+        bg.posq = in.hostPositions ? nullptr : in.posqDev; bg.correction = (const float4*) h.ordCorrection; bg.atomIndex = h.ordAtomIndex;
+        bg.positionsDouble = h.ordDouble; bg.posd = h.posd.p; bg.numAtoms = h.N;
+        launchBegin(bg, st);
+    }
     if (nccl && h.broadcastPositions)
         NCCL_CHECK(nccl, nccl->Broadcast(h.posd.p, h.posd.p, 3*(size_t) h.N, ncclFloat64, 0, h.comm, st));
-    CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemsetAsync(h.zeroBlock.p, 0, h.zeroBytes, st));
+    if (!beginKernel) {
+        CUDA_CHECK(cudaMemcpyAsync(h.stepD.p, h.stepH.p, sizeof(StepParams), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(h.zeroBlock.p, 0, h.zeroBytes, st));
+    }
     // multi-GPU, rank 0: reciprocal space accumulates into buffers of its own, so that the other terms can be reduced
     // between the ranks WHILE it runs; its forces and energies are added after the reduction
     const bool splitRecip = nccl && root;
@@ -1033,7 +1062,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         CUDA_CHECK(cudaEventRecord(h.evBondedDone, h.bondedStream));
         bondedForked = true;
     };
-    if (includeDirect && h.X > 0 && !h.timing && !convertInSort)
+    if (includeDirect && h.X > 0 && !h.timing)
         forkBonded(h.evInputs);
 
     DirectArgs da;
@@ -1048,9 +1077,6 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     }
     tm.mark(1);
     if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
-    // (positions converted inside the sort: the exceptions' stream starts here instead of beside it)
-    if (includeDirect && h.X > 0 && !h.timing && convertInSort)
-        forkBonded(h.evSorted);
 
     // ---- reciprocal space (rank 0): its own stream, beside the tile list / direct-space kernels ----
     auto reciprocal = [&](cudaStream_t ps) {
@@ -1177,6 +1203,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     Range outRange("snb reduce + outputs");
 
     // ---- outputs ----
+    bool resultsStored = false;     // k_finish wrote energies + counters into the pinned mirrors itself
     FinishArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.numAtoms = h.N; fa.paddedAtoms = h.NP;
@@ -1218,6 +1245,10 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         if (includeForces) {
             fa.forcesOut = in.hostPositions ? h.forcesOutD.p : nullptr;
             fa.forcesFixedOut = (long long*) in.forcesFixedOut;
+            if (h.hostResults && h.hEnergyDev && h.hCountersDev) {
+                fa.hostEnergy = h.hEnergyDev; fa.energySrc = h.energyBuf.p; fa.numEnergyHost = SNB_ENERGY_DOUBLES; fa.hostCounters = h.hCountersDev;
+                resultsStored = true;
+            }
             launchFinish(fa, st);
         }
     }
@@ -1229,9 +1260,10 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         if (splitRecip)
             CUDA_CHECK(cudaMemcpyAsync(h.hEnergyPme.p, h.energyPme.p, sizeof(double)*2*SNB_MAX_SLICES, cudaMemcpyDeviceToHost, st));
     }
-    else
+    else if (!resultsStored)
         CUDA_CHECK(cudaMemcpyAsync(h.hEnergy.p, h.energyBuf.p, sizeof(double)*SNB_ENERGY_DOUBLES, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
+    if (!resultsStored)
+        CUDA_CHECK(cudaMemcpyAsync(h.hCounters.p, h.counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, st));
     h.lastDirect = da;
 }
 
@@ -1273,7 +1305,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     key.flags = flags; key.hostPositions = in.hostPositions; key.pbcMode = in.pbcMode;
     for (int k = 0; k < 3; k++) key.cellDim[k] = h.cellDim[k];
     key.numCells = h.numCells;
-    key.fusedSort = h.fusedSort;
+    key.fusedSort = h.fusedSort; key.beginKernel = h.beginKernel;
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     key.maxChunks = h.maxChunks;
     key.share = h.comm ? rank0Share(h) : 0.0;
@@ -1437,7 +1469,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++)
             launches += h.deterministic ? 5 : 4;
     if (includeForces || h.comm) launches += 1+(h.comm && includeForces ? 1 : 0);
-    if (posqDev && !(h.fusedSortUsed && !h.comm)) launches += 1;     // position conversion (inside the fused sort kernel otherwise)
+    if (posqDev || h.beginKernelUsed) launches += 1;     // position conversion, or k_begin (which includes it)
     h.countersOut[2] = launches;
     return true;
 }

@@ -5,6 +5,13 @@
 
 __global__ void k_finish(FinishArgs a) {
     int i = blockIdx.x*blockDim.x+threadIdx.x;
+    if (a.hostEnergy) {
+        // every producer of energies (direct space, exceptions, reciprocal space) was joined before this kernel
+        for (int k = i; k < a.numEnergyHost; k += gridDim.x*blockDim.x)
+            a.hostEnergy[k] = a.energySrc[k];
+        if (i < 8)
+            a.hostCounters[i] = a.counters[i];
+    }
     if (a.reduceOut && i < a.numEnergy) {
         const double v = i == a.overflowSlot ? (double) a.counters[2] : a.energyIn[i];
         a.reduceOut[3*(size_t) a.numAtoms+i] = __double2ll_rn(v*SNB_FORCE_SCALE_D);
@@ -68,6 +75,39 @@ __global__ void k_convertPositions(const void* posq, const float4* correction, c
     }
     const int i = atomIndex ? atomIndex[t] : t;
     posd[3*i] = x; posd[3*i+1] = y; posd[3*i+2] = z;
+}
+
+__global__ void __launch_bounds__(256) k_begin(BeginArgs a) {
+    const size_t tid = blockIdx.x*(size_t) blockDim.x+threadIdx.x, nThreads = gridDim.x*(size_t) blockDim.x;
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < a.stepWords; k += blockDim.x)
+            a.stepDev[k] = ((const volatile int*) a.stepHost)[k];
+    for (size_t k = tid; k < a.zeroWords; k += nThreads)
+        a.zero[k] = 0ull;
+    if (a.posq)
+        for (size_t t = tid; t < (size_t) a.numAtoms; t += nThreads) {
+            double x, y, z;
+            if (a.positionsDouble) {
+                const double4 p = ((const double4*) a.posq)[t];
+                x = p.x; y = p.y; z = p.z;
+            }
+            else {
+                const float4 p = ((const float4*) a.posq)[t];
+                x = p.x; y = p.y; z = p.z;
+                if (a.correction) {
+                    const float4 c = a.correction[t];
+                    x += (double) c.x; y += (double) c.y; z += (double) c.z;
+                }
+            }
+            const size_t i = a.atomIndex ? (size_t) a.atomIndex[t] : t;
+            a.posd[3*i] = x; a.posd[3*i+1] = y; a.posd[3*i+2] = z;
+        }
+}
+
+void launchBegin(const BeginArgs& a, cudaStream_t stream) {
+    const size_t work = a.zeroWords/4 > (size_t) a.numAtoms ? a.zeroWords/4 : (size_t) a.numAtoms;
+    const unsigned grid = (unsigned) ((work+255)/256 > 0 ? (work+255)/256 : 1);
+    k_begin<<<grid, 256, 0, stream>>>(a);
 }
 
 void launchFinish(const FinishArgs& a, cudaStream_t stream) {

@@ -55,13 +55,8 @@ struct SortArgs {
     float4* wrapImage;      // [N] periodic image (whole box vectors) every atom was wrapped by at the last rebuild
     // the sort as one cooperative kernel (k_sortFused: periodic, no list reuse, at most SORT_FUSED_MAX_CELLS cells)
     int fused, numSMs;
-    const void* posqIn;     // device-resident caller: positions converted inside the fused kernel (null: posd is ready)
-    const float4* posqInCorrection;
-    const int* posqInIndex;
-    int posqInDouble;
-    double* posdOut;
 };
-#define SORT_FUSED_MAX_CELLS 8192
+#define SORT_FUSED_MAX_CELLS 4096       /* measured on B200: 648 / 3 000 atoms +5 % / +4 % evaluations/s, 23 558 atoms (5 832 cells) -1.5 % */
 // usedFused (optional): whether the fused kernel took the launch; the error is the cooperative launch's (the caller may
 // fall back to the separate kernels by clearing `fused`)
 cudaError_t launchSort(const SortArgs& a, cudaStream_t stream, bool* usedFused = nullptr);
@@ -207,6 +202,12 @@ struct FinishArgs {
     const int* counters;            // list-build counters; [2] = overflow flag
     const double* energyIn;         // multi-GPU: the slice-energy table + flags, appended to reduceOut in 2^32 fixed point
     int numEnergy, overflowSlot;    // entries of energyIn; which of them takes counters[2] instead
+    // single GPU: the kernel itself stores the energy table and the eight list counters into the host's pinned mirrors
+    // (mapped memory; 2.5 KB of posted writes) instead of two device->host copies behind it
+    double* hostEnergy;             // device-side address of the pinned energy mirror, or null
+    const double* energySrc;
+    int numEnergyHost;
+    int* hostCounters;
 };
 // after the force reduction (root only): reduced [3][N] fixed-point forces -> the caller's layout
 // overflow: the reduced list-overflow flag (device pointer, nonzero = the pass is being discarded) or null
@@ -217,6 +218,23 @@ void launchFinish(const FinishArgs& a, cudaStream_t stream);
 // device positions -> the double array in original atom order.  posq: float4 (or double4 when positionsDouble) per slot;
 // correction: float4 per slot added to a float4 position (OpenMM's mixed precision), or null; atomIndex: original index of
 // the atom in every slot, or null when the slots are in original order
+// First kernel of a single-GPU evaluation: the step's parameters from the host's pinned mirror (mapped memory) to their device
+// copy, every accumulator of the evaluation zeroed, and the positions of a device-resident caller converted -- one launch
+// for what used to be a copy, a memset and a kernel at the head of every chain of the evaluation.
+struct BeginArgs {
+    const int* stepHost;            // device-side address of the pinned StepParams
+    int* stepDev;
+    int stepWords;                  // sizeof(StepParams)/4
+    unsigned long long* zero;       // the block of accumulators (forces, energies, counters)
+    size_t zeroWords;               // its size in 8-byte words
+    const void* posq;               // device-resident positions (null: the host's are already in posd)
+    const float4* correction;
+    const int* atomIndex;
+    int positionsDouble;
+    double* posd;
+    int numAtoms;
+};
+void launchBegin(const BeginArgs& a, cudaStream_t stream);
 void launchConvertPositions(const void* posq, const void* correction, const int* atomIndex, int positionsDouble, double* posd, int numAtoms, cudaStream_t stream);
 
 #endif

@@ -29,6 +29,7 @@
 #define SNB_FORCE_SCALE_D 4294967296.0
 #define SNB_NARROW_MAX_EXTENT 1.0f         /* nm: largest block half extent for which the narrow cutoff band is valid */
 #define SNB_COUNTER_REBUILD 6               /* counters[]: nonzero = this evaluation rebuilds the sorted order and the tile list (list reuse on) */
+#define SNB_COUNTER_BARRIER 7               /* counters[]: arrive count of the fused sort kernel's grid-wide barriers */
 #define SNB_COUNTER_MAX_EXTENT 5            /* counters[]: float bits of the largest block half extent of this evaluation */
 
 enum { PBC_NONE = 0, PBC_SHIFT = 1, PBC_PAIR_ORTHO = 2, PBC_PAIR_TRICLINIC = 3 };

@@ -342,48 +342,46 @@ __global__ void k_blockBounds(SortArgs a) {
 // (list -> direct space, and reciprocal space).  Here they are the phases of one kernel, separated by grid-wide barriers
 // (cooperative launch: every CTA is resident), and the exclusive scan of the cell counts is done by every CTA for itself
 // in shared memory (at most SORT_FUSED_MAX_CELLS cells), which saves the barrier around a one-CTA scan:
-//   A  position conversion (device-resident callers), cell of every atom, slot by atomic counter     | barrier
+//   A  cell of every atom, slot by atomic counter                                                     | barrier
 //   B  scan of the counts -> shared memory; C  scatter into the cell segments, sorted range of every cell | barrier
 //   D  rank inside the cell (deterministic order), counters re-zeroed                                 | barrier
 //   E  blocks of 32: boxes, centres, local coordinates (blockBoundsWarp).
 // Periodic methods without list reuse; everything else takes the separate kernels.
 #define SORT_FUSED_THREADS 256
 
+// Grid-wide barrier of the fused kernel: one arrive counter (counters[SNB_COUNTER_BARRIER], zeroed with the rest of the
+// evaluation's accumulators before the kernel starts), barrier number n is passed when the count reaches n * gridDim.x.
+// The cooperative launch guarantees that every CTA is resident, so the spin cannot starve one.  (cooperative_groups'
+// grid.sync() measured 4-5 us per barrier here; this one is an atomic and a polled line in the L2.)
+__device__ __forceinline__ void gridBarrier(int* counter, int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1);
+        int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(SORT_FUSED_THREADS) k_sortFused(SortArgs a) {
     extern __shared__ int sStart[];                     // [numCells+1] exclusive scan of the cell counts
     __shared__ int warpSums[32];
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    int* const barrier = a.counters+SNB_COUNTER_BARRIER;
+    const int numCtas = (int) gridDim.x;
     const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
     // ---- A
     for (int t = tid; t < a.numAtoms; t += nThreads) {
-        int i = t;
-        double x, y, z;
-        if (a.posqIn) {
-            // k_convertPositions (finish.cu) folded in: the caller's float4 (+ correction) or double4 positions, in its order
-            if (a.posqInDouble) {
-                const double4 p = ((const double4*) a.posqIn)[t];
-                x = p.x; y = p.y; z = p.z;
-            }
-            else {
-                const float4 p = ((const float4*) a.posqIn)[t];
-                x = p.x; y = p.y; z = p.z;
-                if (a.posqInCorrection) {
-                    const float4 c = a.posqInCorrection[t];
-                    x += (double) c.x; y += (double) c.y; z += (double) c.z;
-                }
-            }
-            if (a.posqInIndex)
-                i = a.posqInIndex[t];
-            a.posdOut[3*i] = x; a.posdOut[3*i+1] = y; a.posdOut[3*i+2] = z;
-        }
-        else {
-            x = a.posd[3*i]; y = a.posd[3*i+1]; z = a.posd[3*i+2];
-        }
+        const int i = t;
+        const double x = a.posd[3*i], y = a.posd[3*i+1], z = a.posd[3*i+2];
         const int rank = cellRankOf(a, x, y, z);
         a.atomCell[i] = rank;
         a.atomSlot[i] = atomicAdd(&a.cellCount[rank], 1);
     }
-    grid.sync();
+    gridBarrier(barrier, 1*numCtas);
     // ---- B (every CTA for itself)
     {
         // the counts arrive coalesced; every thread then owns a contiguous run of cells
@@ -418,7 +416,7 @@ __global__ void __launch_bounds__(SORT_FUSED_THREADS) k_sortFused(SortArgs a) {
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i <= a.numCells; i += blockDim.x)
             a.cellStart[i] = sStart[i];
-    grid.sync();
+    gridBarrier(barrier, 2*numCtas);
     // ---- D
     for (int t = tid; t < a.numAtoms; t += nThreads) {
         const int c = __ldcg(a.atomCell+t), s = sStart[c], e = sStart[c+1];
@@ -429,7 +427,7 @@ __global__ void __launch_bounds__(SORT_FUSED_THREADS) k_sortFused(SortArgs a) {
     }
     for (int i = tid; i < a.numCells; i += nThreads)
         a.cellCount[i] = 0;         // ready for the next evaluation
-    grid.sync();
+    gridBarrier(barrier, 3*numCtas);
     // ---- E
     const int lane = threadIdx.x&31;
     for (int warp = tid>>5; warp < a.numBlocks; warp += nThreads>>5)

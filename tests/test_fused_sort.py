@@ -2,7 +2,8 @@
 
 The sorted order is a function of the positions only (cells along the Hilbert curve, atoms of a cell by index), so both
 ways must produce the SAME order, hence the same tile list and -- forces being accumulated in fixed point -- bit-identical
-direct-space forces; the fused kernel also takes over the position conversion of a device-resident caller.
+direct-space forces.  It takes the launch for periodic systems of up to SORT_FUSED_MAX_CELLS = 4 096 cells (16 384 atoms) without
+list reuse; above that the separate kernels are as fast (measured at DHFR size: 1.5 % faster).
 SNB_FUSED_SORT=0 (read when a handle is created) selects the separate kernels; counter [0] tells which way it went."""
 import os
 
@@ -44,7 +45,7 @@ WORKLOADS = {
     "water_pme": lambda: systems.water_box(),
     "water_cutoff": lambda: systems.water_box(method=mm.SlicedNonbondedForce.CutoffPeriodic),
     "fep_ljpme": lambda: systems.fep_ligand(),
-    "dhfr": lambda: systems.dhfr_like(),
+    "small_mixed": lambda: systems.small_mixed(n_side=7, solute_sites=16),
 }
 
 
@@ -76,9 +77,9 @@ def test_fused_sort_matches_separate_kernels(name, props):
     assert abs(e_f-e_s) <= tol*max(1.0, np.abs(s_s).sum())
 
 
-def test_fused_sort_converts_device_positions():
+def test_fused_sort_on_the_device_entry_point():
     import torch
-    w = systems.dhfr_like()
+    w = systems.fep_ligand()
     n = w.num_particles
     posq = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
     posq[:, :3] = torch.from_numpy(w.positions.astype(np.float32)).cuda()
@@ -96,16 +97,59 @@ def test_fused_sort_converts_device_positions():
             if rep:
                 assert np.array_equal(got[0], out[fused][0]), "replay differs from the eager evaluation"
             out[fused] = got
-        # one launch for the sort and none for the conversion, against five and one
+        # one launch for the sort against five
         launches = kernel.getCounters()[2]
         out[fused] += (launches,)
     assert np.array_equal(out[True][0], out[False][0]), "forces differ between the fused sort and the separate kernels"
     assert abs(out[True][1]-out[False][1]) <= 1e-12*max(1.0, abs(out[False][1]))
-    assert out[False][2]-out[True][2] == 5
+    assert out[False][2]-out[True][2] == 4
 
 
-def test_list_reuse_and_nonperiodic_keep_the_separate_kernels():
+def test_list_reuse_and_large_systems_keep_the_separate_kernels():
     w = systems.water_box()
     ctx, kernel = _context(w, True, {"ListSkin": "0.05"})
     _run(ctx, kernel, w.num_particles)
     assert kernel.getCounters()[0] == 0
+    w = systems.dhfr_like()             # 5 832 cells
+    ctx, kernel = _context(w, True)
+    _run(ctx, kernel, w.num_particles)
+    assert kernel.getCounters()[0] == 0
+
+
+@pytest.mark.parametrize("entry", ["host", "device"])
+def test_begin_kernel_matches_copy_memset_convert(entry):
+    """k_begin (parameters from the pinned mirror, accumulators zeroed, positions converted: one launch) against the copy,
+    memset and conversion kernel it replaces (SNB_BEGIN_KERNEL=0), and k_finish's own stores of the energies / counters
+    against the two device->host copies (SNB_HOST_RESULTS=0)."""
+    import torch
+    w = systems.small_mixed(n_side=8, solute_sites=20, scaling=[("lam", 0.5, 0, 1, True, True)], derivatives=["lam"])
+    n = w.num_particles
+    results = []
+    for begin, host_results in (("1", "1"), ("0", "0")):
+        os.environ["SNB_BEGIN_KERNEL"], os.environ["SNB_HOST_RESULTS"] = begin, host_results
+        try:
+            ctx, kernel = _context(w, True, {"DeterministicForces": "true"})
+        finally:
+            del os.environ["SNB_BEGIN_KERNEL"], os.environ["SNB_HOST_RESULTS"]
+        for lam in (0.5, 0.25, 0.25):       # eager, new parameters (captured), replayed
+            ctx.setParameter("lam", lam)
+            if entry == "host":
+                e, f, slices = _run(ctx, kernel, n)
+            else:
+                posq = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+                posq[:, :3] = torch.from_numpy(w.positions.astype(np.float32)).cuda()
+                box = np.ascontiguousarray(w.box, dtype=np.float64).reshape(9)
+                params = np.array([ctx.getParameter(name) for name in kernel.globalNames], dtype=np.float64)
+                acc = torch.zeros((3, n), dtype=torch.int64, device="cuda")
+                kernel.executeDevice(posq.data_ptr(), box, params, _abi.EXECUTE_ALL, acc.data_ptr())
+                torch.cuda.synchronize()
+                e, slices, _ = kernel.readEnergies(_abi.EXECUTE_ALL)
+                f = acc.cpu().numpy().T/2.0**32
+            results.append((begin, lam, e, f, slices.copy(), kernel.getCounters()[1]))
+    half = len(results)//2
+    for new, old in zip(results[:half], results[half:]):
+        assert new[1] == old[1]
+        assert np.array_equal(new[3], old[3]), "forces differ (lambda %g)" % new[1]
+        assert abs(new[2]-old[2]) <= 1e-12*max(1.0, abs(old[2]))
+        assert np.allclose(new[4], old[4], rtol=0, atol=1e-12*max(1.0, np.abs(old[4]).max()))
+        assert new[5] == old[5] and new[5] > 0      # the list length came back through k_finish's own store
