@@ -177,7 +177,7 @@ struct PmeGrid {
 // same nodes with the same arguments (the box and the lambdas travel through StepParams in device
 // memory), so the second one onwards replays a captured CUDA graph.
 struct GraphKey {
-    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast, fusedSort, beginKernel;
+    int flags, hostPositions, pbcMode, cellDim[3], numCells, needEnergy, broadcast, fusedSort, beginKernel, compactSort;
     size_t maxChunks;
     const void *posqDev, *forcesFixedOut, *jList, *hostPos;
     const void *posqCorrection, *atomIndex;     // snb_execute_device_ordered: the caller's atom order
@@ -240,6 +240,7 @@ struct snb_handle {
     int fusedSort = 1;          // the sort as one cooperative kernel where it applies (SNB_FUSED_SORT=0: separate kernels); cleared if its launch fails
     bool fusedSortUsed = false; // the last enqueueStep launched it
     bool fusedSortFailed = false;
+    int compactSort = 1;        // sort in three kernels instead of five where it applies (SNB_COMPACT_SORT=0: five)
     int beginKernel = 1;        // k_begin instead of copy + memset + conversion kernel (SNB_BEGIN_KERNEL=0: those three)
     bool beginKernelUsed = false;
     const int* stepHDev = nullptr;
@@ -249,6 +250,7 @@ struct snb_handle {
     DevBuf<double> posd, paramsD, exception14, extent, energyBuf, forcesOutD;
     DevBuf<float4> params4, posqLocal, sparams, blockExt, posqIn, octetCenter, octetExt, blockCenter;
     DevBuf<double4> posqLocalD, sparamsD;
+    DevBuf<int> slotCell;
     DevBuf<int> subsetD, cellRank, cellCount, cellStart, atomCell, atomSlot, sortedAtom, sortedPos,
                 exclStart, exclList, is14D, counters, cellScratch, tileSum;
     DevBuf<int2> exceptionAtomsD, jList, cellRange;
@@ -569,15 +571,23 @@ snb_handle* createHandle(const snb_desc& d) {
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, h.device));
         h.numSMs = prop.multiProcessorCount;
-        CUDA_CHECK(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&h.pmeStream, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&h.bondedStream, cudaStreamNonBlocking));
+        // Stream priorities (SNB_STREAM_PRIORITY: 0 none [default], 1 reciprocal space + exceptions first, 2 the list /
+        // direct-space stream first).  The kernels of the main stream fill the GPU for most of the evaluation (the direct-space
+        // kernel takes every register of an SM); with equal priorities the short kernels of reciprocal space queue behind
+        // their CTAs and the two chains run one after the other rather than side by side.
+        int prioLow = 0, prioHigh = 0, mode = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+        if (const char* env = getenv("SNB_STREAM_PRIORITY")) mode = atoi(env);
+        CUDA_CHECK(cudaStreamCreateWithPriority(&h.stream, cudaStreamNonBlocking, mode == 2 ? prioHigh : prioLow));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&h.pmeStream, cudaStreamNonBlocking, mode == 1 ? prioHigh : prioLow));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&h.bondedStream, cudaStreamNonBlocking, mode == 1 ? prioHigh : prioLow));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evInputs, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&h.evBondedDone, cudaEventDisableTiming));
         h.useGraph = getenv("SNB_NO_GRAPH") == nullptr;
         if (const char* env = getenv("SNB_FUSED_SORT")) h.fusedSort = atoi(env) != 0;
         if (const char* env = getenv("SNB_HOST_RESULTS")) h.hostResults = atoi(env) != 0;
         if (const char* env = getenv("SNB_BEGIN_KERNEL")) h.beginKernel = atoi(env) != 0;
+        if (const char* env = getenv("SNB_COMPACT_SORT")) h.compactSort = atoi(env) != 0;
         h.stepD.alloc(1);
         h.stepH.alloc(1);
         memset(h.stepH.p, 0, sizeof(StepParams));
@@ -684,7 +694,7 @@ snb_handle* createHandle(const snb_desc& d) {
         h.subsetD.alloc(h.N);
         h.exception14.alloc(3*(size_t) h.X);
         uploadBaseParameters(h);
-        h.atomCell.alloc(h.N); h.atomSlot.alloc(h.N); h.cellScratch.alloc(h.N);
+        h.atomCell.alloc(h.N); h.atomSlot.alloc(h.N); h.cellScratch.alloc(h.N); h.slotCell.alloc(h.N);
         h.sortedAtom.alloc(h.NP); h.sortedPos.alloc(h.N);
         h.posqLocal.alloc(h.NP); h.sparams.alloc(h.NP);
         if (h.doublePrecision) { h.posqLocalD.alloc(h.NP); h.sparamsD.alloc(h.NP); }
@@ -998,7 +1008,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
         sa.reuse = h.skinNow > 0; sa.posRef = h.posRef.p; sa.wrapImage = h.wrapImage.p;
-        sa.fused = h.fusedSort; sa.numSMs = h.numSMs;
+        sa.fused = h.fusedSort && !h.comm; sa.numSMs = h.numSMs;     // (the cooperative kernel stays out of multi-GPU evaluations: untested beside NCCL's kernels) sa.compact = h.compactSort; sa.slotCell = h.slotCell.p;
     }
     // single GPU: the copy of the step's parameters, the memset of the accumulators and the position conversion are ONE
     // kernel (k_begin, finish.cu) -- three graph nodes fewer at the head of every chain of the evaluation
@@ -1305,7 +1315,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     key.flags = flags; key.hostPositions = in.hostPositions; key.pbcMode = in.pbcMode;
     for (int k = 0; k < 3; k++) key.cellDim[k] = h.cellDim[k];
     key.numCells = h.numCells;
-    key.fusedSort = h.fusedSort; key.beginKernel = h.beginKernel;
+    key.fusedSort = h.fusedSort; key.beginKernel = h.beginKernel; key.compactSort = h.compactSort;
     key.needEnergy = (flags&SNB_INCLUDE_ENERGY) || !h.derivativeParams.empty();
     key.maxChunks = h.maxChunks;
     key.share = h.comm ? rank0Share(h) : 0.0;
@@ -1463,7 +1473,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     h.countersOut[5] = includeDirect && h.packedLaunched ? 1 : 0;
     // kernels of THIS library launched by the evaluation (cuFFT's own kernels are not counted)
     long long launches = 0;
-    if (includeDirect) launches += (h.fusedSortUsed ? 1 : (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0))+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
+    if (includeDirect) launches += (h.fusedSortUsed ? 1 : (h.compactSort && periodic && !(h.skinNow > 0) && h.numCells <= SORT_SMEM_MAX_CELLS) ? 3 : (periodic ? 5 : 6)+(h.numCells > 16384 ? 2 : 0))+1+1+(h.X > 0 ? 1 : 0);    // sort, list, direct, bonded
     if (includeRecip && h.method == SNB_EWALD && h.rank == 0) launches += 2;    // structure factors, forces
     if (includeRecip && pmeFamily && h.rank == 0)      // spread (+ finish or fold), convolution, combine, interpolate
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++)

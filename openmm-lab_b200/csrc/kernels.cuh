@@ -55,7 +55,10 @@ struct SortArgs {
     float4* wrapImage;      // [N] periodic image (whole box vectors) every atom was wrapped by at the last rebuild
     // the sort as one cooperative kernel (k_sortFused: periodic, no list reuse, at most SORT_FUSED_MAX_CELLS cells)
     int fused, numSMs;
+    int compact;            // three kernels instead of five where it applies (periodic, no list reuse, <= SORT_SMEM_MAX_CELLS cells)
+    int* slotCell;          // [N] cell (rank along the curve) of every slot of the scattered order
 };
+#define SORT_SMEM_MAX_CELLS 8192        /* the scan of the cell counts fits every CTA's shared memory */
 #define SORT_FUSED_MAX_CELLS 4096       /* measured on B200: 648 / 3 000 atoms +5 % / +4 % evaluations/s, 23 558 atoms (5 832 cells) -1.5 % */
 // usedFused (optional): whether the fused kernel took the launch; the error is the cooperative launch's (the caller may
 // fall back to the separate kernels by clearing `fused`)

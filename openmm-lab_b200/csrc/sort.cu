@@ -231,9 +231,50 @@ __global__ void k_rankInCell(SortArgs a) {
 // binning), the block centre is the middle of the axis-aligned bounding box, and every atom
 // stores its offset from that centre in single precision: |offset| < ~1 nm, so the absolute
 // coordinate error is ~3e-8 nm whatever the size of the system.
-__device__ __forceinline__ void blockBoundsWarp(const SortArgs& a, const int warp, const int lane) {
+// The atom of sorted slot k, found inside its cell: the slot's rank r in the cell's segment -> the entry with exactly r
+// smaller ones (entries are distinct atom indices; the scatter left them in the order of the atomic counter).  O(n^2) loads
+// for a cell of n atoms, all from one or two cache lines: n is ~4 on average (periodic systems only: the cells tile the box).
+__device__ __forceinline__ int atomOfSlot(const SortArgs& a, const int k) {
+    const int c = a.slotCell[k], s = a.cellStart[c], e = a.cellStart[c+1], r = k-s, n = e-s;
+    int atom = -1;
+    if (n <= 8) {
+        // the usual case: the cell's entries in registers (eight independent loads in flight), 64 compares
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            v[j] = j < n ? a.cellScratch[s+j] : 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int smaller = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                smaller += v[q] < v[j];
+            if (smaller == r && j < n)
+                atom = v[j];
+        }
+        return atom;
+    }
+    for (int m = s; m < e; m++) {
+        const int v = a.cellScratch[m];
+        int smaller = 0;
+        for (int m2 = s; m2 < e; m2++)
+            smaller += a.cellScratch[m2] < v;
+        if (smaller == r)
+            atom = v;
+    }
+    return atom;
+}
+
+// RANK: the sorted order is settled here (k_boundsRank, k_sortFused) instead of by a k_rankInCell pass before
+template <bool RANK> __device__ __forceinline__ void blockBoundsWarp(const SortArgs& a, const int warp, const int lane) {
     int k = warp*SNB_BLOCK+lane;
-    int atom = a.sortedAtom[k];
+    int atom;
+    if (RANK) {
+        atom = k < a.numAtoms ? atomOfSlot(a, k) : -1;
+        a.sortedAtom[k] = atom;
+    }
+    else
+        atom = a.sortedAtom[k];
     double p[3] = {0, 0, 0};
     float4 prm = make_float4(0.f, 0.f, 0.f, 0.f);
     if (atom >= 0) {
@@ -333,19 +374,19 @@ __device__ __forceinline__ void blockBoundsWarp(const SortArgs& a, const int war
 __global__ void k_blockBounds(SortArgs a) {
     const int warp = (blockIdx.x*blockDim.x+threadIdx.x)>>5, lane = threadIdx.x&31;
     if (warp < a.numBlocks)
-        blockBoundsWarp(a, warp, lane);
+        blockBoundsWarp<false>(a, warp, lane);
 }
 
 // ---- 5. the whole sort as ONE cooperative kernel (small and medium systems) ---------------------------------
 // Below ~100 000 atoms every kernel above runs for 3-5 us of which most is launch ramp and one chain of dependent memory
 // accesses, and the six of them (with the position conversion) are the head of BOTH critical chains of an evaluation
-// (list -> direct space, and reciprocal space).  Here they are the phases of one kernel, separated by grid-wide barriers
+// (list -> direct space, and reciprocal space).  Here they are the phases of one kernel, separated by two grid-wide barriers
 // (cooperative launch: every CTA is resident), and the exclusive scan of the cell counts is done by every CTA for itself
 // in shared memory (at most SORT_FUSED_MAX_CELLS cells), which saves the barrier around a one-CTA scan:
 //   A  cell of every atom, slot by atomic counter                                                     | barrier
 //   B  scan of the counts -> shared memory; C  scatter into the cell segments, sorted range of every cell | barrier
-//   D  rank inside the cell (deterministic order), counters re-zeroed                                 | barrier
-//   E  blocks of 32: boxes, centres, local coordinates (blockBoundsWarp).
+//   D  the atom of every sorted slot (rank inside its cell: deterministic order); E  blocks of 32: boxes, centres, local
+//      coordinates (blockBoundsWarp); counters re-zeroed.
 // Periodic methods without list reuse; everything else takes the separate kernels.
 #define SORT_FUSED_THREADS 256
 
@@ -367,8 +408,52 @@ __device__ __forceinline__ void gridBarrier(int* counter, int target) {
     __syncthreads();
 }
 
+// Exclusive scan of the cell counts into shared memory, by the whole CTA (sStart[numCells] = total): the counts arrive
+// coalesced, every thread then owns a contiguous run of cells.
+__device__ __forceinline__ void scanCountsShared(const int* cellCount, const int numCells, int* sStart, int* warpSums) {
+    // (loads first, stores after, four int4 per thread in flight: issued one at a time behind their own shared-memory
+    // stores the 23 loads of a DHFR-size grid were 14 us of latency -- ncu, gpurun r3e)
+    const int n4 = numCells>>2;
+    const int4* c4 = (const int4*) cellCount;
+    int4* s4 = (int4*) sStart;
+    for (int base = 0; base < n4; base += 4*(int) blockDim.x) {
+        int4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base+u*(int) blockDim.x+(int) threadIdx.x;
+            v[u] = idx < n4 ? __ldcg(c4+idx) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base+u*(int) blockDim.x+(int) threadIdx.x;
+            if (idx < n4)
+                s4[idx] = v[u];
+        }
+    }
+    for (int i = 4*n4+(int) threadIdx.x; i < numCells; i += blockDim.x)
+        sStart[i] = __ldcg(cellCount+i);
+    __syncthreads();
+    const int per = (numCells+(int) blockDim.x-1)/(int) blockDim.x;
+    const int first = min(numCells, (int) threadIdx.x*per), last = min(numCells, first+per);
+    int sum = 0;
+#pragma unroll 8
+    for (int i = first; i < last; i++)
+        sum += sStart[i];
+    int total;
+    int running = blockExclusiveScan(sum, warpSums, total);
+#pragma unroll 8
+    for (int i = first; i < last; i++) {
+        const int v = sStart[i];
+        sStart[i] = running;
+        running += v;
+    }
+    if (threadIdx.x == 0)
+        sStart[numCells] = total;
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(SORT_FUSED_THREADS) k_sortFused(SortArgs a) {
-    extern __shared__ int sStart[];                     // [numCells+1] exclusive scan of the cell counts
+    extern __shared__ __align__(16) int sStart[];       // [numCells+1] exclusive scan of the cell counts
     __shared__ int warpSums[32];
     int* const barrier = a.counters+SNB_COUNTER_BARRIER;
     const int numCtas = (int) gridDim.x;
@@ -382,56 +467,60 @@ __global__ void __launch_bounds__(SORT_FUSED_THREADS) k_sortFused(SortArgs a) {
         a.atomSlot[i] = atomicAdd(&a.cellCount[rank], 1);
     }
     gridBarrier(barrier, 1*numCtas);
-    // ---- B (every CTA for itself)
-    {
-        // the counts arrive coalesced; every thread then owns a contiguous run of cells
-        for (int i = threadIdx.x; i < a.numCells; i += blockDim.x)
-            sStart[i] = __ldcg(a.cellCount+i);
-        __syncthreads();
-        const int per = (a.numCells+(int) blockDim.x-1)/(int) blockDim.x;
-        const int first = min(a.numCells, (int) threadIdx.x*per), last = min(a.numCells, first+per);
-        int sum = 0;
-        for (int i = first; i < last; i++)
-            sum += sStart[i];
-        int total;
-        int running = blockExclusiveScan(sum, warpSums, total);
-        for (int i = first; i < last; i++) {
-            const int v = sStart[i];
-            sStart[i] = running;
-            running += v;
-        }
-        if (threadIdx.x == 0)
-            sStart[a.numCells] = total;
-        __syncthreads();
+    // ---- B (every CTA for itself) + C
+    scanCountsShared(a.cellCount, a.numCells, sStart, warpSums);
+    for (int t = tid; t < a.numAtoms; t += nThreads) {
+        const int c = __ldcg(a.atomCell+t), pos = sStart[c]+__ldcg(a.atomSlot+t);
+        a.cellScratch[pos] = t;
+        a.slotCell[pos] = c;
     }
-    // ---- C
-    for (int t = tid; t < a.numAtoms; t += nThreads)
-        a.cellScratch[sStart[__ldcg(a.atomCell+t)]+__ldcg(a.atomSlot+t)] = t;
     for (int i = tid; i < a.numCells; i += nThreads) {
         const int r = a.cellRank[i];
         a.cellRange[i] = make_int2(sStart[r], sStart[r+1]);
     }
-    for (int i = tid; i < a.paddedAtoms-a.numAtoms; i += nThreads)
-        a.sortedAtom[a.numAtoms+i] = -1;
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i <= a.numCells; i += blockDim.x)
-            a.cellStart[i] = sStart[i];
+    for (int i = tid; i <= a.numCells; i += nThreads)
+        a.cellStart[i] = sStart[i];
     gridBarrier(barrier, 2*numCtas);
-    // ---- D
-    for (int t = tid; t < a.numAtoms; t += nThreads) {
-        const int c = __ldcg(a.atomCell+t), s = sStart[c], e = sStart[c+1];
-        int rank = 0;
-        for (int k = s; k < e; k++)
-            rank += __ldcg(a.cellScratch+k) < t;
-        a.sortedAtom[s+rank] = t;
-    }
+    // ---- D + E (every CTA is past its scan: the counters can be re-zeroed for the next evaluation)
     for (int i = tid; i < a.numCells; i += nThreads)
-        a.cellCount[i] = 0;         // ready for the next evaluation
-    gridBarrier(barrier, 3*numCtas);
-    // ---- E
+        a.cellCount[i] = 0;
     const int lane = threadIdx.x&31;
     for (int warp = tid>>5; warp < a.numBlocks; warp += nThreads>>5)
-        blockBoundsWarp(a, warp, lane);
+        blockBoundsWarp<true>(a, warp, lane);
+}
+
+// ---- 6. the same three phases as three kernels (periodic systems of up to SORT_SMEM_MAX_CELLS cells, no list reuse):
+// k_assignCells -> k_scanScatter (scan in every CTA's shared memory + scatter) -> k_boundsRank (rank + block bounds),
+// against five with k_scanCells and k_rankInCell as kernels of their own.
+__global__ void __launch_bounds__(SORT_FUSED_THREADS) k_scanScatter(SortArgs a) {
+    extern __shared__ __align__(16) int sStart[];
+    __shared__ int warpSums[32];
+    const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
+    scanCountsShared(a.cellCount, a.numCells, sStart, warpSums);
+    for (int t = tid; t < a.numAtoms; t += nThreads) {
+        const int c = a.atomCell[t], pos = sStart[c]+a.atomSlot[t];
+        a.cellScratch[pos] = t;
+        a.slotCell[pos] = c;
+    }
+    for (int i = tid; i < a.numCells; i += nThreads) {
+        const int r = a.cellRank[i];
+        a.cellRange[i] = make_int2(sStart[r], sStart[r+1]);
+    }
+    for (int i = tid; i <= a.numCells; i += nThreads)
+        a.cellStart[i] = sStart[i];
+}
+
+__global__ void __launch_bounds__(SORT_FUSED_THREADS) k_boundsRank(SortArgs a) {
+    const int tid = blockIdx.x*blockDim.x+threadIdx.x, nThreads = gridDim.x*blockDim.x;
+    for (int i = tid; i < a.numCells; i += nThreads)
+        a.cellCount[i] = 0;
+    const int lane = threadIdx.x&31;
+    for (int warp = tid>>5; warp < a.numBlocks; warp += nThreads>>5)
+        blockBoundsWarp<true>(a, warp, lane);
+}
+
+static bool sortCompactApplies(const SortArgs& a) {
+    return a.compact && !a.reuse && a.periodic && a.numCells <= SORT_SMEM_MAX_CELLS && a.numAtoms > 0;
 }
 
 // Grid of the fused kernel if this is its case and it fits on the device (every CTA resident), else 0: the separate kernels.
@@ -467,6 +556,14 @@ cudaError_t launchSort(const SortArgs& a, cudaStream_t stream, bool* usedFused) 
         *usedFused = fused;
     if (fused)
         return fusedErr;
+    if (sortCompactApplies(a)) {
+        const int t = SORT_FUSED_THREADS;
+        const size_t smem = sizeof(int)*((size_t) a.numCells+1);
+        k_assignCells<<<(a.numAtoms+t-1)/t, t, 0, stream>>>(a);
+        k_scanScatter<<<(max(a.numAtoms, a.numCells+1)+t-1)/t, t, smem, stream>>>(a);
+        k_boundsRank<<<(a.numBlocks*32+t-1)/t, t, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     int threads = 256;
     int atomBlocks = (a.paddedAtoms+threads-1)/threads;
     const int* keep = a.reuse ? a.counters+SNB_COUNTER_REBUILD : nullptr;

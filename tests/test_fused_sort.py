@@ -97,12 +97,12 @@ def test_fused_sort_on_the_device_entry_point():
             if rep:
                 assert np.array_equal(got[0], out[fused][0]), "replay differs from the eager evaluation"
             out[fused] = got
-        # one launch for the sort against five
+        # one launch for the sort against three (k_assignCells, k_scanScatter, k_boundsRank)
         launches = kernel.getCounters()[2]
         out[fused] += (launches,)
     assert np.array_equal(out[True][0], out[False][0]), "forces differ between the fused sort and the separate kernels"
     assert abs(out[True][1]-out[False][1]) <= 1e-12*max(1.0, abs(out[False][1]))
-    assert out[False][2]-out[True][2] == 4
+    assert out[False][2]-out[True][2] == 2
 
 
 def test_list_reuse_and_large_systems_keep_the_separate_kernels():
@@ -153,3 +153,27 @@ def test_begin_kernel_matches_copy_memset_convert(entry):
         assert abs(new[2]-old[2]) <= 1e-12*max(1.0, abs(old[2]))
         assert np.allclose(new[4], old[4], rtol=0, atol=1e-12*max(1.0, np.abs(old[4]).max()))
         assert new[5] == old[5] and new[5] > 0      # the list length came back through k_finish's own store
+
+
+@pytest.mark.parametrize("name", ["dhfr", "water_pme"])
+def test_compact_sort_matches_the_five_kernels(name):
+    """k_assignCells -> k_scanScatter -> k_boundsRank (scan in shared memory, rank settled where the blocks are cut) against
+    the five kernels with k_scanCells and k_rankInCell as launches of their own (SNB_COMPACT_SORT=0): same order, same list,
+    bit-identical direct-space forces."""
+    w = systems.dhfr_like() if name == "dhfr" else systems.water_box()
+    n = w.num_particles
+    out = {}
+    for compact in ("1", "0"):
+        os.environ["SNB_COMPACT_SORT"] = compact
+        try:
+            ctx, kernel = _context(w, False)
+        finally:
+            del os.environ["SNB_COMPACT_SORT"]
+        for rep in range(3):
+            e, f, slices = _run(ctx, kernel, n, reciprocal=False)
+            assert kernel.getCounters()[0] == 0
+        out[compact] = (f, kernel.getCounters()[1], kernel.getCounters()[2], kernel.dumpPairs())
+    assert out["1"][1] == out["0"][1]
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.array_equal(out["1"][3], out["0"][3])
+    assert out["0"][2]-out["1"][2] == 2
