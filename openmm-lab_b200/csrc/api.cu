@@ -900,6 +900,8 @@ double rank0Share(const snb_handle& h) {
     return f0*(h.world-1)/(1.0-f0);
 }
 
+struct FusedSortRefused { std::string msg; };      // the cooperative launch of k_sortFused was refused (nothing has run): fall back
+
 struct StepInputs {
     const double* hostPos;      // host positions to copy from: the caller's own buffer when it is page-locked, else the pinned mirror
     const void* posqDev;        // device float4 positions, or null when the positions come from the host
@@ -1008,7 +1010,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         sa.sortedAtom = h.sortedAtom.p; sa.sortedPos = h.sortedPos.p; sa.posqLocal = h.posqLocal.p; sa.sparams = h.sparams.p;
         sa.blockCenter = h.blockCenter.p; sa.blockExt = h.blockExt.p; sa.octetCenter = h.octetCenter.p; sa.octetExt = h.octetExt.p;
         sa.reuse = h.skinNow > 0; sa.posRef = h.posRef.p; sa.wrapImage = h.wrapImage.p;
-        sa.fused = h.fusedSort && !h.comm; sa.numSMs = h.numSMs;     // (the cooperative kernel stays out of multi-GPU evaluations: untested beside NCCL's kernels) sa.compact = h.compactSort; sa.slotCell = h.slotCell.p;
+        // (the cooperative kernel stays out of multi-GPU evaluations: untested beside NCCL's kernels)
+        sa.fused = h.fusedSort && !h.comm; sa.numSMs = h.numSMs; sa.compact = h.compactSort; sa.slotCell = h.slotCell.p;
     }
     // single GPU: the copy of the step's parameters, the memset of the accumulators and the position conversion are ONE
     // kernel (k_begin, finish.cu) -- three graph nodes fewer at the head of every chain of the evaluation
@@ -1083,6 +1086,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         bool used = false;
         const cudaError_t err = launchSort(sa, st, &used);
         h.fusedSortUsed = used;
+        if (used && err != cudaSuccess)
+            throw FusedSortRefused{std::string("cudaLaunchCooperativeKernel(k_sortFused): ")+cudaGetErrorString(err)};
         CUDA_CHECK(err);
     }
     tm.mark(1);
@@ -1338,13 +1343,16 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
             try {
                 enqueueStep(h, in);
             }
+            catch (const FusedSortRefused&) {
+                cudaStreamEndCapture(st, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                graph = nullptr;
+                captureFailed = true;       // (the cooperative kernel is the one node kind this graph had not held before)
+            }
             catch (...) {
                 cudaStreamEndCapture(st, &graph);
                 if (graph) cudaGraphDestroy(graph);
-                if (!h.fusedSort)
-                    throw;
-                graph = nullptr;
-                captureFailed = true;       // (the cooperative kernel is the one node kind this graph had not held before)
+                throw;
             }
             if (!captureFailed) {
                 CUDA_CHECK(cudaStreamEndCapture(st, &graph));
@@ -1365,9 +1373,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
         try {
             enqueueStep(h, in);
         }
-        catch (...) {
-            if (!h.fusedSortUsed)
-                throw;
+        catch (const FusedSortRefused&) {
             captureFailed = true;           // the cooperative launch was refused: this evaluation again, with the separate kernels
         }
         h.graphKey = key;

@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(PME_THREADS) k_pmeInterpolate(PmeArgs a) {
         const int k = blockIdx.x*PME_ATOMS+threadIdx.x;
         PmeAtomD<R>& me = sAtom[threadIdx.x];
         me.subset = -1;
+        me.idx[0] = me.idx[1] = me.idx[2] = 0;      // (phase 2 gathers without a branch: a valid stencil for every slot)
         if (k < a.numAtoms) {
             const int atom = a.sortedAtom ? a.sortedAtom[k] : k;
             if (atom >= 0) {
@@ -291,36 +292,54 @@ __global__ void __launch_bounds__(PME_THREADS) k_pmeInterpolate(PmeArgs a) {
     const bool active = lane < ORDER*ORDER;
     const int iy = active ? lane/ORDER : 0, iz = active ? lane-iy*ORDER : 0;
     const size_t plane = (size_t) a.ny*a.nz, G = plane*a.nx;
-    for (int i = 0; i < PME_ATOMS_PER_WARP; i++) {
-        PmeAtomD<R>& at = sAtom[warp*PME_ATOMS_PER_WARP+i];
-        if (at.subset < 0)
-            continue;
-        R fx = 0, fy = 0, fz = 0;
-        if (active) {
+    // (the warp's atoms four at a time: their 20 gathers per lane are in flight together and the four reductions interleave --
+    // one atom at a time was eight L2 round trips and eight chains of shuffles in a row)
+    constexpr int BATCH = 4;
+    static_assert(PME_ATOMS_PER_WARP%BATCH == 0, "interpolation batches");
+    for (int i0 = 0; i0 < PME_ATOMS_PER_WARP; i0 += BATCH) {
+        R fx[BATCH], fy[BATCH], fz[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const PmeAtomD<R>& at = sAtom[warp*PME_ATOMS_PER_WARP+i0+u];
+            // no branch around the gathers (a guarded block per atom would serialise them again): an idle lane or an atom with
+            // nothing to do reads the stencil of grid point (0, 0, 0) of subset 0 and its result is dropped
+            const bool on = active && at.subset >= 0;
+            const int sub = max(at.subset, 0);
             int y = at.idx[1]+iy, z = at.idx[2]+iz;
             y -= y >= a.ny ? a.ny : 0;
             z -= z >= a.nz ? a.nz : 0;
-            const R* cell = (const R*) a.grid+(size_t) y*a.nz+z;
-            R s0 = 0, s1 = 0;               // sum_x theta_x * phi, sum_x dtheta_x * phi
+            const R* __restrict__ cell = (const R*) a.grid+sub*G+(size_t) y*a.nz+z;
+            R phi[ORDER];
 #pragma unroll
             for (int ix = 0; ix < ORDER; ix++) {
                 int x = at.idx[0]+ix;
                 x -= x >= a.nx ? a.nx : 0;
-                const R phi = cell[at.subset*G+x*plane];     // already lambda-combined for this subset (k_pmeCombine)
-                s0 += at.th[0][ix]*phi;
-                s1 += at.dth[0][ix]*phi;
+                phi[ix] = __ldg(cell+x*plane);          // already lambda-combined for this subset (k_pmeCombine)
             }
-            fx = s1*at.th[1][iy]*at.th[2][iz];
-            fy = s0*at.dth[1][iy]*at.th[2][iz];
-            fz = s0*at.th[1][iy]*at.dth[2][iz];
+            R s0 = 0, s1 = 0;               // sum_x theta_x * phi, sum_x dtheta_x * phi
+#pragma unroll
+            for (int ix = 0; ix < ORDER; ix++) {
+                s0 += at.th[0][ix]*phi[ix];
+                s1 += at.dth[0][ix]*phi[ix];
+            }
+            fx[u] = on ? s1*at.th[1][iy]*at.th[2][iz] : (R) 0;
+            fy[u] = on ? s0*at.dth[1][iy]*at.th[2][iz] : (R) 0;
+            fz[u] = on ? s0*at.th[1][iy]*at.dth[2][iz] : (R) 0;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
-        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                fx[u] += __shfl_xor_sync(0xffffffffu, fx[u], o);
+                fy[u] += __shfl_xor_sync(0xffffffffu, fy[u], o);
+                fz[u] += __shfl_xor_sync(0xffffffffu, fz[u], o);
+            }
         if (lane == 0) {
-            at.f[0] = fx; at.f[1] = fy; at.f[2] = fz;
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                PmeAtomD<R>& at = sAtom[warp*PME_ATOMS_PER_WARP+i0+u];
+                at.f[0] = fx[u]; at.f[1] = fy[u]; at.f[2] = fz[u];
+            }
         }
     }
     __syncthreads();
