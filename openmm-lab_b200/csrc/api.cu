@@ -240,6 +240,7 @@ struct snb_handle {
     int fusedSort = 1;          // the sort as one cooperative kernel where it applies (SNB_FUSED_SORT=0: separate kernels); cleared if its launch fails
     bool fusedSortUsed = false; // the last enqueueStep launched it
     bool fusedSortFailed = false;
+    int pmeFoldedLaunches = 0;  // reciprocal-space terms of the last enqueueStep whose interpolation did the lambda combination itself
     int compactSort = 1;        // sort in three kernels instead of five where it applies (SNB_COMPACT_SORT=0: five)
     int beginKernel = 1;        // k_begin instead of copy + memset + conversion kernel (SNB_BEGIN_KERNEL=0: those three)
     bool beginKernelUsed = false;
@@ -1081,6 +1082,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     DirectArgs da;
     memset(&da, 0, sizeof(da));
     h.fusedSortUsed = false;
+    h.pmeFoldedLaunches = 0;
     if (includeDirect) {
         Range sortRange("snb sort");
         bool used = false;
@@ -1128,7 +1130,10 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             if (h.doublePrecision) CUFFT_CHECK(cufftExecZ2D(g.inv, (cufftDoubleComplex*) g.cplx.p, (double*) g.real.p));
             else CUFFT_CHECK(cufftExecC2R(g.inv, (cufftComplex*) g.cplx.p, (float*) g.real.p));
             if (bricks && !noBrickInterp) CUDA_CHECK(launchPmeInterpolateBrick(pa, g.brickMap, ps));
-            else launchPmeInterpolate(pa, ps);
+            else {
+                launchPmeInterpolate(pa, ps);
+                if (pmeInterpolateFolds(pa)) h.pmeFoldedLaunches++;
+            }
             if (term == 0) tm.mark(8);
         }
     };
@@ -1484,6 +1489,7 @@ bool runOnce(snb_handle& h, const double* box, int flags, const double* hostPos,
     if (includeRecip && pmeFamily && h.rank == 0)      // spread (+ finish or fold), convolution, combine, interpolate
         for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++)
             launches += h.deterministic ? 5 : 4;
+    launches -= h.pmeFoldedLaunches;      // (one or two subsets: no k_pmeCombine launch)
     if (includeForces || h.comm) launches += 1+(h.comm && includeForces ? 1 : 0);
     if (posqDev || h.beginKernelUsed) launches += 1;     // position conversion, or k_begin (which includes it)
     h.countersOut[2] = launches;

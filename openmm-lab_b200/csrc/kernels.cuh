@@ -173,6 +173,7 @@ struct PmeArgs {
 void launchPmeEterm(const PmeArgs& a, cudaStream_t stream);
 void launchPmeSpread(const PmeArgs& a, cudaStream_t stream);
 void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
+bool pmeInterpolateFolds(const PmeArgs& a);   // the per-atom interpolation does the lambda combination itself (no k_pmeCombine launch)
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);
 // brick path (mixed precision, sorted atoms): shared-memory grid bricks moved by TMA
 bool makeBrickTensorMap(CUtensorMap* map, float* gridPad, int numAtoms, int numSubsets, int nx, int ny, int nzp);

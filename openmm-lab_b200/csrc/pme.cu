@@ -14,6 +14,8 @@
 // of the reference are folded onto the Hermitian half (weight 2 for 0 < kz < nz/2).
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 #include <algorithm>
 
 #define ORDER SNB_PME_ORDER
@@ -260,9 +262,13 @@ template <typename R> struct PmeAtomD {
     int idx[3];
     int subset, atom;   // subset -1: nothing to do
     R f[3];             // phase 2 result: sums over the stencil of (dtheta theta theta, ...) * phi
+    R lam[2];           // FOLD: lambda of the slices the atom's subset forms with subsets 0 and 1
 };
 
-template <typename R>
+// FOLD = 0: the grids were lambda-combined by k_pmeCombine; FOLD = 1 / 2 (one / two subsets): the combination is done here,
+// on the 125 points an atom reads (the same multiply-add sequence as k_pmeCombine: bit-identical potentials) -- the
+// combine pass over the whole grid and its launch drop out of the reciprocal-space chain.
+template <typename R, int FOLD>
 __global__ void __launch_bounds__(PME_THREADS) k_pmeInterpolate(PmeArgs a) {
     __shared__ PmeAtomD<R> sAtom[PME_ATOMS];
     if (threadIdx.x < PME_ATOMS) {
@@ -283,6 +289,11 @@ __global__ void __launch_bounds__(PME_THREADS) k_pmeInterpolate(PmeArgs a) {
                     me.q = q;
                     me.subset = __float_as_int(a.params4[atom].w);
                     me.atom = atom;
+                    if (FOLD) {
+                        const double* lambda = a.term == 0 ? a.sp->lambdaC : a.sp->lambdaV;
+                        me.lam[0] = (R) lambda[sliceOf(me.subset, 0)];
+                        me.lam[1] = FOLD > 1 ? (R) lambda[sliceOf(me.subset, 1)] : (R) 0;
+                    }
                 }
             }
         }
@@ -308,13 +319,31 @@ __global__ void __launch_bounds__(PME_THREADS) k_pmeInterpolate(PmeArgs a) {
             int y = at.idx[1]+iy, z = at.idx[2]+iz;
             y -= y >= a.ny ? a.ny : 0;
             z -= z >= a.nz ? a.nz : 0;
-            const R* __restrict__ cell = (const R*) a.grid+sub*G+(size_t) y*a.nz+z;
+            const R* __restrict__ cell = (const R*) a.grid+(FOLD ? 0 : sub*G)+(size_t) y*a.nz+z;
             R phi[ORDER];
+            if (FOLD) {
+                R v0[ORDER], v1[ORDER];
 #pragma unroll
-            for (int ix = 0; ix < ORDER; ix++) {
-                int x = at.idx[0]+ix;
-                x -= x >= a.nx ? a.nx : 0;
-                phi[ix] = __ldg(cell+x*plane);          // already lambda-combined for this subset (k_pmeCombine)
+                for (int ix = 0; ix < ORDER; ix++) {
+                    int x = at.idx[0]+ix;
+                    x -= x >= a.nx ? a.nx : 0;
+                    v0[ix] = __ldg(cell+x*plane);
+                    v1[ix] = FOLD > 1 ? __ldg(cell+G+x*plane) : (R) 0;
+                }
+#pragma unroll
+                for (int ix = 0; ix < ORDER; ix++) {
+                    phi[ix] = at.lam[0]*v0[ix];
+                    if (FOLD > 1)
+                        phi[ix] += at.lam[1]*v1[ix];
+                }
+            }
+            else {
+#pragma unroll
+                for (int ix = 0; ix < ORDER; ix++) {
+                    int x = at.idx[0]+ix;
+                    x -= x >= a.nx ? a.nx : 0;
+                    phi[ix] = __ldg(cell+x*plane);      // already lambda-combined for this subset (k_pmeCombine)
+                }
             }
             R s0 = 0, s1 = 0;               // sum_x theta_x * phi, sum_x dtheta_x * phi
 #pragma unroll
@@ -391,12 +420,29 @@ void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream) {
     if (a.doublePrecision) k_pmeConvolution<double><<<blocks, 256, 0, stream>>>(a);
     else k_pmeConvolution<float><<<blocks, 256, 0, stream>>>(a);
 }
+bool pmeInterpolateFolds(const PmeArgs& a) {
+    const char* env = getenv("SNB_PME_FOLD");       // (read at enqueue / capture time only)
+    return a.numSubsets <= 2 && !(env && atoi(env) == 0);
+}
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream) {
     const int blocks = (a.numAtoms+PME_ATOMS-1)/PME_ATOMS;
     const size_t G = (size_t) a.nx*a.ny*a.nz;
     const int cb = (int) std::min<size_t>((G+255)/256, 2368);
+    // one or two subsets: the lambda combination happens inside the interpolation (SNB_PME_FOLD=0: a pass of its own, as for
+    // more subsets)
+    if (pmeInterpolateFolds(a)) {
+        if (a.numSubsets == 1) {
+            if (a.doublePrecision) k_pmeInterpolate<double, 1><<<blocks, PME_THREADS, 0, stream>>>(a);
+            else k_pmeInterpolate<float, 1><<<blocks, PME_THREADS, 0, stream>>>(a);
+        }
+        else {
+            if (a.doublePrecision) k_pmeInterpolate<double, 2><<<blocks, PME_THREADS, 0, stream>>>(a);
+            else k_pmeInterpolate<float, 2><<<blocks, PME_THREADS, 0, stream>>>(a);
+        }
+        return;
+    }
     if (a.doublePrecision) k_pmeCombine<double><<<cb, 256, 0, stream>>>(a, G);
     else k_pmeCombine<float><<<cb, 256, 0, stream>>>(a, G);
-    if (a.doublePrecision) k_pmeInterpolate<double><<<blocks, PME_THREADS, 0, stream>>>(a);
-    else k_pmeInterpolate<float><<<blocks, PME_THREADS, 0, stream>>>(a);
+    if (a.doublePrecision) k_pmeInterpolate<double, 0><<<blocks, PME_THREADS, 0, stream>>>(a);
+    else k_pmeInterpolate<float, 0><<<blocks, PME_THREADS, 0, stream>>>(a);
 }

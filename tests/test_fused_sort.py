@@ -177,3 +177,26 @@ def test_compact_sort_matches_the_five_kernels(name):
     assert np.array_equal(out["1"][0], out["0"][0])
     assert np.array_equal(out["1"][3], out["0"][3])
     assert out["0"][2]-out["1"][2] == 2
+
+
+@pytest.mark.parametrize("name", ["water_pme", "fep_ljpme"])
+def test_interpolation_folds_the_lambda_combination(name):
+    """One or two subsets: k_pmeInterpolate combines the subsets' potential grids itself, on the points an atom reads
+    (no k_pmeCombine pass over the whole grid); SNB_PME_FOLD=0 keeps the pass.  Same potentials, same forces."""
+    w = WORKLOADS[name]()
+    n = w.num_particles
+    out = {}
+    for fold in ("1", "0"):
+        os.environ["SNB_PME_FOLD"] = fold
+        try:
+            ctx, kernel = _context(w, True, {"DeterministicForces": "true"})
+            for rep in range(3):
+                e, f, slices = _run(ctx, kernel, n, direct=False)
+            out[fold] = (e, f, slices, kernel.getCounters()[2])
+        finally:
+            del os.environ["SNB_PME_FOLD"]
+    terms = 2 if name == "fep_ljpme" else 1
+    assert out["0"][3]-out["1"][3] == terms
+    rms = np.sqrt((out["0"][1]**2).sum(axis=1).mean())
+    assert np.abs(out["1"][1]-out["0"][1]).max() <= 1e-6*rms
+    assert np.allclose(out["1"][2], out["0"][2], rtol=0, atol=1e-9*max(1.0, np.abs(out["0"][2]).max()))
