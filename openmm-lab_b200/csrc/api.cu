@@ -1068,7 +1068,8 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
         ba.forceOrig = h.forceOrig.p; ba.paddedAtoms = h.NP; ba.energyBuf = h.energyBuf.p;
         launchBonded(ba, bs);
     };
-    if (!h.timing && ((includeDirect && h.X > 0) || h.pmeEarly))
+    const bool inputsRecorded = !h.timing && ((includeDirect && h.X > 0) || h.pmeEarly || (includeRecip && pmeFamily && h.rank == 0));
+    if (inputsRecorded)
         CUDA_CHECK(cudaEventRecord(h.evInputs, st));
     auto forkBonded = [&](cudaEvent_t after) {
         CUDA_CHECK(cudaStreamWaitEvent(h.bondedStream, after, 0));
@@ -1096,6 +1097,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     if (!h.timing) CUDA_CHECK(cudaEventRecord(h.evSorted, st));
 
     // ---- reciprocal space (rank 0): its own stream, beside the tile list / direct-space kernels ----
+    bool gridsZeroed = false;       // the spreading grids were cleared ahead of the sort's end (below)
     auto reciprocal = [&](cudaStream_t ps) {
         Range recipRange("snb reciprocal space");
         if (h.method == SNB_EWALD) {
@@ -1120,7 +1122,7 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
             // atoms in sorted order + mixed precision: shared-memory bricks moved by TMA; else the per-atom kernels
             const bool bricks = g.brick && pa.sortedAtom != nullptr;
             static const bool noBrickInterp = getenv("SNB_NO_BRICK_INTERP") != nullptr;
-            launchPmeSpread(pa, ps);
+            launchPmeSpread(pa, ps, gridsZeroed);
             if (term == 0) tm.mark(5);
             if (h.doublePrecision) CUFFT_CHECK(cufftExecD2Z(g.fwd, (double*) g.real.p, (cufftDoubleComplex*) g.cplx.p));
             else CUFFT_CHECK(cufftExecR2C(g.fwd, (float*) g.real.p, (cufftComplex*) g.cplx.p));
@@ -1139,6 +1141,15 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     };
     const bool doRecip = includeRecip && ewaldFamily && h.rank == 0;
     if (doRecip && !h.timing) {
+        if (pmeFamily && !h.pmeEarly && inputsRecorded) {
+            // the grids are free since the previous evaluation: their memsets run beside the sort instead of behind it
+            CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.evInputs, 0));
+            for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
+                PmeArgs pa = pmeArgs(h, term, includeDirect);
+                launchPmeZero(pa, h.pmeStream);
+            }
+            gridsZeroed = true;
+        }
         CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.pmeEarly ? h.evInputs : h.evSorted, 0));
         if (nccl && !h.balanceFrozen) CUDA_CHECK(cudaEventRecord(h.evRecBegin, h.pmeStream));
         reciprocal(h.pmeStream);

@@ -171,7 +171,8 @@ struct PmeArgs {
     double* energyBuf;
 };
 void launchPmeEterm(const PmeArgs& a, cudaStream_t stream);
-void launchPmeSpread(const PmeArgs& a, cudaStream_t stream);
+void launchPmeZero(const PmeArgs& a, cudaStream_t stream);
+void launchPmeSpread(const PmeArgs& a, cudaStream_t stream, bool zeroed = false);
 void launchPmeConvolution(const PmeArgs& a, cudaStream_t stream);
 bool pmeInterpolateFolds(const PmeArgs& a);   // the per-atom interpolation does the lambda combination itself (no k_pmeCombine launch)
 void launchPmeInterpolate(const PmeArgs& a, cudaStream_t stream);

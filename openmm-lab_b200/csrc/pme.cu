@@ -393,11 +393,19 @@ void launchPmeEterm(const PmeArgs& a, cudaStream_t stream) {
     if (a.doublePrecision) k_pmeEterm<double><<<592, 256, 0, stream>>>(a, (double*) a.eterm);
     else k_pmeEterm<float><<<592, 256, 0, stream>>>(a, (float*) a.eterm);
 }
-void launchPmeSpread(const PmeArgs& a, cudaStream_t stream) {
+// the grid the spreading accumulates into, zeroed: part of launchPmeSpread, or issued ahead of it (beside the sort, which
+// the spreading waits for) with zeroed = true there
+void launchPmeZero(const PmeArgs& a, cudaStream_t stream) {
+    const size_t total = (size_t) a.numSubsets*a.nx*a.ny*a.nz;
+    if (a.gridFixed) cudaMemsetAsync(a.gridFixed, 0, sizeof(long long)*total, stream);
+    else cudaMemsetAsync(a.grid, 0, (a.doublePrecision ? 8 : 4)*total, stream);
+}
+void launchPmeSpread(const PmeArgs& a, cudaStream_t stream, bool zeroed) {
     const size_t total = (size_t) a.numSubsets*a.nx*a.ny*a.nz;
     const int blocks = (a.numAtoms+PME_ATOMS-1)/PME_ATOMS;
+    if (!zeroed)
+        launchPmeZero(a, stream);
     if (a.gridFixed) {
-        cudaMemsetAsync(a.gridFixed, 0, sizeof(long long)*total, stream);
         int fb = (int) std::min<size_t>((total+255)/256, 2368);
         if (a.doublePrecision) {
             k_pmeSpread<double, true><<<blocks, PME_THREADS, 0, stream>>>(a);
@@ -409,7 +417,6 @@ void launchPmeSpread(const PmeArgs& a, cudaStream_t stream) {
         }
     }
     else {
-        cudaMemsetAsync(a.grid, 0, (a.doublePrecision ? 8 : 4)*total, stream);
         if (a.doublePrecision) k_pmeSpread<double, false><<<blocks, PME_THREADS, 0, stream>>>(a);
         else k_pmeSpread<float, false><<<blocks, PME_THREADS, 0, stream>>>(a);
     }
