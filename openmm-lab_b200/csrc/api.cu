@@ -1141,7 +1141,15 @@ void enqueueStep(snb_handle& h, const StepInputs& in) {
     };
     const bool doRecip = includeRecip && ewaldFamily && h.rank == 0;
     if (doRecip && !h.timing) {
-        if (pmeFamily && !h.pmeEarly && inputsRecorded) {
+        static const bool earlyZeroOff = getenv("SNB_EARLY_GRID_ZERO") != nullptr && atoi(getenv("SNB_EARLY_GRID_ZERO")) == 0;
+        // (small grids only: at STMV size the 60 MB memset ahead of the sort's end lets the spreading start together with the
+        // list build, which then loses the SMs it needs first -- 3.01 vs 2.73 ms per evaluation, gpurun r3q)
+        size_t gridBytes = 0;
+        for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {
+            const PmeGrid& g = term == 0 ? h.pme : h.dpme;
+            gridBytes += (size_t) h.S*g.n[0]*g.n[1]*g.n[2]*(h.doublePrecision ? 8 : 4);
+        }
+        if (pmeFamily && !h.pmeEarly && inputsRecorded && !earlyZeroOff && gridBytes <= (size_t) 16<<20) {
             // the grids are free since the previous evaluation: their memsets run beside the sort instead of behind it
             CUDA_CHECK(cudaStreamWaitEvent(h.pmeStream, h.evInputs, 0));
             for (int term = 0; term < (h.method == SNB_LJPME ? 2 : 1); term++) {

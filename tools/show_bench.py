@@ -15,7 +15,7 @@ for f in sys.argv[1:]:
             s = d.get('stmv')
             if s:
                 print('  STMV value', round(s['value'], 2), 'ms', round(s['ms_per_step'], 3), 'dev', round(s['device_ms_per_step'], 3), 'e2e', round(s['e2e']['value'], 2),
-                      'frac', round(s['roofline']['frac'], 4), s['roofline']['interacting_pairs_all_ranks'])
+                      'frac', round(s['roofline']['frac'], 4), s['roofline'].get('interacting_pairs_all_ranks', s['roofline'].get('interacting_pairs')))
                 print('  phases', {k: round(v, 4) for k, v in s['phases_ms'].items()})
             if d.get('cpu_baseline'):
                 print('  cpu', d['cpu_baseline']['value'], d['cpu_baseline']['kind'])
