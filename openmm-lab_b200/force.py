@@ -42,6 +42,10 @@ class SlicedNonbondedForce:
     NoCutoff, CutoffNonPeriodic, CutoffPeriodic, Ewald, PME, LJPME = range(6)
 
     def __init__(self, numSubsets, template=None):
+        # both constructors of the reference (openmmapi/include/SlicedNonbondedForce.h:29-38, python/openmmlab.i:221-232):
+        # SlicedNonbondedForce(numSubsets) and SlicedNonbondedForce(force, numSubsets)
+        if not isinstance(numSubsets, (int, float)) and template is not None:
+            numSubsets, template = template, numSubsets
         self._numSubsets = int(numSubsets)
         self._method = self.NoCutoff
         self._cutoff = 1.0
@@ -294,6 +298,17 @@ class SlicedNonbondedForce:
             if sp in self._scalingParameterDerivatives:
                 raise OpenMMException("This scaling parameter derivative has already been requested")
             self._scalingParameterDerivatives[index] = sp
+
+    # python/openmmlab.i:471-479 (%extend): casting a Force of a System back to its class
+    @staticmethod
+    def cast(force):
+        if not isinstance(force, SlicedNonbondedForce):
+            raise TypeError("not a SlicedNonbondedForce")
+        return force
+
+    @staticmethod
+    def isinstance(force):
+        return isinstance(force, SlicedNonbondedForce)
 
     def getUseCudaFFT(self): return self._useCudaFFT
     def setUseCuFFT(self, use): self._useCudaFFT = bool(use)

@@ -222,3 +222,25 @@ def test_force_through_xml_evaluates_identically(platform, workload):
     assert np.array_equal(a["slices"], b["slices"])
     assert a["derivs"] == b["derivs"]
     assert np.array_equal(a["forces"], b["forces"])
+
+
+def test_python_surface_extras():
+    # python/openmmlab.i:221-232 (both constructors), :471-479 (%extend cast / isinstance)
+    base = F(1)
+    base.setNonbondedMethod(F.PME)
+    base.setCutoffDistance(0.9)
+    base.addParticle(0.5, 0.3, 0.1)
+    base.addParticle(-0.5, 0.3, 0.1)
+    base.addException(0, 1, 0.0, 1.0, 0.0)
+    base.addGlobalParameter("p", 1.0)
+    base.addParticleParameterOffset("p", 0, 0.1, 0.0, 0.0)
+    sliced = F(base, 2)                       # SlicedNonbondedForce(force, numSubsets)
+    assert sliced.getNumSubsets() == 2 and sliced.getNumSlices() == 3
+    assert sliced.getNonbondedMethod() == F.PME and sliced.getCutoffDistance() == 0.9
+    assert sliced.getNumParticles() == 2 and sliced.getNumExceptions() == 1
+    assert sliced.getParticleParameterOffset(0) == ("p", 0, 0.1, 0.0, 0.0)
+    assert F.isinstance(sliced) and not F.isinstance(object())
+    assert F.cast(sliced) is sliced
+    with pytest.raises(TypeError):
+        F.cast(object())
+    assert_same_force(sliced, XmlSerializer.deserialize(XmlSerializer.serialize(sliced)))
