@@ -1,17 +1,25 @@
-/* STAND-IN for openmm/Platform.h (compile check only). */
+/* STAND-IN for openmm/Platform.h: the registry a plugin's registerKernelFactories() works on (bodies in src/mock_openmm.cpp). */
 #ifndef MOCK_OPENMM_PLATFORM_H_
 #define MOCK_OPENMM_PLATFORM_H_
+#include <map>
 #include <string>
 namespace OpenMM {
 class KernelFactory;
+class KernelImpl;
+class ContextImpl;
 class Platform {
 public:
     virtual ~Platform() {}
     static int getNumPlatforms();
     static Platform& getPlatform(int index);
     static Platform& getPlatformByName(const std::string& name);
-    const std::string& getName() const;
+    static void registerPlatform(Platform* platform);
+    virtual const std::string& getName() const;
     void registerKernelFactory(const std::string& name, KernelFactory* factory);
+    /* (Platform::createKernel in OpenMM: looks the factory up by kernel name) */
+    KernelImpl* createKernelImpl(const std::string& name, ContextImpl& context) const;
+private:
+    std::map<std::string, KernelFactory*> factories;
 };
 }
 #endif

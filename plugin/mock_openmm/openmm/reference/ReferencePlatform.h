@@ -1,5 +1,5 @@
 /* STAND-IN for openmm/reference/ReferencePlatform.h: the PlatformData fields the kernels use
- * (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:35-58).  Compile check only. */
+ * (platforms/reference/src/ReferenceOpenMMLabKernels.cpp:35-58). */
 #ifndef MOCK_OPENMM_REFERENCEPLATFORM_H_
 #define MOCK_OPENMM_REFERENCEPLATFORM_H_
 #include "../Platform.h"
@@ -18,6 +18,10 @@ public:
         Vec3* periodicBoxVectors;
         std::map<std::string, double>* energyParameterDerivatives;
     };
+    const std::string& getName() const {
+        static const std::string name = "Reference";
+        return name;
+    }
 };
 }
 #endif

@@ -83,3 +83,18 @@ def test_openmm_plugin_adapter_compiles_against_reference_headers():
                    "B200CudaCalcSlicedNonbondedForceKernel::initialize", "B200CudaOpenMMLabKernelFactory::createKernelImpl",
                    "snb_execute_device_ordered", "snb_set_list_skin"):
         assert needed in syms
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/openmmapi/src/SlicedNonbondedForce.cpp"), reason="the reference's sources are not on this machine")
+@pytest.mark.parametrize("backend", ["ref", "port"])
+def test_openmm_plugin_adapter_links_and_runs(backend):
+    """plugin/Makefile run-check: the adapter, the reference's OWN openmmapi/src/SlicedNonbondedForce.cpp (compiled unchanged) and
+    the stand-in OpenMM linked into one program that registers the factory through the plugin's registerKernelFactories(),
+    creates the kernel by name and drives initialize / execute / copyParametersToContext / getPMEParameters against closed-form
+    answers -- with the CPU oracle behind the C-ABI here (the CUDA library takes its place in `make run-check-cuda`)."""
+    libdir, lib = ("../oracle/_ref", "libsnb_oracle_ref.so") if backend == "ref" else ("../oracle", "libsnb_oracle_port.so")
+    if not os.path.exists(os.path.join(ROOT, "plugin", libdir, lib)):
+        pytest.skip("%s is not built here" % lib)
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "plugin"), "-B", "run-check", "ORACLE_DIR="+libdir, "ORACLE_LIB="+lib],
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().splitlines()[-2].strip() == "OK", out.stdout[-2000:]+out.stderr[-2000:]
