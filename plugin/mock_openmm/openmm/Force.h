@@ -18,6 +18,7 @@ public:
     void setName(const std::string& newName) { name = newName; }
     virtual bool usesPeriodicBoundaryConditions() const { return false; }
 protected:
+    friend class Context;
     virtual ForceImpl* createImpl() const = 0;
     ForceImpl& getImplInContext(Context& context);
     const ForceImpl& getImplInContext(const Context& context) const;

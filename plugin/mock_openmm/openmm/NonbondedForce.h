@@ -4,7 +4,10 @@
 #define MOCK_OPENMM_NONBONDEDFORCE_H_
 #include "Force.h"
 #include "OpenMMException.h"
+#include <cmath>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 namespace OpenMM {
 class NonbondedForce : public Force {
@@ -84,8 +87,42 @@ public:
         const Offset& o = exceptionOffsets.at(index);
         parameter = o.parameter; exceptionIndex = o.index; chargeProdScale = o.q; sigmaScale = o.sigma; epsilonScale = o.epsilon;
     }
+    /* OpenMM's NonbondedForce::createExceptionsFromBonds: 1-2 and 1-3 pairs excluded, 1-4 pairs scaled */
+    void createExceptionsFromBonds(const std::vector<std::pair<int, int> >& bonds, double coulomb14Scale, double lj14Scale) {
+        const int n = getNumParticles();
+        std::vector<std::set<int> > bonded12(n);
+        for (size_t i = 0; i < bonds.size(); i++) {
+            bonded12[bonds[i].first].insert(bonds[i].second);
+            bonded12[bonds[i].second].insert(bonds[i].first);
+        }
+        for (int i = 0; i < n; i++) {
+            std::set<int> within2, within3;
+            for (std::set<int>::const_iterator j = bonded12[i].begin(); j != bonded12[i].end(); ++j) {
+                within2.insert(*j);
+                within2.insert(bonded12[*j].begin(), bonded12[*j].end());
+            }
+            within2.erase(i);
+            within3 = within2;
+            for (std::set<int>::const_iterator j = within2.begin(); j != within2.end(); ++j)
+                within3.insert(bonded12[*j].begin(), bonded12[*j].end());
+            within3.erase(i);
+            for (std::set<int>::const_iterator j = within3.begin(); j != within3.end(); ++j) {
+                if (*j >= i)
+                    continue;
+                if (within2.find(*j) != within2.end())
+                    addException(*j, i, 0.0, 1.0, 0.0);
+                else {
+                    const Particle& a = particles[*j];
+                    const Particle& b = particles[i];
+                    addException(*j, i, coulomb14Scale*a.q*b.q, 0.5*(a.sigma+b.sigma), lj14Scale*std::sqrt(a.epsilon*b.epsilon));
+                }
+            }
+        }
+    }
+    /* (plain NonbondedForce in a stand-in Context: evaluated as a one-subset SlicedNonbondedForce; src/mock_openmm.cpp) */
+    void updateParametersInContext(Context& context);
 protected:
-    ForceImpl* createImpl() const { return 0; }
+    ForceImpl* createImpl() const;
 private:
     struct Particle { double q, sigma, epsilon; Particle(double q, double s, double e) : q(q), sigma(s), epsilon(e) {} };
     struct Exception { int p1, p2; double q, sigma, epsilon; Exception(int a, int b, double q, double s, double e) : p1(a), p2(b), q(q), sigma(s), epsilon(e) {} };

@@ -1,9 +1,11 @@
-/* STAND-IN for openmm/Platform.h: the registry a plugin's registerKernelFactories() works on (bodies in src/mock_openmm.cpp). */
+/* STAND-IN for openmm/Platform.h: the registry a plugin's registerKernelFactories() works on and Platform::createKernel
+ * (bodies in src/mock_openmm.cpp). */
 #ifndef MOCK_OPENMM_PLATFORM_H_
 #define MOCK_OPENMM_PLATFORM_H_
 #include <map>
 #include <string>
 namespace OpenMM {
+class Kernel;
 class KernelFactory;
 class KernelImpl;
 class ContextImpl;
@@ -15,8 +17,9 @@ public:
     static Platform& getPlatformByName(const std::string& name);
     static void registerPlatform(Platform* platform);
     virtual const std::string& getName() const;
+    const std::string& getPropertyDefaultValue(const std::string& property) const;
     void registerKernelFactory(const std::string& name, KernelFactory* factory);
-    /* (Platform::createKernel in OpenMM: looks the factory up by kernel name) */
+    Kernel createKernel(const std::string& name, ContextImpl& context) const;
     KernelImpl* createKernelImpl(const std::string& name, ContextImpl& context) const;
 private:
     std::map<std::string, KernelFactory*> factories;

@@ -1,25 +1,34 @@
-/* STAND-IN for openmm/internal/ContextImpl.h: the three calls the kernels make on it (header-only). */
+/* STAND-IN for openmm/internal/ContextImpl.h: what kernels and ForceImpls call on it (header-only). */
 #ifndef MOCK_OPENMM_CONTEXTIMPL_H_
 #define MOCK_OPENMM_CONTEXTIMPL_H_
 #include "../OpenMMException.h"
+#include "../Platform.h"
 #include "../System.h"
 #include <map>
 #include <string>
 namespace OpenMM {
 class ContextImpl {
 public:
-    ContextImpl(const System& system, void* platformData) : system(system), platformData(platformData) {}
+    ContextImpl(const System& system, void* platformData, Platform* platform = 0) : system(system), platformData(platformData), platform(platform) {}
     void* getPlatformData() { return platformData; }
+    Platform& getPlatform() {
+        if (platform == 0)
+            throw OpenMMException("mock OpenMM: this ContextImpl has no Platform");
+        return *platform;
+    }
     double getParameter(std::string name) {
         if (parameters.find(name) == parameters.end())
             throw OpenMMException("Called getParameter() with invalid parameter name");
         return parameters[name];
     }
     void setParameter(std::string name, double value) { parameters[name] = value; }
+    const std::map<std::string, double>& getParameters() const { return parameters; }
     const System& getSystem() const { return system; }
+    void systemChanged() {}
 private:
     const System& system;
     void* platformData;
+    Platform* platform;
     std::map<std::string, double> parameters;
 };
 }
