@@ -244,3 +244,44 @@ def test_python_surface_extras():
     with pytest.raises(TypeError):
         F.cast(object())
     assert_same_force(sliced, XmlSerializer.deserialize(XmlSerializer.serialize(sliced)))
+
+
+HAVE_REFERENCE = os.path.isfile("/root/reference/serialization/src/SlicedNonbondedForceProxy.cpp")
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference's sources are not on this machine")
+def test_reference_proxy_and_its_own_test_on_the_stand_in_serializer(tmp_path):
+    """plugin/Makefile run-serialization-test: the reference's OWN proxy (serialization/src/SlicedNonbondedForceProxy.cpp), its
+    registration unit and its serialization test (serialization/tests/TestSerializeSlicedNonbondedForce.cpp), compiled unchanged,
+    on the stand-in XmlSerializer of plugin/mock_openmm -- and the cross-language check: what that proxy writes is, byte for byte,
+    what serialization.py writes; each side reads the other's documents."""
+    import subprocess
+    plugin = os.path.join(ROOT, "plugin")
+    out = subprocess.run(["make", "-C", plugin, "-B", "run-serialization-test"], capture_output=True, text=True)
+    assert out.returncode == 0 and "\nDone\n" in out.stdout, out.stdout[-2000:]+out.stderr[-2000:]
+    exe = os.path.join(plugin, "build", "xml_cross")
+    # C++ -> Python
+    written = str(tmp_path/"from_cpp.xml")
+    subprocess.run([exe, "write", written], check=True)
+    text = open(written).read()
+    assert text == FIXTURE == XmlSerializer.serialize(reference_test_force(), "Force")
+    assert_same_force(reference_test_force(), XmlSerializer.deserialize(text))
+    # Python -> C++ -> Python, on forces with awkward doubles: the FEP workload's force and random parameters
+    rng = np.random.default_rng(11)
+    forces = [systems.fep_ligand().force, systems.water_box().force]
+    odd = F(2)
+    for v in np.concatenate([rng.normal(size=40), 10.0**rng.uniform(-12, 12, size=40), [1e-5, 1e-6, 123456789.125, 1e15, 1e16, 1e17, 0.1, -0.0]]):
+        odd.addParticle(v, abs(v)+0.1, 0.5*abs(v))
+    odd.setParticleSubset(3, 1)
+    odd.addGlobalParameter("x", 1/3)
+    odd.addScalingParameter("x", 0, 1, True, False)
+    forces.append(odd)
+    for k, force in enumerate(forces):
+        mine = XmlSerializer.serialize(force)
+        src, dst = str(tmp_path/("py%d.xml" % k)), str(tmp_path/("cpp%d.xml" % k))
+        open(src, "w").write(mine)
+        done = subprocess.run([exe, "copy", src, dst], capture_output=True, text=True)
+        assert done.returncode == 0, done.stdout
+        theirs = open(dst).read()
+        assert_same_force(force, XmlSerializer.deserialize(theirs))
+        assert theirs == mine, "the two writers disagree on the bytes of force %d" % k
