@@ -3,7 +3,9 @@
 #ifndef MOCK_OPENMM_FORCE_H_
 #define MOCK_OPENMM_FORCE_H_
 #include <string>
+#ifndef OPENMM_EXPORT
 #define OPENMM_EXPORT
+#endif
 namespace OpenMM {
 class ForceImpl;
 class Context;

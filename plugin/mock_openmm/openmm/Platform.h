@@ -4,6 +4,9 @@
 #define MOCK_OPENMM_PLATFORM_H_
 #include <map>
 #include <string>
+#ifndef OPENMM_EXPORT
+#define OPENMM_EXPORT
+#endif
 namespace OpenMM {
 class Kernel;
 class KernelFactory;

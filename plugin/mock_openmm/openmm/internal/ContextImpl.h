@@ -25,11 +25,18 @@ public:
     const std::map<std::string, double>& getParameters() const { return parameters; }
     const System& getSystem() const { return system; }
     void systemChanged() {}
+    /* (what the reference's ExtendedCustomCVForce kernel, in the same source file as the nonbonded one, calls) */
+    void getPeriodicBoxVectors(Vec3& a, Vec3& b, Vec3& c) { a = box[0]; b = box[1]; c = box[2]; }
+    void setPeriodicBoxVectors(const Vec3& a, const Vec3& b, const Vec3& c) { box[0] = a; box[1] = b; box[2] = c; }
+    double getTime() const { return time; }
+    void setTime(double t) { time = t; }
 private:
     const System& system;
     void* platformData;
     Platform* platform;
     std::map<std::string, double> parameters;
+    Vec3 box[3];
+    double time = 0;
 };
 }
 #endif
