@@ -147,13 +147,13 @@ def test_oracle_kernel_glue_matches_the_reference_own_glue(backend):
     cannot compile without OpenMM); here the real glue, compiled unchanged on the stand-in OpenMM, and the oracle (through the
     plugin adapter) evaluate the same random systems -- three subsets, exceptions from bonds, scaling parameters with derivatives,
     particle and exception offsets, switching function, dispersion correction, separate reciprocal-space force group, new
-    parameter values, updateParametersInContext -- with all six methods: 43 380 numbers equal to 1e-9 of their scale (measured: 4e-14)."""
+    parameter values, updateParametersInContext -- with all six methods, also in a triclinic box: 61 455 numbers equal to 1e-9 of their scale (measured: 4e-14)."""
     libdir, lib = ("../oracle/_ref", "libsnb_oracle_ref.so") if backend == "ref" else ("../oracle", "libsnb_oracle_port.so")
     if not os.path.exists(os.path.join(ROOT, "plugin", libdir, lib)):
         pytest.skip("%s is not built here" % lib)
     out = subprocess.run(["make", "-C", os.path.join(ROOT, "plugin"), "-B", "run-diff-own-vs-oracle", "ORACLE_DIR="+libdir, "ORACLE_LIB="+lib],
                          capture_output=True, text=True)
-    assert out.returncode == 0 and "\nOK\n" in out.stdout and "43380 comparisons" in out.stdout, out.stdout[-2000:]+out.stderr[-2000:]
+    assert out.returncode == 0 and "\nOK\n" in out.stdout and "61455 comparisons" in out.stdout, out.stdout[-2000:]+out.stderr[-2000:]
 
 
 @pytest.mark.gpu
